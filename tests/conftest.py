@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box: pytest -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return GOLDEN
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """Build the native library and the C part of the oracle once per session if they are missing."""
+    import __graft_entry__ as ge
+
+    if not (os.path.exists(os.path.join(ROOT, "yolort_b200", "libyolort_b200.so"))
+            and os.path.exists(os.path.join(ROOT, "oracle", "libnms_ref.so"))):
+        ge.build()

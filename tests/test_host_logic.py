@@ -1,0 +1,145 @@
+"""CPU-only checks of the host side: C-ABI loads and exports every declared symbol, host geometry
+functions agree with the reference fixtures, module layout/state-dict keys equal the reference's, graph
+lowering emits the reference's algorithmic work.  No kernel is launched."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import parity_util as util
+from yolort_b200 import _C
+from yolort_b200.models import yolov5l, yolov5m, yolov5n, yolov5s, yolov5x, YOLOv5
+from yolort_b200.models._utils import depth_gain, make_divisible
+from yolort_b200.models.anchor_utils import AnchorGenerator
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _C.lib()
+    header = open(os.path.join(ROOT, "include", "yolort_b200.h")).read()
+    declared = set(re.findall(r"\b(yb_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_C.EXPORTED_SYMBOLS), declared ^ set(_C.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.yb_abi_version() == 1
+
+
+def test_ctypes_structs_match_header_sizes(tmp_path):
+    """The ctypes mirrors must have the C layout of include/yolort_b200.h (checked with the C compiler)."""
+    import subprocess
+
+    src = tmp_path / "sz.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "yolort_b200.h"\n'
+        'int main(void){printf("%zu %zu %zu %zu\\n", sizeof(yb_letterbox_geom), sizeof(yb_op_desc), '
+        'sizeof(yb_head_level), sizeof(yb_nms_params));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(_C.LetterboxGeom), ctypes.sizeof(_C.OpDesc), ctypes.sizeof(_C.HeadLevel),
+                     ctypes.sizeof(_C.NmsParams)]
+
+
+def test_letterbox_geometry_matches_reference(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "letterbox_geometry.json")))
+    sizes = [(h, w) for h, w, _, _ in g["sizes"]]
+    geoms, _ = _C.letterbox_geometry(sizes, 640.0, 640.0, 32, None)
+    for (h, w, nh, nw), gg in zip(g["sizes"], geoms):
+        assert (gg.new_h, gg.new_w) == (nh, nw), (h, w)
+        assert gg.ratio_h == np.float32(h) / np.float32(nh) and gg.ratio_w == np.float32(w) / np.float32(nw)
+    for b in g["batches"]:
+        sz = [sizes[i] for i in b["idx"]]
+        geoms, (Hb, Wb) = _C.letterbox_geometry(sz, 640.0, 640.0, 32, None)
+        assert (Hb, Wb) == (b["Hb"], b["Wb"])
+        assert [(gg.top, gg.left) for gg in geoms] == [tuple(o) for o in b["offsets"]]
+        probe = np.array([[10.0, 20.0, 300.5, 400.25], [0.0, 0.0, Wb, Hb]], dtype=np.float32)
+        for (h, w), ref in zip(sz, b["scaled"]):
+            gain, px, py = (np.float32(v) for v in _C.scale_coords_params(Hb, Wb, h, w))
+            got = probe.copy()
+            got[:, 0::2] = (got[:, 0::2] - px) / gain
+            got[:, 1::2] = (got[:, 1::2] - py) / gain
+            assert np.array_equal(got, np.array(ref, dtype=np.float32))
+
+
+def test_letterbox_geometry_fixed_shape_and_errors():
+    geoms, hw = _C.letterbox_geometry([(480, 640)], 640.0, 640.0, 32, (672, 672))
+    assert hw == (672, 672) and (geoms[0].new_h, geoms[0].new_w) == (480, 640)
+    assert (geoms[0].top, geoms[0].left) == (96, 16)
+    with pytest.raises(_C.NativeLibraryError):
+        _C.letterbox_geometry([(480, 640)], 640.0, 640.0, 32, (320, 320))
+
+
+def test_make_divisible_known_answers():
+    # yolort test/test_models_utils.py:16-37
+    assert make_divisible(16.0, 8) == 16
+    assert make_divisible(17.0, 8) == 16
+    assert make_divisible(1.0, 8, min_value=8) == 8
+    assert make_divisible(1.0, 8, min_value=16) == 16
+    assert make_divisible(20.0, 16) >= 0.9 * 20.0
+    assert make_divisible(256.0, 8) == 256
+    assert [depth_gain(n, 0.33) for n in (3, 6, 9)] == [1, 2, 3]
+    assert [depth_gain(n, 1.33) for n in (3, 6, 9)] == [4, 8, 12]
+
+
+def test_anchor_generator_golden():
+    # yolort test/test_models_anchor_utils.py:14-30
+    grids, shifts = AnchorGenerator([4], [[6, 14]])([torch.rand(2, 8, 2, 2)])
+    assert tuple(grids[0].shape) == (1, 1, 2, 2, 2)
+    torch.testing.assert_close(grids[0], torch.tensor([[[[[0.0, 0.0], [1.0, 0.0]], [[0.0, 1.0], [1.0, 1.0]]]]]))
+    torch.testing.assert_close(shifts[0], torch.tensor([[[[[6.0, 14.0], [6.0, 14.0]], [[6.0, 14.0], [6.0, 14.0]]]]]))
+
+
+@pytest.mark.parametrize("name,ctor", [("n", yolov5n), ("s", yolov5s), ("m", yolov5m), ("l", yolov5l), ("x", yolov5x)])
+def test_state_dict_layout_equals_reference(name, ctor):
+    ref = util.layouts()[name]
+    sd = ctor().state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    assert {k: list(v.shape) for k, v in sd.items()} == ref
+    m = ctor()
+    m.load_state_dict(util.synth_state_dict(ref))  # a reference-layout state dict loads unchanged
+
+
+def test_constructor_surface_and_errors():
+    m = YOLOv5(arch="yolov5_darknet_pan_s_r60", score_thresh=0.3, nms_thresh=0.5, detections_per_img=100,
+               size=(320, 416), size_divisible=64, fill_color=0)
+    pp = m.model.post_process
+    assert (pp.score_thresh, pp.nms_thresh, pp.detections_per_img) == (0.3, 0.5, 100)
+    assert (m.transform.min_size, m.transform.max_size, m.transform.size_divisible, m.transform.fill_color) == (320, 416, 64, 0.0)
+    assert yolov5s().model.post_process.score_thresh == 0.005  # yolo.py:77-79 defaults
+    with pytest.raises(NotImplementedError):
+        yolov5s(upstream_version="r4.0")
+    with pytest.raises(ValueError):
+        YOLOv5(arch="nope")
+    with pytest.raises(NotImplementedError):
+        m.collate_images(123, None)
+
+
+def test_no_cpu_fallback():
+    m = yolov5n().eval()
+    with pytest.raises(_C.NativeLibraryError):
+        m([torch.rand(3, 64, 64)])            # CPU tensors: must fail loudly, never compute on the host
+    with pytest.raises(RuntimeError):
+        m.model.backbone.body["0"](torch.rand(1, 3, 64, 64))
+    assert m.training is False
+    with pytest.raises(NotImplementedError):
+        yolov5n().train()([torch.rand(3, 64, 64)])
+
+
+@pytest.mark.parametrize("name,ctor,gflop,n_convs", [("n", yolov5n, 4.468, 60), ("s", yolov5s, 16.434, 60), ("m", yolov5m, 48.872, 82)])
+def test_lowering_carries_the_reference_work(name, ctor, gflop, n_convs):
+    """conv counts and GFLOP/image at 640x640 measured on the reference modules."""
+    from yolort_b200.engine import lower_yolo
+
+    L, x0, heads, _ = lower_yolo(ctor().model, torch.float16, torch.device("cpu"))
+    convs = [op for op in L.ops if op.kind == _C.YB_OP_CONV]
+    n_c3 = sum(1 for op in convs if op.name.endswith("cv1+cv2"))
+    assert len(convs) + n_c3 == n_convs          # each fused cv1||cv2 launch covers two reference convs
+    total = sum(op.flops_per_pixel * (640 // op.dst.buf.div) ** 2 for op in convs)
+    assert total / 1e9 == pytest.approx(gflop, rel=2e-3)
+    assert sum(1 for op in L.ops if op.kind == _C.YB_OP_UPSAMPLE2X) == 2
+    assert sum(1 for op in L.ops if op.kind == _C.YB_OP_SPP_POOL) == 1

@@ -1,0 +1,426 @@
+// Conv2d(+folded BN)+SiLU(+residual) as an implicit GEMM on the 5th-gen tensor cores.
+//
+//   D[m, co] = sum_{r,s,ci} X[n, ho*stride - pad + r, wo*stride - pad + s, ci] * W[co, r, s, ci]
+//   m = (n*Ho + ho)*Wo + wo      (NHWC activations, K-major weights)
+//
+// Replaces the arithmetic of yolort/v5/models/common.py:42-73 (Conv = conv2d -> BN(eps 1e-3) -> SiLU),
+// :94-116 (Bottleneck residual) and the 1x1 head convs of yolort/models/box_head.py:35-37,68-82.
+//
+// One CTA computes a 128 x block_n output tile:
+//   warp 0   : TMA producer.  A tiles come from a 4-D im2col tensor map (the TMA engine walks 128
+//              output pixels and applies padding/stride, zero-filling the halo) or, for 1x1/s1
+//              convs, from a plain 2-D tiled map; B tiles (weights) from a 2-D tiled map.  Both land
+//              in shared memory in the 32/64/128-byte swizzled K-major layout UMMA expects.
+//   warp 1   : allocates TMEM and issues tcgen05.mma (M=128, N=block_n, K=16) from one thread,
+//              accumulating in TMEM; tcgen05.commit releases smem stages / signals the epilogue.
+//   warps 2-5: epilogue.  tcgen05.ld the fp32 accumulator (one output pixel per thread), add bias,
+//              SiLU, optional residual, convert to fp16/bf16 and store 32-byte runs into the NHWC
+//              destination slice (which may be a channel window of a concat buffer).
+#include "common.cuh"
+#include "conv_sm100.h"
+
+namespace yb {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;
+
+struct ConvKernelParams {
+  int M, Cout, block_n, block_k;
+  int ksize, chunks, num_k_iters;
+  int mode;  // 0: 2-D tiled rows (1x1 stride 1), 1: 4-D im2col
+  int HoWo, Wo, stride, pad;
+  int stages;
+  uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, idesc;
+  int act, is_bf16;
+  void* out;
+  int out_cstride;
+  const float* bias;
+  const void* residual;
+  int res_cstride;
+};
+
+__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+template <bool kBf16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (kBf16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+template <bool kBf16>
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+  if constexpr (kBf16) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  } else {
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
+  }
+}
+
+template <bool kBf16>
+__device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const uint32_t (&acc)[16],
+                                               long long row, int col) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    v[j] = __uint_as_float(acc[j]) + __ldg(p.bias + col + j);
+    if (p.act == YB_ACT_SILU) v[j] = silu(v[j]);
+  }
+  if (p.residual != nullptr) {
+    const uint4* r = reinterpret_cast<const uint4*>(
+        reinterpret_cast<const uint16_t*>(p.residual) + row * p.res_cstride + col);
+    uint4 r0 = __ldg(r), r1 = __ldg(r + 1);
+    const uint32_t ru[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float2 f = unpack2<kBf16>(ru[j]);
+      v[2 * j] += f.x;
+      v[2 * j + 1] += f.y;
+    }
+  }
+  uint4 o0, o1;
+  o0.x = pack2<kBf16>(v[0], v[1]);
+  o0.y = pack2<kBf16>(v[2], v[3]);
+  o0.z = pack2<kBf16>(v[4], v[5]);
+  o0.w = pack2<kBf16>(v[6], v[7]);
+  o1.x = pack2<kBf16>(v[8], v[9]);
+  o1.y = pack2<kBf16>(v[10], v[11]);
+  o1.z = pack2<kBf16>(v[12], v[13]);
+  o1.w = pack2<kBf16>(v[14], v[15]);
+  uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + row * p.out_cstride + col;
+  const int rem = p.Cout - col;  // Cout is a multiple of 8
+  if (rem >= 16) {
+    reinterpret_cast<uint4*>(dst)[0] = o0;
+    reinterpret_cast<uint4*>(dst)[1] = o1;
+  } else if (rem >= 8) {
+    reinterpret_cast<uint4*>(dst)[0] = o0;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                 const __grid_constant__ CUtensorMap tmap_b, const ConvKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  // Swizzled operand tiles need 1024-byte alignment.
+  uint8_t* tiles = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBlockM;
+  const int n0 = blockIdx.y * p.block_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&accum_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(&tmem_base_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int cw = 0, ch = 0, cn = 0;
+      if (p.mode == 1) {
+        cn = m0 / p.HoWo;
+        const int rem = m0 - cn * p.HoWo;
+        const int ho = rem / p.Wo;
+        const int wo = rem - ho * p.Wo;
+        ch = ho * p.stride - p.pad;
+        cw = wo * p.stride - p.pad;
+      }
+      const uint32_t tx_bytes = kBlockM * p.block_k * 2 + p.block_n * p.block_k * 2;
+      for (int it = 0; it < p.num_k_iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* a_dst = tiles + s * stage_bytes;
+        uint8_t* b_dst = a_dst + p.a_stage_bytes;
+        mbar_expect_tx(&full_bar[s], tx_bytes);
+        const int tap = it / p.chunks;
+        const int chunk = it - tap * p.chunks;
+        if (p.mode == 0) {
+          tma_load_2d(&tmap_a, &full_bar[s], a_dst, chunk * p.block_k, m0);
+        } else {
+          const int r = tap / p.ksize;
+          const int sx = tap - r * p.ksize;
+          tma_load_im2col_4d(&tmap_a, &full_bar[s], a_dst, chunk * p.block_k, cw, ch, cn,
+                             static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+        }
+        tma_load_2d(&tmap_b, &full_bar[s], b_dst, it * p.block_k, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t row_bytes = p.block_k * 2;
+      for (int it = 0; it < p.num_k_iters; ++it) {
+        const int s = it % p.stages;
+        const uint32_t ph = (it / p.stages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(tiles + s * stage_bytes);
+        const uint32_t b_addr = a_addr + p.a_stage_bytes;
+        const int kk = p.block_k >> 4;
+        for (int k = 0; k < kk; ++k) {
+          const uint64_t da = make_kmajor_desc(a_addr + k * 32, row_bytes);
+          const uint64_t db = make_kmajor_desc(b_addr + k * 32, row_bytes);
+          umma_f16(tmem_base, da, db, p.idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+      }
+      umma_commit(&accum_bar);  // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    mbar_wait(&accum_bar, 0);
+    tc_fence_after();
+    const long long row = static_cast<long long>(m0) + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (int c = 0; c < p.block_n; c += 16) {
+      uint32_t acc[16];
+      tmem_ld_32x32b_x16(taddr + c, acc);
+      tmem_ld_wait();
+      const int col = n0 + c;
+      if (row_ok && col < p.Cout) {
+        if (p.is_bf16)
+          epilogue_chunk<true>(p, acc, row, col);
+        else
+          epilogue_chunk<false>(p, acc, row, col);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                   cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+
+int load_driver_entry_points() {
+  if (g_encode_tiled && g_encode_im2col) return YB_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  YB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  YB_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess,
+             "cuTensorMapEncodeTiled not available from the driver");
+  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  fn = nullptr;
+  YB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres));
+  YB_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess,
+             "cuTensorMapEncodeIm2col not available from the driver");
+  g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+  return YB_OK;
+}
+
+CUtensorMapSwizzle swizzle_for(int block_k) {
+  return block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                       : (block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+uint32_t pow2_cols(int n) {
+  uint32_t c = 32;
+  while (static_cast<int>(c) < n) c <<= 1;
+  return c;
+}
+
+}  // namespace
+
+struct ConvOp {
+  CUtensorMap tmap_a, tmap_b;
+  ConvKernelParams kp;
+  dim3 grid;
+  size_t smem_bytes;
+};
+
+int conv_op_create(const yb_op_desc& d, ConvOp** out) {
+  int rc = load_driver_entry_points();
+  if (rc != YB_OK) return rc;
+  YB_REQUIRE(d.dtype == YB_F16 || d.dtype == YB_BF16, "conv: dtype must be f16 or bf16");
+  YB_REQUIRE(d.ksize >= 1 && d.ksize <= 7 && d.stride >= 1 && d.stride <= 2, "conv: ksize/stride");
+  YB_REQUIRE(d.Cin % 8 == 0 && d.in_cstride % 8 == 0 && d.in_cstride >= d.Cin,
+             "conv: Cin/in_cstride must be multiples of 8 (16-byte TMA granularity), got %d/%d", d.Cin,
+             d.in_cstride);
+  YB_REQUIRE(d.Cout % 8 == 0 && d.out_cstride % 8 == 0 && d.out_cstride >= d.Cout,
+             "conv: Cout/out_cstride must be multiples of 8, got %d/%d", d.Cout, d.out_cstride);
+  YB_REQUIRE(d.Cin_pad % 16 == 0 && d.Cin_pad >= d.Cin, "conv: Cin_pad must be a multiple of 16");
+  YB_REQUIRE(d.Cout_pad % 16 == 0 && d.Cout_pad >= d.Cout, "conv: Cout_pad must be a multiple of 16");
+  YB_REQUIRE((reinterpret_cast<uintptr_t>(d.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.out) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(d.weight) & 15) == 0,
+             "conv: tensors must be 16-byte aligned");
+  YB_REQUIRE(d.residual == nullptr ||
+                 ((reinterpret_cast<uintptr_t>(d.residual) & 15) == 0 && d.res_cstride % 8 == 0),
+             "conv: residual alignment");
+  const int Ho = (d.H + 2 * d.pad - d.ksize) / d.stride + 1;
+  const int Wo = (d.W + 2 * d.pad - d.ksize) / d.stride + 1;
+  YB_REQUIRE(Ho == d.Ho && Wo == d.Wo, "conv: output extent mismatch (%d,%d) vs (%d,%d)", Ho, Wo, d.Ho,
+             d.Wo);
+  const long long M_ll = static_cast<long long>(d.N) * Ho * Wo;
+  YB_REQUIRE(M_ll > 0 && M_ll < (1ll << 31), "conv: M out of range");
+
+  ConvOp* op = new ConvOp();
+  ConvKernelParams& kp = op->kp;
+  kp.M = static_cast<int>(M_ll);
+  kp.Cout = d.Cout;
+  const int n_tiles = (d.Cout + 255) / 256;
+  kp.block_n = (((d.Cout + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
+  kp.block_k = (d.Cin_pad % 64 == 0) ? 64 : ((d.Cin_pad % 32 == 0) ? 32 : 16);
+  kp.ksize = d.ksize;
+  kp.chunks = d.Cin_pad / kp.block_k;
+  kp.num_k_iters = d.ksize * d.ksize * kp.chunks;
+  kp.mode = (d.ksize == 1 && d.stride == 1 && d.pad == 0) ? 0 : 1;
+  kp.HoWo = Ho * Wo;
+  kp.Wo = Wo;
+  kp.stride = d.stride;
+  kp.pad = d.pad;
+  kp.a_stage_bytes = kBlockM * kp.block_k * 2;
+  kp.b_stage_bytes = (static_cast<uint32_t>(kp.block_n * kp.block_k * 2) + 1023u) & ~1023u;
+  const uint32_t stage_bytes = kp.a_stage_bytes + kp.b_stage_bytes;
+  // Two CTAs per SM when four stages fit in ~100 KB (their epilogues overlap each other's
+  // main loops); otherwise one CTA with as many stages as fit.
+  int stages;
+  if (stage_bytes * 4 <= 100 * 1024) {
+    stages = static_cast<int>((100 * 1024) / stage_bytes);
+  } else {
+    stages = static_cast<int>((200 * 1024) / stage_bytes);
+  }
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages > kp.num_k_iters) stages = kp.num_k_iters;
+  if (stages < 1) stages = 1;
+  kp.stages = stages;
+  kp.tmem_cols = pow2_cols(kp.block_n);
+  kp.is_bf16 = d.dtype == YB_BF16;
+  const uint32_t fmt = kp.is_bf16 ? 1u : 0u;
+  kp.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(kp.block_n >> 3) << 17) |
+             (static_cast<uint32_t>(kBlockM >> 4) << 24);
+  kp.act = d.act;
+  kp.out = d.out;
+  kp.out_cstride = d.out_cstride;
+  kp.bias = d.bias;
+  kp.residual = d.residual;
+  kp.res_cstride = d.res_cstride;
+  op->grid = dim3((kp.M + kBlockM - 1) / kBlockM, n_tiles, 1);
+  op->smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024;
+
+  const CUtensorMapDataType dt =
+      kp.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = swizzle_for(kp.block_k);
+  CUresult cr;
+  if (kp.mode == 0) {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.Cin), static_cast<cuuint64_t>(kp.M)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.in_cstride) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kp.block_k), kBlockM};
+    cuuint32_t estr[2] = {1, 1};
+    cr = g_encode_tiled(&op->tmap_a, dt, 2, const_cast<void*>(d.in), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(d.Cin), static_cast<cuuint64_t>(d.W),
+                          static_cast<cuuint64_t>(d.H), static_cast<cuuint64_t>(d.N)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(d.in_cstride) * 2,
+                             static_cast<cuuint64_t>(d.in_cstride) * 2 * d.W,
+                             static_cast<cuuint64_t>(d.in_cstride) * 2 * d.W * d.H};
+    int lower[2] = {-d.pad, -d.pad};
+    int upper[2] = {d.pad - (d.ksize - 1), d.pad - (d.ksize - 1)};
+    cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(d.stride), static_cast<cuuint32_t>(d.stride), 1};
+    cr = g_encode_im2col(&op->tmap_a, dt, 4, const_cast<void*>(d.in), dims, strides, lower, upper,
+                         static_cast<cuuint32_t>(kp.block_k), kBlockM, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // Driver workaround also applied by CUTLASS (copy_traits_sm90_im2col.hpp): for tensors smaller
+    // than 128 KiB, drivers <= 13.1 set a descriptor bit that makes im2col loads fault.
+    int drv = 0;
+    cudaDriverGetVersion(&drv);
+    const size_t span = static_cast<size_t>(d.in_cstride) * 2 * d.W * d.H * d.N;
+    if (cr == CUDA_SUCCESS && drv <= 13010 && span < 131072) {
+      reinterpret_cast<uint64_t*>(&op->tmap_a)[1] &= ~(1ull << 21);
+    }
+  }
+  if (cr != CUDA_SUCCESS) {
+    set_error("conv: cuTensorMapEncode (A, mode %d) failed with CUresult %d (Cin=%d cs=%d H=%d W=%d N=%d k=%d s=%d bk=%d)",
+              kp.mode, static_cast<int>(cr), d.Cin, d.in_cstride, d.H, d.W, d.N, d.ksize, d.stride,
+              kp.block_k);
+    delete op;
+    return YB_ERR_CUDA;
+  }
+  {
+    const int ktot = d.ksize * d.ksize * d.Cin_pad;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(d.Cout_pad)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ktot) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kp.block_k), static_cast<cuuint32_t>(kp.block_n)};
+    cuuint32_t estr[2] = {1, 1};
+    cr = g_encode_tiled(&op->tmap_b, dt, 2, const_cast<void*>(d.weight), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_error("conv: cuTensorMapEncodeTiled (weights) failed with CUresult %d", static_cast<int>(cr));
+      delete op;
+      return YB_ERR_CUDA;
+    }
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         220 * 1024);
+    if (e != cudaSuccess) {
+      set_error("conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      delete op;
+      return YB_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  *out = op;
+  return YB_OK;
+}
+
+int conv_op_launch(const ConvOp* op, cudaStream_t stream) {
+  conv_umma_kernel<<<op->grid, kThreads, op->smem_bytes, stream>>>(op->tmap_a, op->tmap_b, op->kp);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+void conv_op_destroy(ConvOp* op) { delete op; }
+
+}  // namespace yb

@@ -1,0 +1,635 @@
+// Post-processing: anchor decode + multi-label threshold + batched NMS + top-k + box rescale.
+//
+// Replaces PostProcess.forward (yolort/models/box_head.py:388-429):
+//   _concat_pred_logits  :328-348  sigmoid, det_utils.decode_single (_utils.py:43-62)
+//   _decode_pred_logits  :351-360  scores = cls * obj ; box_convert(cxcywh -> xyxy)
+//   torch.where(scores > thr) :418 row-major (anchor, class) candidates -- multi-label
+//   torchvision.ops.batched_nms :422 (coordinate-offset trick or per-class, by numel) ; keep[:max_det]
+// and YOLOTransform.postprocess / scale_coords (yolort/models/transform.py:332-367).
+//
+// Two kernels per batch, no host round trip:
+//   1. decode_candidates_kernel -- one thread per anchor.  Reads the objectness logit first; an anchor
+//      whose sigmoid(obj) <= thr cannot produce a candidate (cls < 1), so most threads touch one 32-byte
+//      sector.  Survivors decode the box once (fp32, unfused ops in the reference's order), write it to a
+//      dense per-anchor array and append one 64-bit sort key per (anchor, class) over threshold:
+//          key = ~orderable(score) << 32 | (anchor * nc + class)
+//      so ascending key order == score descending, ties in row-major candidate order (what a stable
+//      sort of the reference's candidate list gives).
+//   2. nms_image_kernel -- one 1024-thread CTA per image: sorts the image's keys (bitonic network in
+//      shared memory up to 4096 keys, in-CTA LSD radix sort through global memory above that), then the
+//      greedy sweep: candidates are consumed 1024 at a time; each thread tests its candidate against the
+//      kept list (<= max_det boxes in shared memory), then survivors are resolved in order with warp
+//      ballots.  The sweep stops at max_det keeps, exactly like keep[:detections_per_img].
+// IoU arithmetic mirrors torchvision's CPU nms kernel in fp32 with explicit non-fused operations so the
+// keep set is bit-identical on identical inputs.
+#include "common.cuh"
+
+namespace yb {
+namespace {
+
+constexpr int kNmsThreads = 1024;
+constexpr int kSmallSort = 4096;  // keys sorted in shared memory
+
+__device__ __forceinline__ uint32_t orderable_desc(float f) {
+  uint32_t u = __float_as_uint(f);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending order of floats
+  return ~u;                                       // descending
+}
+__device__ __forceinline__ float from_orderable_desc(uint32_t k) {
+  uint32_t u = ~k;
+  u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ int float_to_ordered_int(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7FFFFFFF;
+}
+__device__ __forceinline__ float ordered_int_to_float(int i) {
+  return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF);
+}
+
+__device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+
+template <typename T>
+__device__ __forceinline__ float ld_logit(const void* base, long long off);
+template <>
+__device__ __forceinline__ float ld_logit<float>(const void* base, long long off) {
+  return __ldg(static_cast<const float*>(base) + off);
+}
+template <>
+__device__ __forceinline__ float ld_logit<__half>(const void* base, long long off) {
+  return __half2float(__ldg(static_cast<const __half*>(base) + off));
+}
+template <>
+__device__ __forceinline__ float ld_logit<__nv_bfloat16>(const void* base, long long off) {
+  return __bfloat162float(static_cast<const __nv_bfloat16*>(base)[off]);
+}
+
+struct DecodeParams {
+  yb_head_level lvl[YB_MAX_LEVELS];
+  int lvl_start[YB_MAX_LEVELS + 1];  // first flat anchor index of each level
+  int n_images, n_levels, n_anchors, n_classes;
+  int anchors_per_image;
+  float score_thresh;
+  long long cap_per_image;
+};
+
+// workspace carve-up (device)
+struct Workspace {
+  uint64_t* keys_a;    // [n][cap]
+  uint64_t* keys_b;    // [n][cap]
+  float4* boxes;       // [n][anchors_per_image]
+  int* img_count;      // [n]
+  int* img_maxc;       // [n] ordered-int max coordinate over candidate boxes
+  long long* status;   // [4] scratch status block (used when the caller passes none)
+};
+
+template <typename T>
+__global__ void decode_candidates_kernel(const __grid_constant__ DecodeParams p, Workspace ws) {
+  const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(p.n_images) * p.anchors_per_image;
+  if (gid >= total) return;
+  const int img = static_cast<int>(gid / p.anchors_per_image);
+  const int anchor = static_cast<int>(gid - static_cast<long long>(img) * p.anchors_per_image);
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < YB_MAX_LEVELS; ++i)
+    if (i < p.n_levels && anchor >= p.lvl_start[i]) l = i;
+  const yb_head_level& L = p.lvl[l];
+  int r = anchor - p.lvl_start[l];
+  const int x = r % L.W;
+  r /= L.W;
+  const int y = r % L.H;
+  const int a = r / L.H;
+  const long long off = img * L.stride_n + a * L.stride_a + y * L.stride_y + x * L.stride_x;
+
+  const float obj = sigmoidf_ref(ld_logit<T>(L.logits, off + 4));
+  if (!(obj > p.score_thresh)) return;  // score = cls*obj <= obj
+
+  bool have_box = false;
+  for (int k = 0; k < p.n_classes; ++k) {
+    const float cls = sigmoidf_ref(ld_logit<T>(L.logits, off + 5 + k));
+    const float score = __fmul_rn(cls, obj);
+    if (!(score > p.score_thresh)) continue;
+    if (!have_box) {
+      have_box = true;
+      const float sx = sigmoidf_ref(ld_logit<T>(L.logits, off + 0));
+      const float sy = sigmoidf_ref(ld_logit<T>(L.logits, off + 1));
+      const float sw = sigmoidf_ref(ld_logit<T>(L.logits, off + 2));
+      const float sh = sigmoidf_ref(ld_logit<T>(L.logits, off + 3));
+      // _utils.py:59-60 in the reference's op order: (y*2 - 0.5 + grid) * stride ; (y*2)**2 * anchor
+      const float cx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.0f), 0.5f), static_cast<float>(x)), L.stride_px);
+      const float cy = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.0f), 0.5f), static_cast<float>(y)), L.stride_px);
+      const float tw = __fmul_rn(sw, 2.0f), th = __fmul_rn(sh, 2.0f);
+      const float w = __fmul_rn(__fmul_rn(tw, tw), L.anchors_px[2 * a]);
+      const float h = __fmul_rn(__fmul_rn(th, th), L.anchors_px[2 * a + 1]);
+      // torchvision box_convert cxcywh -> xyxy
+      const float hw = __fmul_rn(0.5f, w), hh = __fmul_rn(0.5f, h);
+      const float4 b = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+      ws.boxes[static_cast<long long>(img) * p.anchors_per_image + anchor] = b;
+      const float m = fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w));
+      atomicMax(&ws.img_maxc[img], float_to_ordered_int(m));
+    }
+    const int slot = atomicAdd(&ws.img_count[img], 1);
+    if (slot < p.cap_per_image) {
+      const uint64_t key = (static_cast<uint64_t>(orderable_desc(score)) << 32) |
+                           static_cast<uint32_t>(anchor * p.n_classes + k);
+      ws.keys_a[static_cast<long long>(img) * p.cap_per_image + slot] = key;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-image sort + greedy sweep
+// ---------------------------------------------------------------------------------------------
+struct NmsParams {
+  int n_classes;        // decode mode: label = idx % nc, anchor = idx / nc ; explicit mode: 0
+  int anchors_per_image;
+  long long cap_per_image;
+  float iou_thresh;
+  int max_det;
+  int semantics;
+  int explicit_mode;    // 1: yb_batched_nms (boxes/labels indexed by candidate index)
+  const float4* x_boxes;     // explicit mode
+  const int64_t* x_labels;   // explicit mode
+  const float* rescale;      // [n][3] or null
+  float* out_boxes;          // [n][max_det][4]
+  float* out_scores;         // [n][max_det]
+  int64_t* out_labels;       // [n][max_det]
+  int64_t* out_keep;         // explicit mode: [max_det]
+  int* out_counts;           // [n]
+  long long* status;         // [4]
+};
+
+__device__ __forceinline__ float box_area(const float4& b) {
+  return __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+}
+// torchvision/csrc/ops/cpu/nms_kernel.cpp: inter / (iarea + areas[j] - inter) > thr
+__device__ __forceinline__ bool iou_over(const float4& a, float area_a, const float4& b, float area_b, float thr) {
+  const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+  const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  const float w = fmaxf(0.f, __fsub_rn(xx2, xx1));
+  const float h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
+  return ovr > thr;
+}
+
+// In-CTA bitonic sort of n (power of two) keys in shared memory.
+__device__ void bitonic_sort_smem(uint64_t* keys, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const uint64_t a = keys[i], b = keys[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            keys[i] = b;
+            keys[ixj] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// In-CTA stable LSD radix sort (8-bit digits) of `count` keys living in global memory.
+// scratch: hist[256] + base[256] + warp_cnt[32][256] (uint32).  Returns the buffer holding the result.
+__device__ uint64_t* block_radix_sort(uint64_t* a, uint64_t* b, int count, uint32_t* scratch) {
+  uint32_t* hist = scratch;
+  uint32_t* base = scratch + 256;
+  uint32_t* wcnt = scratch + 512;  // [32][256]
+  __shared__ int s_skip;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  for (int i = tid; i < 32 * 256; i += blockDim.x) wcnt[i] = 0;
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = pass * 8;
+    if (tid < 256) hist[tid] = 0;
+    if (tid == 0) s_skip = 0;
+    __syncthreads();
+    for (int i = tid; i < count; i += blockDim.x) atomicAdd(&hist[(a[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    if (tid < 256 && hist[tid] == static_cast<uint32_t>(count)) s_skip = 1;  // digit constant: no-op pass
+    __syncthreads();
+    if (s_skip) {
+      __syncthreads();
+      continue;
+    }
+    if (tid < 32) {  // exclusive scan of 256 bins by one warp, 8 bins per lane
+      uint32_t v[8], sum = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i] = hist[tid * 8 + i];
+        sum += v[i];
+      }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      uint32_t run = incl - sum;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        base[tid * 8 + i] = run;
+        run += v[i];
+      }
+    }
+    __syncthreads();
+    for (int t0 = 0; t0 < count; t0 += blockDim.x) {
+      const int i = t0 + tid;
+      const bool valid = i < count;
+      const uint64_t key = valid ? a[i] : 0ull;
+      const uint32_t d = valid ? static_cast<uint32_t>((key >> shift) & 255u) : (256u + lane);
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const uint32_t rank = __popc(peers & lt_mask);
+      const bool leader = valid && rank == 0;
+      if (leader) wcnt[warp * 256 + d] = __popc(peers);
+      __syncthreads();
+      if (tid < 256) {  // per-digit exclusive scan across the 32 warps, continuing the running base
+        uint32_t run = base[tid];
+        for (int w = 0; w < 32; ++w) {
+          const uint32_t t = wcnt[w * 256 + tid];
+          wcnt[w * 256 + tid] = run;
+          run += t;
+        }
+        base[tid] = run;
+      }
+      __syncthreads();
+      if (valid) b[wcnt[warp * 256 + d] + rank] = key;
+      __syncthreads();
+      if (tid < 256) {
+        for (int w = 0; w < 32; ++w) wcnt[w * 256 + tid] = 0;
+      }
+      __syncthreads();
+    }
+    uint64_t* t = a;
+    a = b;
+    b = t;
+    __syncthreads();
+  }
+  return a;
+}
+
+__global__ void __launch_bounds__(kNmsThreads)
+nms_image_kernel(const NmsParams p, Workspace ws) {
+  extern __shared__ __align__(16) uint8_t dyn_smem[];
+  // layout: [sort region 36 KB: 4096 keys | radix scratch] [kept boxes max_det*16] [kept areas] [kept labels]
+  uint64_t* s_keys = reinterpret_cast<uint64_t*>(dyn_smem);
+  uint32_t* s_scratch = reinterpret_cast<uint32_t*>(dyn_smem);
+  float4* k_box = reinterpret_cast<float4*>(dyn_smem + 36 * 1024);
+  float* k_area = reinterpret_cast<float*>(k_box + p.max_det);
+  int* k_label = reinterpret_cast<int*>(k_area + p.max_det);
+  __shared__ int s_kcount, s_first, s_warp_first[32];
+  __shared__ float4 s_pick_box;
+  __shared__ float s_pick_area;
+  __shared__ int s_pick_label;
+
+  const int img = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long raw_count = ws.img_count[img];
+  int count = static_cast<int>(raw_count < p.cap_per_image ? raw_count : p.cap_per_image);
+  if (tid == 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(&p.status[0]), static_cast<unsigned long long>(raw_count));
+    atomicMax(reinterpret_cast<unsigned long long*>(&p.status[2]), static_cast<unsigned long long>(raw_count));
+    if (raw_count > p.cap_per_image) {
+      atomicExch(reinterpret_cast<unsigned long long*>(&p.status[1]), 1ull);
+      p.out_counts[img] = 0;
+    }
+    s_kcount = 0;
+  }
+  if (raw_count > p.cap_per_image) return;  // host grows the arena and re-runs
+
+  uint64_t* keys_g = ws.keys_a + static_cast<long long>(img) * p.cap_per_image;
+  const uint64_t* sorted;
+  if (count <= kSmallSort) {
+    int n2 = 32;
+    while (n2 < count) n2 <<= 1;
+    for (int i = tid; i < n2; i += blockDim.x) s_keys[i] = i < count ? keys_g[i] : ~0ull;
+    __syncthreads();
+    bitonic_sort_smem(s_keys, n2);
+    sorted = s_keys;
+  } else {
+    __syncthreads();
+    sorted = block_radix_sort(keys_g, ws.keys_b + static_cast<long long>(img) * p.cap_per_image, count, s_scratch);
+  }
+  __syncthreads();
+
+  // semantics for this image
+  bool trick;
+  if (p.semantics == YB_NMS_TV_AUTO)
+    trick = static_cast<long long>(count) * 4 <= 4000;  // torchvision: boxes.numel() > 4000 -> per-class
+  else
+    trick = p.semantics == YB_NMS_OFFSET_TRICK;
+  float off_unit = 0.f;
+  if (trick) off_unit = __fadd_rn(ordered_int_to_float(ws.img_maxc[img]), 1.0f);  // max_coordinate + 1
+
+  float gain = 1.f, padx = 0.f, pady = 0.f;
+  if (p.rescale) {
+    gain = p.rescale[img * 3 + 0];
+    padx = p.rescale[img * 3 + 1];
+    pady = p.rescale[img * 3 + 2];
+  }
+
+  for (int base = 0; base < count; base += blockDim.x) {
+    const int j = base + tid;
+    bool alive = j < count;
+    float4 box = make_float4(0.f, 0.f, 0.f, 0.f), nbox = box;
+    float area = 0.f, score = 0.f;
+    int label = 0;
+    uint32_t cidx = 0;
+    if (alive) {
+      const uint64_t key = sorted[j];
+      score = from_orderable_desc(static_cast<uint32_t>(key >> 32));
+      cidx = static_cast<uint32_t>(key);
+      if (p.explicit_mode) {
+        box = p.x_boxes[cidx];
+        label = static_cast<int>(p.x_labels[cidx]);
+      } else {
+        const int anchor = cidx / p.n_classes;
+        label = cidx - anchor * p.n_classes;
+        box = ws.boxes[static_cast<long long>(img) * p.anchors_per_image + anchor];
+      }
+      nbox = box;
+      if (trick) {
+        const float off = __fmul_rn(static_cast<float>(label), off_unit);
+        nbox = make_float4(__fadd_rn(box.x, off), __fadd_rn(box.y, off), __fadd_rn(box.z, off), __fadd_rn(box.w, off));
+      }
+      area = box_area(nbox);
+      const int kc = s_kcount;
+      for (int i = 0; i < kc; ++i) {
+        if (!trick && k_label[i] != label) continue;
+        if (iou_over(k_box[i], k_area[i], nbox, area, p.iou_thresh)) {
+          alive = false;
+          break;
+        }
+      }
+    }
+    // resolve the survivors of this batch in candidate order
+    while (true) {
+      const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+      if (lane == 0) s_warp_first[warp] = bal ? (warp * 32 + __ffs(bal) - 1) : 0x7fffffff;
+      __syncthreads();
+      if (warp == 0) {
+        int v = s_warp_first[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (lane == 0) s_first = v;
+      }
+      __syncthreads();
+      const int first = s_first;
+      if (first == 0x7fffffff) break;
+      if (tid == first) {
+        const int slot = s_kcount;
+        k_box[slot] = nbox;
+        k_area[slot] = area;
+        k_label[slot] = label;
+        s_pick_box = nbox;
+        s_pick_area = area;
+        s_pick_label = label;
+        // emit the detection
+        const long long o = static_cast<long long>(img) * p.max_det + slot;
+        if (p.explicit_mode) {
+          p.out_keep[slot] = static_cast<int64_t>(cidx);
+        } else {
+          float4 ob = box;
+          if (p.rescale) {  // transform.py:362-365: (x - pad) / gain, fp32, no clipping
+            ob.x = __fdiv_rn(__fsub_rn(box.x, padx), gain);
+            ob.z = __fdiv_rn(__fsub_rn(box.z, padx), gain);
+            ob.y = __fdiv_rn(__fsub_rn(box.y, pady), gain);
+            ob.w = __fdiv_rn(__fsub_rn(box.w, pady), gain);
+          }
+          reinterpret_cast<float4*>(p.out_boxes)[o] = ob;
+          p.out_scores[o] = score;
+          p.out_labels[o] = static_cast<int64_t>(label);
+        }
+        s_kcount = slot + 1;
+        alive = false;
+      }
+      __syncthreads();
+      if (s_kcount >= p.max_det) break;
+      if (alive && (trick || s_pick_label == label) &&
+          iou_over(s_pick_box, s_pick_area, nbox, area, p.iou_thresh))
+        alive = false;
+      __syncthreads();
+    }
+    __syncthreads();
+    if (s_kcount >= p.max_det) break;
+  }
+  __syncthreads();
+  if (tid == 0) p.out_counts[img] = s_kcount;
+}
+
+// explicit-candidate key builder for yb_batched_nms
+__global__ void build_keys_kernel(const float* __restrict__ scores, const float4* __restrict__ boxes,
+                                  long long n, Workspace ws) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  ws.keys_a[i] = (static_cast<uint64_t>(orderable_desc(scores[i])) << 32) | static_cast<uint32_t>(i);
+  const float4 b = boxes[i];
+  atomicMax(&ws.img_maxc[0], float_to_ordered_int(fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
+}
+
+__global__ void init_counters_kernel(Workspace ws, int n, long long* status, int preset_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    ws.img_count[i] = preset_count;
+    ws.img_maxc[i] = float_to_ordered_int(-INFINITY);
+  }
+  if (i < 4 && status) status[i] = 0;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
+
+size_t carve(Workspace& ws, uint8_t* base, int n, long long cap, long long anchors) {
+  size_t off = 0;
+  ws.keys_a = reinterpret_cast<uint64_t*>(base + off);
+  off += align256(static_cast<size_t>(n) * cap * 8);
+  ws.keys_b = reinterpret_cast<uint64_t*>(base + off);
+  off += align256(static_cast<size_t>(n) * cap * 8);
+  ws.boxes = reinterpret_cast<float4*>(base + off);
+  off += align256(static_cast<size_t>(n) * anchors * 16);
+  ws.img_count = reinterpret_cast<int*>(base + off);
+  off += align256(static_cast<size_t>(n) * 4);
+  ws.img_maxc = reinterpret_cast<int*>(base + off);
+  off += align256(static_cast<size_t>(n) * 4);
+  ws.status = reinterpret_cast<long long*>(base + off);
+  off += align256(4 * sizeof(long long));
+  return off;
+}
+
+size_t nms_smem_bytes(int max_det) { return 36 * 1024 + static_cast<size_t>(max_det) * (16 + 4 + 4); }
+
+int ensure_nms_smem(size_t bytes) {
+  static size_t configured = 0;
+  if (bytes > configured) {
+    YB_CHECK_CUDA(cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(bytes)));
+    configured = bytes;
+  }
+  return YB_OK;
+}
+
+long long anchors_per_image(const yb_nms_params* p, const yb_head_level* lv) {
+  long long a = 0;
+  for (int l = 0; l < p->n_levels; ++l) a += static_cast<long long>(p->n_anchors) * lv[l].H * lv[l].W;
+  return a;
+}
+
+}  // namespace
+}  // namespace yb
+
+using namespace yb;
+
+extern "C" size_t yb_decode_nms_workspace_bytes(const yb_nms_params* p, const yb_head_level* levels) {
+  if (!p || !levels || p->n_images <= 0 || p->n_levels <= 0 || p->n_levels > YB_MAX_LEVELS) return 0;
+  Workspace ws;
+  const long long cap = (p->max_candidates + p->n_images - 1) / p->n_images;
+  return carve(ws, nullptr, p->n_images, cap > 0 ? cap : 1, anchors_per_image(p, levels));
+}
+
+extern "C" int yb_decode_nms(const yb_nms_params* p, const yb_head_level* levels, const float* rescale_dev,
+                             float* boxes_dev, float* scores_dev, int64_t* labels_dev, int32_t* counts_dev,
+                             int64_t* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  YB_REQUIRE(p && levels && boxes_dev && scores_dev && labels_dev && counts_dev && status_dev && workspace_dev,
+             "decode_nms: null argument");
+  YB_REQUIRE(p->n_images > 0 && p->n_levels > 0 && p->n_levels <= YB_MAX_LEVELS, "decode_nms: n_images/n_levels");
+  YB_REQUIRE(p->n_anchors > 0 && p->n_anchors <= YB_MAX_ANCHORS && p->n_classes > 0, "decode_nms: anchors/classes");
+  YB_REQUIRE(p->max_det > 0 && p->max_det <= 4096, "decode_nms: max_det must be in [1, 4096]");
+  YB_REQUIRE(p->semantics >= 0 && p->semantics <= 2, "decode_nms: bad semantics");
+  const long long apm = anchors_per_image(p, levels);
+  YB_REQUIRE(apm > 0, "decode_nms: no anchors");
+  YB_REQUIRE(apm * p->n_classes < (1ll << 31), "decode_nms: anchors*classes overflows the candidate index");
+  const long long cap = (p->max_candidates + p->n_images - 1) / p->n_images;
+  YB_REQUIRE(cap >= 1, "decode_nms: max_candidates too small");
+  Workspace ws;
+  const size_t need = carve(ws, static_cast<uint8_t*>(workspace_dev), p->n_images, cap, apm);
+  if (need > workspace_bytes) {
+    set_error("decode_nms: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+    return YB_ERR_WORKSPACE;
+  }
+  DecodeParams dp;
+  int dtype = levels[0].dtype;
+  dp.lvl_start[0] = 0;
+  for (int l = 0; l < YB_MAX_LEVELS; ++l) {
+    if (l < p->n_levels) {
+      YB_REQUIRE(levels[l].dtype == dtype, "decode_nms: all levels must share a dtype");
+      YB_REQUIRE(levels[l].logits != nullptr && levels[l].H > 0 && levels[l].W > 0, "decode_nms: level %d empty", l);
+      dp.lvl[l] = levels[l];
+      dp.lvl_start[l + 1] = dp.lvl_start[l] + p->n_anchors * levels[l].H * levels[l].W;
+    } else {
+      dp.lvl[l] = levels[0];
+      dp.lvl_start[l + 1] = dp.lvl_start[l];
+    }
+  }
+  dp.n_images = p->n_images;
+  dp.n_levels = p->n_levels;
+  dp.n_anchors = p->n_anchors;
+  dp.n_classes = p->n_classes;
+  dp.anchors_per_image = static_cast<int>(apm);
+  dp.score_thresh = p->score_thresh;
+  dp.cap_per_image = cap;
+
+  init_counters_kernel<<<(p->n_images + 127) / 128 + 1, 128, 0, stream>>>(ws, p->n_images, reinterpret_cast<long long*>(status_dev), 0);
+  YB_CHECK_CUDA(cudaGetLastError());
+  const long long total = static_cast<long long>(p->n_images) * apm;
+  const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  switch (dtype) {
+    case YB_F32:
+      decode_candidates_kernel<float><<<blocks, 256, 0, stream>>>(dp, ws);
+      break;
+    case YB_F16:
+      decode_candidates_kernel<__half><<<blocks, 256, 0, stream>>>(dp, ws);
+      break;
+    case YB_BF16:
+      decode_candidates_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(dp, ws);
+      break;
+    default:
+      set_error("decode_nms: unsupported logits dtype %d", dtype);
+      return YB_ERR_INVALID;
+  }
+  YB_CHECK_CUDA(cudaGetLastError());
+
+  NmsParams np;
+  np.n_classes = p->n_classes;
+  np.anchors_per_image = static_cast<int>(apm);
+  np.cap_per_image = cap;
+  np.iou_thresh = p->iou_thresh;
+  np.max_det = p->max_det;
+  np.semantics = p->semantics;
+  np.explicit_mode = 0;
+  np.x_boxes = nullptr;
+  np.x_labels = nullptr;
+  np.rescale = rescale_dev;
+  np.out_boxes = boxes_dev;
+  np.out_scores = scores_dev;
+  np.out_labels = labels_dev;
+  np.out_keep = nullptr;
+  np.out_counts = counts_dev;
+  np.status = reinterpret_cast<long long*>(status_dev);
+  const size_t smem = nms_smem_bytes(p->max_det);
+  int rc = ensure_nms_smem(smem);
+  if (rc != YB_OK) return rc;
+  nms_image_kernel<<<p->n_images, kNmsThreads, smem, stream>>>(np, ws);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+extern "C" size_t yb_batched_nms_workspace_bytes(int64_t n_boxes) {
+  Workspace ws;
+  return carve(ws, nullptr, 1, n_boxes > 0 ? n_boxes : 1, 1);
+}
+
+extern "C" int yb_batched_nms(const float* boxes_dev, const float* scores_dev, const int64_t* labels_dev,
+                              int64_t n_boxes, float iou_thresh, int semantics, int32_t max_keep,
+                              int64_t* keep_dev, int32_t* n_keep_dev, void* workspace_dev,
+                              size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  YB_REQUIRE(keep_dev && n_keep_dev && workspace_dev, "batched_nms: null argument");
+  YB_REQUIRE(n_boxes >= 0 && n_boxes < (1ll << 31), "batched_nms: n_boxes out of range");
+  YB_REQUIRE(max_keep > 0 && max_keep <= 4096, "batched_nms: max_keep must be in [1, 4096]");
+  YB_REQUIRE(semantics >= 0 && semantics <= 2, "batched_nms: bad semantics");
+  YB_REQUIRE(n_boxes == 0 || (boxes_dev && scores_dev && labels_dev), "batched_nms: null inputs");
+  YB_REQUIRE((reinterpret_cast<uintptr_t>(boxes_dev) & 15) == 0, "batched_nms: boxes must be 16-byte aligned");
+  Workspace ws;
+  const long long cap = n_boxes > 0 ? n_boxes : 1;
+  const size_t need = carve(ws, static_cast<uint8_t*>(workspace_dev), 1, cap, 1);
+  if (need > workspace_bytes) {
+    set_error("batched_nms: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
+    return YB_ERR_WORKSPACE;
+  }
+  init_counters_kernel<<<1, 128, 0, stream>>>(ws, 1, ws.status, static_cast<int>(n_boxes));
+  YB_CHECK_CUDA(cudaGetLastError());
+  if (n_boxes > 0) {
+    build_keys_kernel<<<static_cast<unsigned>((n_boxes + 255) / 256), 256, 0, stream>>>(
+        scores_dev, reinterpret_cast<const float4*>(boxes_dev), n_boxes, ws);
+    YB_CHECK_CUDA(cudaGetLastError());
+  }
+  NmsParams np;
+  np.n_classes = 0;
+  np.anchors_per_image = 0;
+  np.cap_per_image = cap;
+  np.iou_thresh = iou_thresh;
+  np.max_det = max_keep;
+  np.semantics = semantics;
+  np.explicit_mode = 1;
+  np.x_boxes = reinterpret_cast<const float4*>(boxes_dev);
+  np.x_labels = labels_dev;
+  np.rescale = nullptr;
+  np.out_boxes = nullptr;
+  np.out_scores = nullptr;
+  np.out_labels = nullptr;
+  np.out_keep = keep_dev;
+  np.out_counts = n_keep_dev;
+  np.status = ws.status;  // not reported through this entry point
+  const size_t smem = nms_smem_bytes(max_keep);
+  int rc = ensure_nms_smem(smem);
+  if (rc != YB_OK) return rc;
+  nms_image_kernel<<<1, kNmsThreads, smem, stream>>>(np, ws);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return YB_OK;
+}

@@ -1,0 +1,326 @@
+"""Lowering of the YOLOv5 r6.0 graph (backbone + PAN + head) to a native launch plan.
+
+The reference executes ~60-126 `conv2d -> batch_norm -> silu` triples plus `cat`/`Upsample`/
+`max_pool2d` as separate PyTorch ops (yolort/models/backbone_utils.py:54-57,
+path_aggregation_network.py:199-239, box_head.py:68-82).  Here the module tree is walked ONCE per
+(batch, canvas) shape and turned into a flat list of `yb_op_desc` for libyolort_b200.so:
+
+  * BatchNorm (eps = module.eps = 1e-3) is folded into the conv weights in fp64, then rounded to the
+    compute dtype; the folded shift becomes the fp32 epilogue bias.
+  * activations live in NHWC buffers of one arena; every `torch.cat` of the reference disappears
+    because producers write straight into channel windows of the concat buffer.
+  * C3's sibling 1x1 convs cv1 and cv2 (common.py:168-169) read the same input, so they run as one
+    GEMM with concatenated output channels.
+  * the 6x6/s2 stem (darknetv6.py:82) runs as a 3x3/s1 conv over the space-to-depth input the
+    letterbox kernel emits (exact rewrite: tap kh = 2a+dy, kw = 2b+dx).
+
+Host code only prepares descriptors; all arithmetic happens in csrc/*.cu.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import _C
+from .models.common import C3, Bottleneck, Conv, SPP
+
+
+def _round_up(v: int, m: int) -> int:
+    return (v + m - 1) // m * m
+
+
+@dataclass
+class _Buf:
+    name: str
+    div: int          # spatial divisor w.r.t. the canvas
+    C: int            # total channels (pixel stride)
+    offset: int = 0   # byte offset in the arena
+
+
+@dataclass
+class _View:
+    buf: _Buf
+    ch0: int
+    C: int
+
+
+@dataclass
+class _Op:
+    kind: int
+    src: _View
+    dst: _View
+    ksize: int = 1
+    stride: int = 1
+    pad: int = 0
+    act: int = _C.YB_ACT_NONE
+    weight: Optional[torch.Tensor] = None  # packed [Cout_pad, taps, Cin_pad] compute dtype
+    bias: Optional[torch.Tensor] = None    # fp32 [Cout_pad]
+    residual: Optional[_View] = None
+    name: str = ""
+    flops_per_pixel: int = 0               # 2*MACs per output pixel of the REFERENCE conv (algorithmic work)
+
+
+# ---------------------------------------------------------------------------------------------------
+# parameter preparation
+# ---------------------------------------------------------------------------------------------------
+def fold_conv_bn(m: Conv) -> Tuple[torch.Tensor, torch.Tensor]:
+    """w' = w * gamma/sqrt(var+eps), b' = beta - mean*gamma/sqrt(var+eps), in fp64.
+    (Equivalent to conv -> BatchNorm2d.eval(), yolort/v5/models/common.py:60-70.)"""
+    w = m.conv.weight.detach().double().cpu()
+    bn = m.bn
+    scale = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
+    shift = bn.bias.detach().double().cpu() - bn.running_mean.detach().double().cpu() * scale
+    return w * scale.view(-1, 1, 1, 1), shift
+
+
+def stem_to_s2d(w: torch.Tensor) -> torch.Tensor:
+    """[Co,3,6,6] stride-2 pad-2 kernel -> [Co,16,3,3] stride-1 pad-1 kernel over the space-to-depth
+    input whose channel is (dy*2+dx)*4 + c (c == 3 is a zero channel)."""
+    co = w.shape[0]
+    out = torch.zeros((co, 16, 3, 3), dtype=w.dtype)
+    for a in range(3):
+        for b in range(3):
+            for dy in range(2):
+                for dx in range(2):
+                    q = (dy * 2 + dx) * 4
+                    out[:, q:q + 3, a, b] = w[:, :, 2 * a + dy, 2 * b + dx]
+    return out
+
+
+def pack_weight(w: torch.Tensor, dtype: torch.dtype, device: torch.device) -> Tuple[torch.Tensor, int, int]:
+    """[Co,Ci,k,k] -> K-major [Co_pad, k*k, Ci_pad] (zero padded, both multiples of 16)."""
+    co, ci, kh, kw = w.shape
+    ci_pad, co_pad = _round_up(ci, 16), _round_up(co, 16)
+    p = torch.zeros((co_pad, kh * kw, ci_pad), dtype=torch.float64)
+    p[:co, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci)
+    return p.to(dtype).to(device).contiguous(), ci_pad, co_pad
+
+
+def pack_bias(b: torch.Tensor, co_pad: int, device: torch.device) -> torch.Tensor:
+    out = torch.zeros((co_pad,), dtype=torch.float64)
+    out[: b.numel()] = b
+    return out.to(torch.float32).to(device).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------
+# graph lowering
+# ---------------------------------------------------------------------------------------------------
+class _Lowering:
+    def __init__(self, dtype: torch.dtype, device: torch.device):
+        self.bufs: List[_Buf] = []
+        self.ops: List[_Op] = []
+        self.dtype = dtype
+        self.device = device
+
+    def buf(self, name: str, div: int, C: int) -> _Buf:
+        b = _Buf(name, div, C)
+        self.bufs.append(b)
+        return b
+
+    def conv(self, name, w, b, src: _View, dst: _View, k, s, p, act, residual=None, ref_flops_per_pixel=None):
+        assert w.shape[1] == src.C and w.shape[0] <= dst.C, (name, tuple(w.shape), src.C, dst.C)
+        wp, _, co_pad = pack_weight(w, self.dtype, self.device)
+        bp = pack_bias(b, co_pad, self.device)
+        if ref_flops_per_pixel is None:
+            ref_flops_per_pixel = 2 * w.shape[0] * w.shape[1] * k * k
+        self.ops.append(_Op(_C.YB_OP_CONV, src, dst, k, s, p, act, wp, bp, residual, name, ref_flops_per_pixel))
+
+    def conv_module(self, name, m: Conv, src: _View, dst: _View, residual=None):
+        w, b = fold_conv_bn(m)
+        k, s, p = m.conv.kernel_size[0], m.conv.stride[0], m.conv.padding[0]
+        self.conv(name, w, b, src, dst, k, s, p, _C.YB_ACT_SILU, residual)
+
+    def c3(self, name, m: C3, src: _View, dst: _View):
+        div = src.buf.div
+        c_ = m.cv1.conv.out_channels
+        cat = self.buf(f"{name}.cat", div, 2 * c_)
+        w1, b1 = fold_conv_bn(m.cv1)
+        w2, b2 = fold_conv_bn(m.cv2)
+        # cv1 || cv2 as one GEMM: channels [0,c_) = cv1(x), [c_,2c_) = cv2(x)  (common.py:173 cat order)
+        self.conv(f"{name}.cv1+cv2", torch.cat([w1, w2], 0), torch.cat([b1, b2], 0), src,
+                  _View(cat, 0, 2 * c_), 1, 1, 0, _C.YB_ACT_SILU)
+        y = _View(cat, 0, c_)
+        n = len(m.m)
+        for i, blk in enumerate(m.m):
+            t = self.buf(f"{name}.m{i}.t", div, c_)
+            self.conv_module(f"{name}.m.{i}.cv1", blk.cv1, y, _View(t, 0, c_))
+            out = _View(cat, 0, c_) if i == n - 1 else _View(self.buf(f"{name}.m{i}.y", div, c_), 0, c_)
+            self.conv_module(f"{name}.m.{i}.cv2", blk.cv2, _View(t, 0, c_), out, residual=y if blk.add else None)
+            y = out
+        self.conv_module(f"{name}.cv3", m.cv3, _View(cat, 0, 2 * c_), dst)
+
+    def spp(self, name, m: SPP, src: _View, dst: _View):
+        if tuple(m.k) != (5, 9, 13):
+            raise NotImplementedError("SPP pooling kernel implements k=(5,9,13) (the r6.0 neck)")
+        div = src.buf.div
+        c_ = m.cv1.conv.out_channels
+        cat = self.buf(f"{name}.cat", div, 4 * c_)
+        self.conv_module(f"{name}.cv1", m.cv1, src, _View(cat, 0, c_))
+        self.ops.append(_Op(_C.YB_OP_SPP_POOL, _View(cat, 0, c_), _View(cat, c_, 3 * c_), name=f"{name}.pool"))
+        self.conv_module(f"{name}.cv2", m.cv2, _View(cat, 0, 4 * c_), dst)
+
+    def upsample(self, name, src: _View, dst: _View):
+        self.ops.append(_Op(_C.YB_OP_UPSAMPLE2X, src, dst, name=name))
+
+
+def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
+    """Walk YOLO.backbone / YOLO.head and emit (lowering, input_buf, head_bufs)."""
+    L = _Lowering(dtype, device)
+    bb = model.backbone
+    body, pan = bb.body, bb.pan
+    if len(model.head.head) != 3 or getattr(pan, "intermediate_blocks", None) is not None:
+        raise NotImplementedError("only the 3-level r6.0 topology is lowered (P6 is 'next' in SURVEY.md 8f)")
+    c3, c4, c5 = bb.out_channels
+
+    x0 = L.buf("input.s2d", 2, 16)
+    stem: Conv = body["0"]
+    if stem.conv.kernel_size != (6, 6) or stem.conv.stride != (2, 2) or stem.conv.padding != (2, 2):
+        raise NotImplementedError("stem must be the r6.0 6x6/s2/p2 convolution")
+    w, b = fold_conv_bn(stem)
+    t0 = L.buf("body.0", 2, w.shape[0])
+    L.conv("body.0(stem as 3x3 over s2d)", stem_to_s2d(w), b, _View(x0, 0, 16), _View(t0, 0, w.shape[0]), 3, 1, 1,
+           _C.YB_ACT_SILU, ref_flops_per_pixel=2 * w.shape[0] * 3 * 36)
+
+    # concat buffers of the neck (path_aggregation_network.py:215-237)
+    cat1 = L.buf("pan.cat1[up(lat1)|f6]", 16, 2 * c4)
+    cat2 = L.buf("pan.cat2[up(lat2)|f4]", 8, 2 * c3)
+    cat_p4 = L.buf("pan.cat_p4[down(p3)|lat2]", 16, 2 * c3)
+    cat_p5 = L.buf("pan.cat_p5[down(p4)|lat1]", 32, 2 * c4)
+
+    cur = _View(t0, 0, w.shape[0])
+    div = 2
+    tap_dst = {4: _View(cat2, c3, c3), 6: _View(cat1, c4, c4)}
+    for i in range(1, 9):
+        m = body[str(i)]
+        if isinstance(m, Conv):
+            div *= 2
+            co = m.conv.out_channels
+            t = L.buf(f"body.{i}", div, co)
+            L.conv_module(f"body.{i}", m, cur, _View(t, 0, co))
+            cur = _View(t, 0, co)
+        else:
+            co = m.cv3.conv.out_channels
+            dst = tap_dst.get(i) or _View(L.buf(f"body.{i}", div, co), 0, co)
+            assert dst.C == co
+            L.c3(f"body.{i}", m, cur, dst)
+            cur = dst
+    f8 = cur
+
+    inner, layer = pan.inner_blocks, pan.layer_blocks
+    s = _View(L.buf("pan.spp", 32, c5), 0, c5)
+    L.spp("pan.inner_blocks.0", inner[0], f8, s)
+    lat1 = _View(cat_p5, c4, c4)
+    L.conv_module("pan.inner_blocks.1", inner[1], s, lat1)
+    L.upsample("pan.inner_blocks.2", lat1, _View(cat1, 0, c4))
+    u1 = _View(L.buf("pan.u1", 16, c4), 0, c4)
+    L.c3("pan.inner_blocks.3", inner[3], _View(cat1, 0, 2 * c4), u1)
+    lat2 = _View(cat_p4, c3, c3)
+    L.conv_module("pan.inner_blocks.4", inner[4], u1, lat2)
+    L.upsample("pan.inner_blocks.5", lat2, _View(cat2, 0, c3))
+    p3 = _View(L.buf("pan.p3", 8, c3), 0, c3)
+    L.c3("pan.layer_blocks.0", layer[0], _View(cat2, 0, 2 * c3), p3)
+    L.conv_module("pan.layer_blocks.1", layer[1], p3, _View(cat_p4, 0, c3))
+    p4 = _View(L.buf("pan.p4", 16, c4), 0, c4)
+    L.c3("pan.layer_blocks.2", layer[2], _View(cat_p4, 0, 2 * c3), p4)
+    L.conv_module("pan.layer_blocks.3", layer[3], p4, _View(cat_p5, 0, c4))
+    p5 = _View(L.buf("pan.p5", 32, c5), 0, c5)
+    L.c3("pan.layer_blocks.4", layer[4], _View(cat_p5, 0, 2 * c4), p5)
+
+    head_bufs = []
+    for i, (feat, conv) in enumerate(zip((p3, p4, p5), model.head.head)):
+        co = conv.out_channels
+        co_buf = _round_up(co, 16)
+        hb = L.buf(f"head.{i}", feat.buf.div, co_buf)
+        L.conv(f"head.head.{i}", conv.weight.detach().double().cpu(), conv.bias.detach().double().cpu(), feat,
+               _View(hb, 0, co_buf), 1, 1, 0, _C.YB_ACT_NONE)
+        head_bufs.append(hb)
+    return L, x0, head_bufs, {"p3": p3, "p4": p4, "p5": p5}
+
+
+# ---------------------------------------------------------------------------------------------------
+# plan instances
+# ---------------------------------------------------------------------------------------------------
+class PlanInstance:
+    """Arena + native plan for one (N, H, W)."""
+
+    def __init__(self, L: _Lowering, x0: _Buf, head_bufs: List[_Buf], feats: Dict[str, _View], N: int, H: int, W: int):
+        if H % 32 or W % 32:
+            raise ValueError(f"canvas {H}x{W} must be a multiple of 32")
+        self.N, self.H, self.W = N, H, W
+        self.dtype, self.device = L.dtype, L.device
+        esz = 2
+        off = 0
+        for b in L.bufs:
+            b.offset = off
+            off += _round_up(N * (H // b.div) * (W // b.div) * b.C * esz, 1024)
+        self.arena = torch.zeros((off,), dtype=torch.uint8, device=L.device)
+        self.arena_bytes = off
+        base = self.arena.data_ptr()
+        code = _C.dtype_code(L.dtype)
+
+        def ptr(v: _View) -> int:
+            return base + v.buf.offset + v.ch0 * esz
+
+        descs = []
+        self.op_names = []
+        self.op_flops = []
+        for op in L.ops:
+            d = _C.OpDesc()
+            hi, wi = H // op.src.buf.div, W // op.src.buf.div
+            ho, wo = H // op.dst.buf.div, W // op.dst.buf.div
+            d.kind, d.dtype = op.kind, code
+            d.N, d.H, d.W = N, hi, wi
+            d.Cin, d.in_cstride, d.in_ = op.src.C, op.src.buf.C, ptr(op.src)
+            d.Ho, d.Wo = ho, wo
+            d.Cout, d.out_cstride, d.out = op.dst.C, op.dst.buf.C, ptr(op.dst)
+            d.ksize, d.stride, d.pad, d.act = op.ksize, op.stride, op.pad, op.act
+            flops = 0
+            if op.kind == _C.YB_OP_CONV:
+                d.weight, d.bias = op.weight.data_ptr(), op.bias.data_ptr()
+                d.Cout_pad, _, d.Cin_pad = op.weight.shape
+                flops = N * ho * wo * op.flops_per_pixel
+            if op.residual is not None:
+                d.residual, d.res_cstride = ptr(op.residual), op.residual.buf.C
+            descs.append(d)
+            self.op_names.append(op.name)
+            self.op_flops.append(flops)
+        self._keepalive = [op.weight for op in L.ops] + [op.bias for op in L.ops]
+        self.plan = _C.Plan(descs, L.device)
+
+        def nhwc(b: _Buf) -> torch.Tensor:
+            h, w = H // b.div, W // b.div
+            n = N * h * w * b.C
+            return self.arena[b.offset: b.offset + n * esz].view(L.dtype).view(N, h, w, b.C)
+
+        self.input = nhwc(x0)                      # [N, H/2, W/2, 16] space-to-depth canvas
+        self.heads = [nhwc(b) for b in head_bufs]  # [N, h, w, round_up(3*(nc+5), 16)]
+        self.features = {k: nhwc(v.buf) for k, v in feats.items()}
+        self.buffers = {b.name: nhwc(b) for b in L.bufs}
+
+    def run(self, first: int = 0, count: Optional[int] = None) -> None:
+        self.plan.run(first, count)
+
+
+class Engine:
+    """Per-model cache of plan instances keyed by (N, H, W)."""
+
+    def __init__(self, model: nn.Module, dtype: torch.dtype, device: torch.device):
+        if device.type != "cuda":
+            raise _C.NativeLibraryError(
+                f"yolort_b200 runs on sm_100a GPUs only; model parameters are on {device} (no CPU fallback)")
+        if dtype not in (torch.float16, torch.bfloat16):
+            raise _C.NativeLibraryError(f"compute dtype must be float16 or bfloat16, got {dtype}")
+        _C.lib()
+        self.model, self.dtype, self.device = model, dtype, device
+        self._plans: Dict[Tuple[int, int, int], PlanInstance] = {}
+
+    def plan(self, N: int, H: int, W: int) -> PlanInstance:
+        key = (N, H, W)
+        inst = self._plans.get(key)
+        if inst is None:
+            with torch.cuda.device(self.device):
+                L, x0, head_bufs, feats = lower_yolo(self.model, self.dtype, self.device)
+                inst = PlanInstance(L, x0, head_bufs, feats, N, H, W)
+            self._plans[key] = inst
+        return inst

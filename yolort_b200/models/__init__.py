@@ -1,0 +1,30 @@
+"""Model constructors with the reference's names and kwargs (yolort/models/__init__.py:24-185), plus
+`yolov5x`, which the reference defines as an architecture (yolo.py:592-619) but does not export."""
+from typing import Any
+
+from .yolo import YOLO
+from .yolov5 import YOLOv5
+
+__all__ = ["YOLO", "YOLOv5", "yolov5n", "yolov5s", "yolov5m", "yolov5l", "yolov5x"]
+
+
+def _make(size: str):
+    def ctor(upstream_version: str = "r6.0", export_friendly: bool = False, **kwargs: Any) -> YOLOv5:
+        """Args:
+            upstream_version (str): ultralytics release; only "r6.0" is built here.
+            export_friendly (bool): accepted for signature compatibility; there is no export path here
+                (SiLU is evaluated inside the conv epilogue either way).
+        """
+        if upstream_version != "r6.0":
+            raise NotImplementedError("Currently only supports r6.0 versions (r4.0/r3.1 are 'next' in SURVEY.md 8f)")
+        return YOLOv5(arch=f"yolov5_darknet_pan_{size}_r60", **kwargs)
+
+    ctor.__name__ = f"yolov5{size}"
+    return ctor
+
+
+yolov5n = _make("n")
+yolov5s = _make("s")
+yolov5m = _make("m")
+yolov5l = _make("l")
+yolov5x = _make("x")

@@ -1,0 +1,44 @@
+"""`darknet_pan_backbone`: CSPDarknet body + PAN, same constructor contract as the reference
+(yolort/models/backbone_utils.py:60-122).  `body` keeps the module names "0".."8" so that
+state-dict keys read `backbone.body.<i>...`, as produced by torchvision's IntermediateLayerGetter
+in the reference (`backbone_utils.py:45`)."""
+from typing import List, Optional
+
+from torch import nn
+
+from .common import _PlanOnly
+from .darknetv6 import darknet_v6_features
+from .path_aggregation_network import PathAggregationNetwork
+
+
+class BackboneWithPAN(_PlanOnly):
+    def __init__(self, body: nn.Sequential, returned_layers: List[int], in_channels_list: List[int],
+                 depth_multiple: float, version: str, use_p6: bool = False):
+        super().__init__()
+        last = max(returned_layers)
+        self.body = nn.ModuleDict({str(i): m for i, m in enumerate(body) if i <= last})
+        self.returned_layers = list(returned_layers)
+        self.pan = PathAggregationNetwork(in_channels_list, depth_multiple, version=version, use_p6=use_p6)
+        self.out_channels = in_channels_list
+
+
+def darknet_pan_backbone(
+    backbone_name: str,
+    depth_multiple: float,
+    width_multiple: float,
+    pretrained: Optional[bool] = False,
+    returned_layers: Optional[List[int]] = None,
+    version: str = "r6.0",
+    use_p6: bool = False,
+) -> BackboneWithPAN:
+    if version != "r6.0":
+        raise NotImplementedError("Currently only upstream version 'r6.0' is built (SURVEY.md section 8f lists r4.0/r3.1 as next).")
+    if pretrained:
+        raise ValueError("no backbone checkpoints exist offline")
+    last_channel = 768 if use_p6 else 1024
+    body = darknet_v6_features(depth_multiple, width_multiple, last_channel=last_channel)
+    if returned_layers is None:
+        returned_layers = [4, 6, 8]
+    grow_widths = [256, 512, 768, 1024] if use_p6 else [256, 512, 1024]
+    in_channels_list = [int(gw * width_multiple) for gw in grow_widths]
+    return BackboneWithPAN(body, returned_layers, in_channels_list, depth_multiple, version, use_p6=use_p6)

@@ -1,0 +1,159 @@
+"""`YOLO`: backbone + head + post-process on the native plan, and the r6.0 model zoo.
+
+Mirrors the constructor / forward contract of the reference (yolort/models/yolo.py:38-183) and its
+factories `yolov5_darknet_pan_{n,s,m,l,x}_r60` (`:468-619`).  `forward(samples[N,3,H,W])` converts the
+batch to the plan's input layout with the letterbox kernel (identity geometry), runs the plan and the
+decode+NMS kernels; nothing is computed by PyTorch ops.
+"""
+from typing import Any, Callable, Dict, List, Optional
+
+import torch
+from torch import nn, Tensor
+
+from .. import _C
+from ..engine import Engine
+from .anchor_utils import AnchorGenerator
+from .backbone_utils import darknet_pan_backbone
+from .box_head import PostProcess, YOLOHead
+
+__all__ = [
+    "YOLO",
+    "yolov5_darknet_pan_n_r60",
+    "yolov5_darknet_pan_s_r60",
+    "yolov5_darknet_pan_m_r60",
+    "yolov5_darknet_pan_l_r60",
+    "yolov5_darknet_pan_x_r60",
+]
+
+DEFAULT_STRIDES = [8, 16, 32]
+DEFAULT_ANCHOR_GRIDS = [
+    [10, 13, 16, 30, 33, 23],
+    [30, 61, 62, 45, 59, 119],
+    [116, 90, 156, 198, 373, 326],
+]
+
+
+class YOLO(nn.Module):
+    def __init__(
+        self,
+        backbone: nn.Module,
+        num_classes: int,
+        strides: Optional[List[int]] = None,
+        anchor_grids: Optional[List[List[float]]] = None,
+        anchor_generator: Optional[nn.Module] = None,
+        head: Optional[nn.Module] = None,
+        criterion: Optional[Callable[..., Dict[str, Tensor]]] = None,
+        score_thresh: float = 0.005,
+        nms_thresh: float = 0.45,
+        detections_per_img: int = 300,
+        post_process: Optional[nn.Module] = None,
+    ):
+        super().__init__()
+        if not hasattr(backbone, "out_channels"):
+            raise ValueError(
+                "backbone should contain an attribute out_channels specifying the number of output "
+                "channels (assumed to be the same for all the levels)")
+        self.backbone = backbone
+        # accept tensors too: the reference loader passes `model.stride` as a Tensor
+        strides = DEFAULT_STRIDES if strides is None else [int(s) for s in strides]
+        anchor_grids = DEFAULT_ANCHOR_GRIDS if anchor_grids is None else anchor_grids
+        if anchor_generator is None:
+            anchor_generator = AnchorGenerator(strides, anchor_grids)
+        self.anchor_generator = anchor_generator
+        self.compute_loss = criterion  # training loss is out of scope
+        self.num_classes = num_classes
+        if head is None:
+            head = YOLOHead(backbone.out_channels, anchor_generator.num_anchors, anchor_generator.strides, num_classes)
+        self.head = head
+        if post_process is None:
+            post_process = PostProcess(anchor_generator.strides, score_thresh, nms_thresh, detections_per_img,
+                                       anchors_px=anchor_generator.anchors_px())
+        self.post_process = post_process
+        self._engine: Optional[Engine] = None
+
+    # -- engine lifetime -----------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):  # .to()/.half()/.cuda() invalidate prepared weights
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._engine = None
+        return super().load_state_dict(*a, **k)
+
+    def engine(self) -> Engine:
+        if self._engine is None:
+            p = next(self.parameters())
+            dtype = torch.bfloat16 if p.dtype == torch.bfloat16 else torch.float16
+            self._engine = Engine(self, dtype, p.device)
+        return self._engine
+
+    # -- stages --------------------------------------------------------------------------------------
+    def run_plan(self, plan) -> List[Tensor]:
+        """backbone + PAN + head on the prepared input canvas; returns the raw head logits (NHWC)."""
+        plan.run()
+        return plan.heads
+
+    def detect(self, plan, rescale: Optional[Tensor] = None) -> List[Dict[str, Tensor]]:
+        heads = self.run_plan(plan)
+        pp = self.post_process
+        return _C.decode_nms(heads, "nhwc", pp.strides, self.anchor_generator.anchors_px(), pp.score_thresh,
+                             pp.nms_thresh, pp.detections_per_img, getattr(pp, "nms_semantics", _C.NMS_TV_AUTO),
+                             rescale=rescale, num_classes=self.num_classes)
+
+    def forward(self, samples: Tensor, targets: Optional[Tensor] = None):
+        if self.training or targets is not None:
+            raise NotImplementedError("the training path (SetCriterion) is out of scope of this build; call .eval()")
+        if samples.dim() != 4 or samples.shape[1] != 3:
+            raise ValueError(f"samples must be [N,3,H,W], got {tuple(samples.shape)}")
+        N, _, H, W = (int(v) for v in samples.shape)
+        plan = self.engine().plan(N, H, W)
+        geoms = (_C.LetterboxGeom * N)()
+        for g in geoms:
+            g.src_h, g.src_w, g.new_h, g.new_w, g.top, g.left = H, W, H, W, 0, 0
+            g.ratio_h = g.ratio_w = 1.0
+        samples = samples.contiguous()
+        _C.letterbox([samples[i] for i in range(N)], geoms, H, W, 0.0, plan.input, _C.YB_LAYOUT_S2D16)
+        return self.detect(plan)
+
+    @classmethod
+    def load_from_yolov5(cls, checkpoint_path: str, score_thresh: float = 0.25, nms_thresh: float = 0.45,
+                         version: str = "r6.0", post_process: Optional[nn.Module] = None):
+        from ._checkpoint import load_from_ultralytics
+
+        info = load_from_ultralytics(checkpoint_path, version=version)
+        backbone = darknet_pan_backbone(f"darknet_{info['size']}_{version.replace('.', '_')}", info["depth_multiple"],
+                                        info["width_multiple"], version=version, use_p6=info["use_p6"])
+        model = cls(backbone, info["num_classes"], strides=info["strides"], anchor_grids=info["anchor_grids"],
+                    score_thresh=score_thresh, nms_thresh=nms_thresh, post_process=post_process)
+        model.load_state_dict(info["state_dict"])
+        return model
+
+
+def build_model(backbone_name: str, depth_multiple: float, width_multiple: float, version: str,
+                weights_name: Optional[str] = None, pretrained: bool = False, progress: bool = True,
+                num_classes: int = 80, use_p6: bool = False, **kwargs: Any) -> YOLO:
+    backbone = darknet_pan_backbone(backbone_name, depth_multiple, width_multiple, version=version, use_p6=use_p6)
+    model = YOLO(backbone, num_classes, **kwargs)
+    if pretrained:
+        raise ValueError(
+            f"No checkpoint is available offline for model {weights_name}; load a converted state_dict with "
+            "model.load_state_dict(...) or an upstream .pt with YOLO.load_from_yolov5(...)")
+    return model
+
+
+def _factory(size: str, depth: float, width: float):
+    def fn(pretrained: bool = False, progress: bool = True, num_classes: int = 80, **kwargs: Any) -> YOLO:
+        return build_model(f"darknet_{size}_r6_0", depth, width, "r6.0", f"yolov5_darknet_pan_{size}_r60_coco",
+                           pretrained, progress, num_classes, **kwargs)
+
+    fn.__name__ = f"yolov5_darknet_pan_{size}_r60"
+    fn.__doc__ = f"yolov5 {size} release 6.0 (depth_multiple={depth}, width_multiple={width})."
+    return fn
+
+
+# (depth, width) table: yolort/models/yolo.py:468-619
+yolov5_darknet_pan_n_r60 = _factory("n", 0.33, 0.25)
+yolov5_darknet_pan_s_r60 = _factory("s", 0.33, 0.5)
+yolov5_darknet_pan_m_r60 = _factory("m", 0.67, 0.75)
+yolov5_darknet_pan_l_r60 = _factory("l", 1.0, 1.0)
+yolov5_darknet_pan_x_r60 = _factory("x", 1.33, 1.25)

@@ -1,0 +1,118 @@
+"""`YOLOv5`: letterbox -> backbone/PAN/head -> decode+NMS -> rescale, end to end on the GPU.
+
+Keeps the public surface of the reference wrapper (yolort/models/yolov5.py:19-297): constructor kwargs,
+`forward(List[Tensor[3,H,W]]) -> List[Dict]` with keys (scores, labels, boxes), `predict`,
+`collate_images`, `default_loader`, `load_from_yolov5`.  Differences, all additive: uint8 images are
+accepted (the /255 is fused into the letterbox kernel), and `forward_padded` exposes the fixed-shape
+device outputs for callers that gather across ranks.
+"""
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+import torch
+from torch import nn, Tensor
+
+from .. import _C
+from . import yolo
+from .transform import YOLOTransform
+from .yolo import YOLO
+
+__all__ = ["YOLOv5"]
+
+
+class YOLOv5(nn.Module):
+    def __init__(
+        self,
+        arch: Optional[str] = None,
+        model: Optional[nn.Module] = None,
+        num_classes: int = 80,
+        pretrained: bool = False,
+        progress: bool = True,
+        size: Tuple[int, int] = (640, 640),
+        size_divisible: int = 32,
+        fixed_shape: Optional[Tuple[int, int]] = None,
+        fill_color: int = 114,
+        **kwargs: Any,
+    ) -> None:
+        super().__init__()
+        self.arch = arch
+        self.num_classes = num_classes
+        if model is None:
+            if arch is None or not hasattr(yolo, arch):
+                raise ValueError(f"unknown architecture {arch!r}; available: {yolo.__all__[1:]}")
+            model = getattr(yolo, arch)(pretrained=pretrained, progress=progress, num_classes=num_classes, **kwargs)
+        self.model = model
+        self.transform = YOLOTransform(size[0], size[1], size_divisible=size_divisible, fixed_shape=fixed_shape,
+                                       fill_color=fill_color)
+
+    # ---------------------------------------------------------------------------------------------
+    def _prepare(self, inputs: List[Tensor], batch_hw: Optional[Tuple[int, int]] = None):
+        """Letterbox `inputs` straight into the plan's input canvas; returns (plan, rescale[n,3] on device)."""
+        if self.training:
+            raise NotImplementedError("the training path is out of scope of this build; call .eval()")
+        inputs = list(inputs)
+        if len(inputs) == 0:
+            raise ValueError("empty image list")
+        original_image_sizes = [(int(im.shape[-2]), int(im.shape[-1])) for im in inputs]
+        geoms, (Hb, Wb) = self.transform.geometry(inputs, batch_hw)
+        plan = self.model.engine().plan(len(inputs), Hb, Wb)
+        self.transform.letterbox_into(inputs, geoms, Hb, Wb, plan.input, _C.YB_LAYOUT_S2D16)
+        rescale = self.transform.rescale_params((Hb, Wb), original_image_sizes).to(plan.device, non_blocking=True)
+        return plan, rescale
+
+    def forward(self, inputs: List[Tensor], targets: Optional[List[Dict[str, Tensor]]] = None):
+        if targets is not None:
+            raise NotImplementedError("the training path is out of scope of this build")
+        plan, rescale = self._prepare(inputs)
+        return self.model.detect(plan, rescale)
+
+    def forward_padded(self, inputs: List[Tensor], batch_hw: Optional[Tuple[int, int]] = None):
+        """Same computation, fixed-shape device outputs and no host synchronisation:
+        (boxes [n,D,4], scores [n,D], labels [n,D] int64, counts [n] int32, status [4] int64).
+        `batch_hw` pins the canvas (multi-GPU shards must letterbox to the GLOBAL batch shape to
+        reproduce single-GPU boxes: SURVEY.md section 8e)."""
+        plan, rescale = self._prepare(inputs, batch_hw)
+        m = self.model
+        heads = m.run_plan(plan)
+        pp = m.post_process
+        return _C.decode_nms_padded(heads, "nhwc", pp.strides, m.anchor_generator.anchors_px(), m.num_classes,
+                                    pp.score_thresh, pp.nms_thresh, pp.detections_per_img,
+                                    getattr(pp, "nms_semantics", _C.NMS_TV_AUTO), rescale)
+
+    @torch.no_grad()
+    def predict(self, x: Any, image_loader: Optional[Callable] = None) -> List[Dict[str, Tensor]]:
+        image_loader = image_loader or self.default_loader
+        images = self.collate_images(x, image_loader)
+        return self.forward(images)
+
+    def default_loader(self, img_path: str) -> Tensor:
+        """uint8 RGB [3,H,W]; the `/ 255.0` of the reference loader (yolov5.py:228) happens in the kernel."""
+        from torchvision.io import ImageReadMode, read_image
+
+        return read_image(img_path, mode=ImageReadMode.RGB)
+
+    def collate_images(self, samples: Any, image_loader: Callable) -> List[Tensor]:
+        p = next(self.parameters())
+
+        def place(t: Tensor) -> Tensor:
+            if t.dtype == torch.uint8:
+                return t.to(p.device, non_blocking=True)
+            return t.to(p.device).type_as(p)
+
+        if isinstance(samples, Tensor):
+            return [place(samples)]
+        if isinstance(samples, (list, tuple)) and len(samples) > 0 and all(isinstance(s, Tensor) for s in samples):
+            return [place(s) for s in samples]
+        if isinstance(samples, str):
+            samples = [samples]
+        if isinstance(samples, (list, tuple)) and all(isinstance(s, str) for s in samples):
+            return [place(image_loader(s)) for s in samples]
+        raise NotImplementedError(
+            f"The type of the sample is {type(samples)}, we currently don't support it now, the "
+            "samples should be either a tensor, list of tensors, a image path or list of image paths.")
+
+    @classmethod
+    def load_from_yolov5(cls, checkpoint_path: str, *, size: Tuple[int, int] = (640, 640), size_divisible: int = 32,
+                         fixed_shape: Optional[Tuple[int, int]] = None, fill_color: int = 114, **kwargs: Any):
+        model = YOLO.load_from_yolov5(checkpoint_path, **kwargs)
+        return cls(model=model, size=size, size_divisible=size_divisible, fixed_shape=fixed_shape,
+                   fill_color=fill_color)
