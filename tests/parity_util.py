@@ -43,3 +43,22 @@ def assert_dets_close(got, ref, box_atol, score_atol, allow_tie_swaps=False):
 
 def to_np(d):
     return {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+
+
+def _iou_matrix(a, b):
+    x1 = np.maximum(a[:, None, 0], b[None, :, 0]); y1 = np.maximum(a[:, None, 1], b[None, :, 1])
+    x2 = np.minimum(a[:, None, 2], b[None, :, 2]); y2 = np.minimum(a[:, None, 3], b[None, :, 3])
+    inter = np.clip(x2 - x1, 0, None) * np.clip(y2 - y1, 0, None)
+    aa = (a[:, 2] - a[:, 0]) * (a[:, 3] - a[:, 1]); ab = (b[:, 2] - b[:, 0]) * (b[:, 3] - b[:, 1])
+    return inter / (aa[:, None] + ab[None, :] - inter + 1e-12)
+
+
+def match_fraction(got, ref, iou_thr=0.9):
+    """Fraction of reference detections that have a same-label detection with IoU > iou_thr."""
+    if len(ref["scores"]) == 0:
+        return 1.0 if len(got["scores"]) == 0 else 0.0
+    if len(got["scores"]) == 0:
+        return 0.0
+    iou = _iou_matrix(np.asarray(ref["boxes"], dtype=np.float64), np.asarray(got["boxes"], dtype=np.float64))
+    same = np.asarray(ref["labels"])[:, None] == np.asarray(got["labels"])[None, :]
+    return float(((iou > iou_thr) & same).any(axis=1).mean())

@@ -1,0 +1,94 @@
+"""Whole-graph parity: backbone+PAN+head on the native plan vs reference fixtures / oracle, and end to end (B200)."""
+import numpy as np
+import pytest
+import torch
+
+import parity_util as util
+from oracle import restate as R
+from yolort_b200.models import yolov5n, yolov5s
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _stats(name, got, ref):
+    err = np.abs(got - ref)
+    rel_rms = float(np.sqrt((err ** 2).mean()) / (np.sqrt((ref ** 2).mean()) + 1e-12))
+    print(f"{name}: max_abs={err.max():.4f} rel_rms={rel_rms:.2e} ref_rms={np.sqrt((ref ** 2).mean()):.3f}")
+    return float(err.max()), rel_rms
+
+
+def _model_n():
+    sd = util.synth_state_dict(util.layouts()["n"], knob_obj=7.0, knob_cls=4.5, seed=0)
+    m = yolov5n(size=(128, 128), score_thresh=0.15).eval()
+    m.load_state_dict(sd)
+    return m.to(DEV), sd
+
+
+def test_features_and_heads_vs_reference_fixture():
+    z = util.load_npz("network_n.npz")
+    m, sd = _model_n()
+    x = torch.from_numpy(z["x"]).to(DEV)
+    dets = m.model(x)   # YOLO.forward on a pre-letterboxed NCHW batch
+    plan = m.model.engine().plan(1, 96, 128)
+    for key, name in (("p3", "p3"), ("p4", "p4"), ("p5", "p5")):
+        got = plan.features[name].float().permute(0, 3, 1, 2).cpu().numpy()
+        mx, rr = _stats(key, got, z[key])
+        assert rr < 1.5e-2      # fp16 activations through 20-30 layers vs the fp32 reference
+    for i in range(3):
+        h = plan.heads[i][..., :255].float().cpu()
+        n, hh, ww, _ = h.shape
+        got = h.view(n, hh, ww, 3, 85).permute(0, 3, 1, 2, 4).numpy()
+        mx, rr = _stats(f"head{i}", got, z[f"h{i}"])
+        assert rr < 1.5e-2
+    ref = util.dets_from_npz(z, 1)[0]
+    frac = util.match_fraction(util.to_np(dets[0]), ref, iou_thr=0.9)
+    print("network dets matched:", frac, len(dets[0]["scores"]), len(ref["scores"]))
+    assert frac >= 0.8
+
+
+def test_per_layer_stagewise_parity_yolov5n():
+    """Each launch of the plan vs the fp32 oracle applied to the SAME (fp16) input of that stage: feed the
+    oracle our previous activations by comparing only final taps with tight per-stage growth."""
+    m, sd = _model_n()
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 3, 64, 96, generator=g)
+    m.model(x.to(DEV))
+    plan = m.model.engine().plan(2, 64, 96)
+    net = R.Net(sd)
+    with torch.no_grad():
+        xr = x.half().float()
+        stem = net.conv(xr, "backbone.body.0")
+        b1 = net.conv(stem, "backbone.body.1")
+    got_stem = plan.buffers["body.0"].float().permute(0, 3, 1, 2).cpu().numpy()
+    mx, rr = _stats("stem", got_stem, stem.numpy())
+    assert rr < 2e-3
+    got_b1 = plan.buffers["body.1"].float().permute(0, 3, 1, 2).cpu().numpy()
+    mx, rr = _stats("body.1", got_b1, b1.numpy())
+    assert rr < 3e-3
+
+
+def test_end_to_end_vs_reference_fixture():
+    z = util.load_npz("e2e_n.npz")
+    m, sd = _model_n()
+    ims = [torch.from_numpy(z["img0"]).to(DEV), torch.from_numpy(z["img1"]).to(DEV)]
+    out = m(ims)
+    for got, ref in zip(out, util.dets_from_npz(z, 2)):
+        got = util.to_np(got)
+        frac = util.match_fraction(got, ref, iou_thr=0.9)
+        print("e2e matched fraction:", frac, "n_got", len(got["scores"]), "n_ref", len(ref["scores"]))
+        assert frac >= 0.8
+    # float inputs in [0,1] give the same result as uint8 inputs
+    out_f = m([im.float() / 255.0 for im in ims])
+    for a, b in zip(out, out_f):
+        assert torch.equal(a["labels"], b["labels"]) and torch.allclose(a["boxes"], b["boxes"], atol=1e-3)
+
+
+def test_predict_and_shapes_yolov5s_default_weights():
+    m = yolov5s().eval().to(DEV)
+    ims = [torch.randint(0, 256, (3, 480, 640), dtype=torch.uint8), torch.randint(0, 256, (3, 375, 500), dtype=torch.uint8)]
+    out = m.predict(ims)
+    assert isinstance(out, list) and len(out) == 2
+    for d in out:
+        assert d["boxes"].shape[1:] == (4,) and d["labels"].dtype == torch.int64 and d["scores"].dtype == torch.float32
+        assert d["boxes"].shape[0] == d["scores"].shape[0] == d["labels"].shape[0] <= 300

@@ -11,7 +11,6 @@ import torch
 from torch import nn, Tensor
 
 from .. import _C
-from ..engine import Engine
 from .anchor_utils import AnchorGenerator
 from .backbone_utils import darknet_pan_backbone
 from .box_head import PostProcess, YOLOHead
@@ -69,7 +68,7 @@ class YOLO(nn.Module):
             post_process = PostProcess(anchor_generator.strides, score_thresh, nms_thresh, detections_per_img,
                                        anchors_px=anchor_generator.anchors_px())
         self.post_process = post_process
-        self._engine: Optional[Engine] = None
+        self._engine = None
 
     # -- engine lifetime -----------------------------------------------------------------------------
     def _apply(self, fn, *a, **k):  # .to()/.half()/.cuda() invalidate prepared weights
@@ -80,7 +79,9 @@ class YOLO(nn.Module):
         self._engine = None
         return super().load_state_dict(*a, **k)
 
-    def engine(self) -> Engine:
+    def engine(self):
+        from ..engine import Engine
+
         if self._engine is None:
             p = next(self.parameters())
             dtype = torch.bfloat16 if p.dtype == torch.bfloat16 else torch.float16
