@@ -1,0 +1,87 @@
+"""Batch sharding across the GPUs of one box (one process per GPU, torch.distributed / NCCL as plumbing).
+
+The path shards by image: letterbox, convs and NMS are per-image independent, weights are
+replicated, and the ONLY exchange is one all-gather of the final padded detections when a single output list is
+required.  One subtlety is reproduced: the reference pads every image to the batch-wide canvas
+(yolort/models/transform.py:307-314) and rescales boxes with it (yolov5.py:179-181), so every rank letterboxes
+its shard to the GLOBAL (Hb, Wb), computed on the host from the image sizes alone -- no collective needed.
+"""
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from . import _C
+
+
+def shard_bounds(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous chunk [lo, hi) of `n_items` owned by `rank`; sizes differ by at most one, earlier ranks larger."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def global_canvas(sizes: Sequence[Tuple[int, int]], min_size: float, max_size: float, size_divisible: int = 32,
+                  fixed_shape: Optional[Tuple[int, int]] = None) -> Tuple[int, int]:
+    """(Hb, Wb) of the whole (unsharded) batch; host arithmetic only."""
+    _, hw = _C.letterbox_geometry(list(sizes), float(min_size), float(max_size), size_divisible, fixed_shape)
+    return hw
+
+
+def pack_detections(boxes: Tensor, scores: Tensor, labels: Tensor) -> Tensor:
+    """[n, D, 6] fp32 rows (x1, y1, x2, y2, score, label) -- the all-gather payload (24 B per detection slot).
+    Labels < 2^24 are exact in fp32."""
+    return torch.cat([boxes, scores.unsqueeze(-1), labels.to(torch.float32).unsqueeze(-1)], dim=-1).contiguous()
+
+
+def unpack_detections(packed: Tensor, counts: Tensor) -> List[Dict[str, Tensor]]:
+    out = []
+    host_counts = counts.to("cpu", torch.int64).tolist()
+    for i, c in enumerate(host_counts):
+        row = packed[i, :c]
+        out.append({"scores": row[:, 4], "labels": row[:, 5].to(torch.int64), "boxes": row[:, :4]})
+    return out
+
+
+def all_gather_detections(packed: Tensor, counts: Tensor, shard_sizes: Sequence[int], group=None) -> Tuple[Tensor, Tensor]:
+    """One collective pair over equal-sized buffers: shards are padded to the largest shard so that
+    all_gather_into_tensor (NCCL all-gather over NVLink) can be used; returns ([N_total, D, 6], [N_total])."""
+    world = dist.get_world_size(group)
+    n_max = max(shard_sizes)
+    D = packed.shape[1]
+    send = packed.new_zeros((n_max, D, 6))
+    send[: packed.shape[0]] = packed
+    send_c = counts.new_zeros((n_max,))
+    send_c[: counts.shape[0]] = counts
+    recv = packed.new_empty((world * n_max, D, 6))
+    recv_c = counts.new_empty((world * n_max,))
+    dist.all_gather_into_tensor(recv, send, group=group)
+    dist.all_gather_into_tensor(recv_c, send_c, group=group)
+    keep = torch.cat([torch.arange(r * n_max, r * n_max + s) for r, s in enumerate(shard_sizes)]).to(recv.device)
+    return recv[keep], recv_c[keep]
+
+
+def predict_sharded(model, images: List[Tensor], group=None) -> List[Dict[str, Tensor]]:
+    """Every rank passes the SAME full list of images (host tensors or tensors on its device); each rank runs
+    its contiguous shard on its own GPU and all ranks return the full, ordered detection list."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    tr = model.transform
+    sizes = [(int(im.shape[-2]), int(im.shape[-1])) for im in images]
+    canvas = global_canvas(sizes, tr.min_size, tr.max_size, tr.size_divisible, tr.fixed_shape)
+    bounds = [shard_bounds(len(images), r, world) for r in range(world)]
+    lo, hi = bounds[rank]
+    p = next(model.parameters())
+    D = model.model.post_process.detections_per_img
+    if hi > lo:
+        mine = model.collate_images(images[lo:hi], None)
+        boxes, scores, labels, counts, status = model.forward_padded(mine, batch_hw=canvas)
+        if int(status[1].item()) != 0:   # candidate arena overflow: grow and retry (never truncate)
+            model.forward(mine)          # the list API grows the arena
+            boxes, scores, labels, counts, status = model.forward_padded(mine, batch_hw=canvas)
+        packed = pack_detections(boxes, scores, labels)
+    else:
+        packed = torch.zeros((0, D, 6), dtype=torch.float32, device=p.device)
+        counts = torch.zeros((0,), dtype=torch.int32, device=p.device)
+    all_packed, all_counts = all_gather_detections(packed, counts, [b[1] - b[0] for b in bounds], group)
+    return unpack_detections(all_packed, all_counts)
