@@ -16,6 +16,7 @@ run postprocess 600 python -m pytest tests/test_gpu_postprocess.py -q -m gpu -s
 for t in test_conv1x1 test_conv1x1_ragged test_conv3x3 test_conv3x3_crosses test_bottleneck test_head_conv test_wide_output test_bf16 test_large_m test_rejects; do
   run conv_$t 240 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "$t"
 done
+run pool 300 python -m pytest tests/test_gpu_pool_upsample.py -q -m gpu -s
 run network 600 python -m pytest tests/test_gpu_network.py -q -m gpu -s
 run smoke 300 python __graft_entry__.py smoke
 if [ "$1" != "quick" ]; then

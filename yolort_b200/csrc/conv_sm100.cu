@@ -6,16 +6,21 @@
 // Replaces the arithmetic of yolort/v5/models/common.py:42-73 (Conv = conv2d -> BN(eps 1e-3) -> SiLU),
 // :94-116 (Bottleneck residual) and the 1x1 head convs of yolort/models/box_head.py:35-37,68-82.
 //
-// One CTA computes a 128 x block_n output tile:
-//   warp 0   : TMA producer.  A tiles come from a 4-D im2col tensor map (the TMA engine walks 128
-//              output pixels and applies padding/stride, zero-filling the halo) or, for 1x1/s1
-//              convs, from a plain 2-D tiled map; B tiles (weights) from a 2-D tiled map.  Both land
-//              in shared memory in the 32/64/128-byte swizzled K-major layout UMMA expects.
-//   warp 1   : allocates TMEM and issues tcgen05.mma (M=128, N=block_n, K=16) from one thread,
-//              accumulating in TMEM; tcgen05.commit releases smem stages / signals the epilogue.
-//   warps 2-5: epilogue.  tcgen05.ld the fp32 accumulator (one output pixel per thread), add bias,
-//              SiLU, optional residual, convert to fp16/bf16 and store 32-byte runs into the NHWC
-//              destination slice (which may be a channel window of a concat buffer).
+// Persistent kernel, one CTA per SM, static round-robin over 128 x block_n output tiles:
+//   warp 0     : TMA producer.  A tiles come from a 4-D im2col tensor map (the TMA engine walks 128
+//                output pixels, applies padding/stride and zero-fills the halo) or, for 1x1/s1 convs,
+//                from a 2-D tiled map; B tiles (weights) from a 2-D tiled map.  Both land in shared
+//                memory in the 32/64/128-byte swizzled K-major layout UMMA expects.  The producer
+//                runs ahead across tile boundaries, so the next tile's operands stream in while the
+//                current tile is still being multiplied / drained.
+//   warp 1     : allocates TMEM (two accumulator stages) and issues tcgen05.mma (M=128, N=block_n,
+//                K=16) from one thread; tcgen05.commit releases smem stages and publishes accumulators.
+//   warps 2-9  : two epilogue groups of 4 warps; group g drains accumulator stage g (tiles alternate),
+//                so one tile's epilogue overlaps the next tile's MMAs and the other group's epilogue.
+//                tcgen05.ld (one output pixel per thread) -> +bias -> SiLU -> (+residual) -> fp16/bf16
+//                -> swizzled shared-memory staging -> TMA store into the NHWC destination view (a
+//                channel window of a concat buffer is just a strided tensor map; ragged M is clipped
+//                by the TMA unit).
 #include "common.cuh"
 #include "conv_sm100.h"
 
@@ -25,7 +30,11 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;
+constexpr int kEpiGroups = 2;
+constexpr int kThreads = 64 + kEpiGroups * 128;
+constexpr int kStageBufBytes = 128 * 128;  // 128 rows x (up to) 64 columns x 2 B
+constexpr int kMaxBlockN = 256;
+constexpr size_t kSmemBudget = 222 * 1024;  // dynamic shared memory per CTA (227 KB limit minus static)
 
 struct ConvKernelParams {
   int M, Cout, block_n, block_k;
@@ -33,10 +42,11 @@ struct ConvKernelParams {
   int mode;  // 0: 2-D tiled rows (1x1 stride 1), 1: 4-D im2col
   int HoWo, Wo, stride, pad;
   int stages;
+  int n_tiles, num_tiles;
+  int store_cols;  // columns per TMA store box: 64 / 32 / 16
+  int bias_len;    // length of the (padded) bias vector
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, idesc;
   int act, is_bf16;
-  void* out;
-  int out_cstride;
   const float* bias;
   const void* residual;
   int res_cstride;
@@ -63,28 +73,30 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
   }
 }
 
+// 16 accumulator columns -> bias, activation, residual, convert; result as two 16-byte chunks.
 template <bool kBf16>
-__device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const uint32_t (&acc)[16],
-                                               long long row, int col) {
+__device__ __forceinline__ void finish16(const ConvKernelParams& p, const uint32_t (&acc)[16],
+                                         const float* __restrict__ s_bias, long long row, bool row_ok,
+                                         int col, uint4& o0, uint4& o1) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
-    v[j] = __uint_as_float(acc[j]) + __ldg(p.bias + col + j);
+    v[j] = __uint_as_float(acc[j]) + s_bias[j];
     if (p.act == YB_ACT_SILU) v[j] = silu(v[j]);
   }
-  if (p.residual != nullptr) {
+  if (p.residual != nullptr && row_ok && col < p.Cout) {
     const uint4* r = reinterpret_cast<const uint4*>(
         reinterpret_cast<const uint16_t*>(p.residual) + row * p.res_cstride + col);
-    uint4 r0 = __ldg(r), r1 = __ldg(r + 1);
+    const uint4 r0 = __ldg(r);
+    const uint4 r1 = (col + 8 < p.Cout) ? __ldg(r + 1) : make_uint4(0, 0, 0, 0);
     const uint32_t ru[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float2 f = unpack2<kBf16>(ru[j]);
+      const float2 f = unpack2<kBf16>(ru[j]);
       v[2 * j] += f.x;
       v[2 * j + 1] += f.y;
     }
   }
-  uint4 o0, o1;
   o0.x = pack2<kBf16>(v[0], v[1]);
   o0.y = pack2<kBf16>(v[2], v[3]);
   o0.z = pack2<kBf16>(v[4], v[5]);
@@ -93,43 +105,48 @@ __device__ __forceinline__ void epilogue_chunk(const ConvKernelParams& p, const 
   o1.y = pack2<kBf16>(v[10], v[11]);
   o1.z = pack2<kBf16>(v[12], v[13]);
   o1.w = pack2<kBf16>(v[14], v[15]);
-  uint16_t* dst = reinterpret_cast<uint16_t*>(p.out) + row * p.out_cstride + col;
-  const int rem = p.Cout - col;  // Cout is a multiple of 8
-  if (rem >= 16) {
-    reinterpret_cast<uint4*>(dst)[0] = o0;
-    reinterpret_cast<uint4*>(dst)[1] = o1;
-  } else if (rem >= 8) {
-    reinterpret_cast<uint4*>(dst)[0] = o0;
-  }
 }
 
-__global__ void __launch_bounds__(kThreads)
-conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
-                 const __grid_constant__ CUtensorMap tmap_b, const ConvKernelParams p) {
+// Physical 16-byte chunk index of logical chunk `j` in row `r` of a tile whose rows are `row_bytes`
+// long, under the TMA/UMMA swizzle of the same width (address bits [4,7) ^= bits [7,10), truncated).
+__device__ __forceinline__ int swizzle_chunk(int r, int j, int row_bytes) {
+  if (row_bytes == 128) return j ^ (r & 7);
+  if (row_bytes == 64) return j ^ ((r >> 1) & 3);
+  return j ^ ((r >> 2) & 1);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_out, const ConvKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t accum_bar;
+  __shared__ __align__(8) uint64_t acc_full[kEpiGroups];
+  __shared__ __align__(8) uint64_t acc_empty[kEpiGroups];
   __shared__ uint32_t tmem_base_slot;
+  __shared__ float s_bias[kEpiGroups][kMaxBlockN];
 
-  // Swizzled operand tiles need 1024-byte alignment.
+  // Swizzled tiles need 1024-byte alignment.
   uint8_t* tiles = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  uint8_t* staging = tiles + static_cast<size_t>(p.stages) * stage_bytes;  // [kEpiGroups][2][kStageBufBytes]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBlockM;
-  const int n0 = blockIdx.y * p.block_n;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_out);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&accum_bar, 1);
+    for (int g = 0; g < kEpiGroups; ++g) {
+      mbar_init(&acc_full[g], 1);
+      mbar_init(&acc_empty[g], 4);  // one arrival per epilogue warp of the group
+    }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -144,77 +161,129 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int cw = 0, ch = 0, cn = 0;
-      if (p.mode == 1) {
-        cn = m0 / p.HoWo;
-        const int rem = m0 - cn * p.HoWo;
-        const int ho = rem / p.Wo;
-        const int wo = rem - ho * p.Wo;
-        ch = ho * p.stride - p.pad;
-        cw = wo * p.stride - p.pad;
-      }
       const uint32_t tx_bytes = kBlockM * p.block_k * 2 + p.block_n * p.block_k * 2;
-      for (int it = 0; it < p.num_k_iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* a_dst = tiles + s * stage_bytes;
-        uint8_t* b_dst = a_dst + p.a_stage_bytes;
-        mbar_expect_tx(&full_bar[s], tx_bytes);
-        const int tap = it / p.chunks;
-        const int chunk = it - tap * p.chunks;
-        if (p.mode == 0) {
-          tma_load_2d(&tmap_a, &full_bar[s], a_dst, chunk * p.block_k, m0);
-        } else {
-          const int r = tap / p.ksize;
-          const int sx = tap - r * p.ksize;
-          tma_load_im2col_4d(&tmap_a, &full_bar[s], a_dst, chunk * p.block_k, cw, ch, cn,
-                             static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+      int kit = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        const int n0 = (tile - m_tile * p.n_tiles) * p.block_n;
+        const int m0 = m_tile * kBlockM;
+        int cw = 0, ch = 0, cn = 0;
+        if (p.mode == 1) {
+          cn = m0 / p.HoWo;
+          const int rem = m0 - cn * p.HoWo;
+          const int ho = rem / p.Wo;
+          const int wo = rem - ho * p.Wo;
+          ch = ho * p.stride - p.pad;
+          cw = wo * p.stride - p.pad;
         }
-        tma_load_2d(&tmap_b, &full_bar[s], b_dst, it * p.block_k, n0);
+        for (int it = 0; it < p.num_k_iters; ++it, ++kit) {
+          const int s = kit % p.stages;
+          const uint32_t ph = (kit / p.stages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          uint8_t* a_dst = tiles + s * stage_bytes;
+          uint8_t* b_dst = a_dst + p.a_stage_bytes;
+          mbar_expect_tx(&full_bar[s], tx_bytes);
+          const int tap = it / p.chunks;
+          const int chunk = it - tap * p.chunks;
+          if (p.mode == 0) {
+            tma_load_2d(&tmap_a, &full_bar[s], a_dst, chunk * p.block_k, m0);
+          } else {
+            const int r = tap / p.ksize;
+            const int sx = tap - r * p.ksize;
+            tma_load_im2col_4d(&tmap_a, &full_bar[s], a_dst, chunk * p.block_k, cw, ch, cn,
+                               static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+          }
+          tma_load_2d(&tmap_b, &full_bar[s], b_dst, it * p.block_k, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t row_bytes = p.block_k * 2;
-      for (int it = 0; it < p.num_k_iters; ++it) {
-        const int s = it % p.stages;
-        const uint32_t ph = (it / p.stages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      const int kk = p.block_k >> 4;
+      int kit = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+        const int as = lt & 1;
+        const uint32_t aph = (lt >> 1) & 1;
+        mbar_wait(&acc_empty[as], aph ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(tiles + s * stage_bytes);
-        const uint32_t b_addr = a_addr + p.a_stage_bytes;
-        const int kk = p.block_k >> 4;
-        for (int k = 0; k < kk; ++k) {
-          const uint64_t da = make_kmajor_desc(a_addr + k * 32, row_bytes);
-          const uint64_t db = make_kmajor_desc(b_addr + k * 32, row_bytes);
-          umma_f16(tmem_base, da, db, p.idesc, (it | k) != 0 ? 1u : 0u);
+        const uint32_t tmem_d = tmem_base + as * p.block_n;
+        for (int it = 0; it < p.num_k_iters; ++it, ++kit) {
+          const int s = kit % p.stages;
+          const uint32_t ph = (kit / p.stages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(tiles + s * stage_bytes);
+          const uint32_t b_addr = a_addr + p.a_stage_bytes;
+          for (int k = 0; k < kk; ++k) {
+            const uint64_t da = make_kmajor_desc(a_addr + k * 32, row_bytes);
+            const uint64_t db = make_kmajor_desc(b_addr + k * 32, row_bytes);
+            umma_f16(tmem_d, da, db, p.idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
         }
-        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+        umma_commit(&acc_full[as]);  // accumulator of this tile complete
       }
-      umma_commit(&accum_bar);  // accumulator complete
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    mbar_wait(&accum_bar, 0);
-    tc_fence_after();
-    const long long row = static_cast<long long>(m0) + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    for (int c = 0; c < p.block_n; c += 16) {
-      uint32_t acc[16];
-      tmem_ld_32x32b_x16(taddr + c, acc);
-      tmem_ld_wait();
-      const int col = n0 + c;
-      if (row_ok && col < p.Cout) {
-        if (p.is_bf16)
-          epilogue_chunk<true>(p, acc, row, col);
-        else
-          epilogue_chunk<false>(p, acc, row, col);
+    // ===================== epilogue groups (warps 2..9) =====================
+    const int g = (warp - 2) >> 2;   // group == accumulator stage it drains
+    const int q = warp & 3;          // TMEM lane quarter this warp may access
+    const int gtid = threadIdx.x - 64 - g * 128;
+    const int row_in_tile = q * 32 + lane;
+    const bool issuer = (gtid == 0);
+    const uint32_t bar_id = 1 + g;
+    const int row_bytes = p.store_cols * 2;
+    uint8_t* my_staging = staging + static_cast<size_t>(g) * 2 * kStageBufBytes;
+    float* bias_s = s_bias[g];
+    int lt = 0, store_idx = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+      if ((lt & 1) != g) continue;
+      const uint32_t aph = (lt >> 1) & 1;
+      const int m_tile = tile / p.n_tiles;
+      const int n0 = (tile - m_tile * p.n_tiles) * p.block_n;
+      const int m0 = m_tile * kBlockM;
+      const long long row = static_cast<long long>(m0) + row_in_tile;
+      const bool row_ok = row < p.M;
+      for (int i = gtid; i < p.block_n; i += 128) bias_s[i] = (n0 + i < p.bias_len) ? __ldg(p.bias + n0 + i) : 0.f;
+      named_bar_sync(bar_id, 128);
+      mbar_wait(&acc_full[g], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * p.block_n;
+      for (int c0 = 0; c0 < p.block_n; c0 += p.store_cols, ++store_idx) {
+        uint8_t* buf = my_staging + (store_idx & 1) * kStageBufBytes;
+        if (issuer) tma_store_wait_read<1>();  // the store that used this buffer two boxes ago has read it
+        named_bar_sync(bar_id, 128);
+        uint8_t* my_row = buf + row_in_tile * row_bytes;
+        for (int c = 0; c < p.store_cols; c += 16) {
+          uint32_t acc[16];
+          tmem_ld_32x32b_x16(taddr + c0 + c, acc);
+          tmem_ld_wait();
+          uint4 o0, o1;
+          if (p.is_bf16)
+            finish16<true>(p, acc, bias_s + c0 + c, row, row_ok, n0 + c0 + c, o0, o1);
+          else
+            finish16<false>(p, acc, bias_s + c0 + c, row, row_ok, n0 + c0 + c, o0, o1);
+          const int j = c >> 3;
+          *reinterpret_cast<uint4*>(my_row + swizzle_chunk(row_in_tile, j, row_bytes) * 16) = o0;
+          *reinterpret_cast<uint4*>(my_row + swizzle_chunk(row_in_tile, j + 1, row_bytes) * 16) = o1;
+        }
+        if (c0 + p.store_cols >= p.block_n) {
+          // all TMEM reads of this tile are done: hand the accumulator stage back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[g]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (issuer) {
+          if (n0 + c0 < p.Cout) tma_store_2d(&tmap_out, buf, n0 + c0, m0);
+          tma_store_commit();
+        }
       }
     }
+    if (issuer) tma_store_wait_all<0>();
   }
 
   tc_fence_before();
@@ -255,9 +324,9 @@ int load_driver_entry_points() {
   return YB_OK;
 }
 
-CUtensorMapSwizzle swizzle_for(int block_k) {
-  return block_k == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
-                       : (block_k == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
 uint32_t pow2_cols(int n) {
@@ -269,7 +338,7 @@ uint32_t pow2_cols(int n) {
 }  // namespace
 
 struct ConvOp {
-  CUtensorMap tmap_a, tmap_b;
+  CUtensorMap tmap_a, tmap_b, tmap_out;
   ConvKernelParams kp;
   dim3 grid;
   size_t smem_bytes;
@@ -304,8 +373,19 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
   ConvKernelParams& kp = op->kp;
   kp.M = static_cast<int>(M_ll);
   kp.Cout = d.Cout;
-  const int n_tiles = (d.Cout + 255) / 256;
-  kp.block_n = (((d.Cout + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
+  const int m_tiles = (kp.M + kBlockM - 1) / kBlockM;
+  const int sms = num_sms();
+  // N tile: the whole Cout up to 256 columns (fewest A re-reads); halve it when that leaves fewer
+  // than two tiles per SM so the persistent grid balances better.
+  int n_tiles = (d.Cout + kMaxBlockN - 1) / kMaxBlockN;
+  int block_n = (((d.Cout + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
+  if (m_tiles * n_tiles < 2 * sms && block_n > 128 && block_n % 32 == 0) {
+    block_n /= 2;
+    n_tiles = (d.Cout + block_n - 1) / block_n;
+  }
+  kp.block_n = block_n;
+  kp.n_tiles = n_tiles;
+  kp.num_tiles = m_tiles * n_tiles;
   kp.block_k = (d.Cin_pad % 64 == 0) ? 64 : ((d.Cin_pad % 32 == 0) ? 32 : 16);
   kp.ksize = d.ksize;
   kp.chunks = d.Cin_pad / kp.block_k;
@@ -315,38 +395,34 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
   kp.Wo = Wo;
   kp.stride = d.stride;
   kp.pad = d.pad;
+  kp.store_cols = (block_n % 64 == 0) ? 64 : ((block_n % 32 == 0) ? 32 : 16);
+  kp.bias_len = d.Cout_pad;
   kp.a_stage_bytes = kBlockM * kp.block_k * 2;
   kp.b_stage_bytes = (static_cast<uint32_t>(kp.block_n * kp.block_k * 2) + 1023u) & ~1023u;
   const uint32_t stage_bytes = kp.a_stage_bytes + kp.b_stage_bytes;
-  // Two CTAs per SM when four stages fit in ~100 KB (their epilogues overlap each other's
-  // main loops); otherwise one CTA with as many stages as fit.
-  int stages;
-  if (stage_bytes * 4 <= 100 * 1024) {
-    stages = static_cast<int>((100 * 1024) / stage_bytes);
-  } else {
-    stages = static_cast<int>((200 * 1024) / stage_bytes);
-  }
+  const size_t fixed = static_cast<size_t>(kEpiGroups) * 2 * kStageBufBytes + 1024;
+  int stages = static_cast<int>((kSmemBudget - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
-  if (stages > kp.num_k_iters) stages = kp.num_k_iters;
-  if (stages < 1) stages = 1;
+  if (stages < 2) stages = 2;
   kp.stages = stages;
-  kp.tmem_cols = pow2_cols(kp.block_n);
+  kp.tmem_cols = pow2_cols(2 * kp.block_n);
   kp.is_bf16 = d.dtype == YB_BF16;
   const uint32_t fmt = kp.is_bf16 ? 1u : 0u;
   kp.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(kp.block_n >> 3) << 17) |
              (static_cast<uint32_t>(kBlockM >> 4) << 24);
   kp.act = d.act;
-  kp.out = d.out;
-  kp.out_cstride = d.out_cstride;
   kp.bias = d.bias;
   kp.residual = d.residual;
   kp.res_cstride = d.res_cstride;
-  op->grid = dim3((kp.M + kBlockM - 1) / kBlockM, n_tiles, 1);
-  op->smem_bytes = static_cast<size_t>(stages) * stage_bytes + 1024;
+  op->grid = dim3(kp.num_tiles < sms ? kp.num_tiles : sms, 1, 1);
+  // >= 120 KB so that two CTAs can never share an SM (each owns up to all 512 TMEM columns)
+  size_t smem = static_cast<size_t>(stages) * stage_bytes + fixed;
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  op->smem_bytes = smem;
 
   const CUtensorMapDataType dt =
       kp.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  const CUtensorMapSwizzle sw = swizzle_for(kp.block_k);
+  const CUtensorMapSwizzle sw = swizzle_for_row_bytes(kp.block_k * 2);
   CUresult cr;
   if (kp.mode == 0) {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.Cin), static_cast<cuuint64_t>(kp.M)};
@@ -400,10 +476,25 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
       return YB_ERR_CUDA;
     }
   }
+  {
+    // destination view [M rows, Cout channels], row pitch = out_cstride; boxes of 128 rows x store_cols
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.Cout), static_cast<cuuint64_t>(kp.M)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.out_cstride) * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kp.store_cols), kBlockM};
+    cuuint32_t estr[2] = {1, 1};
+    cr = g_encode_tiled(&op->tmap_out, dt, 2, d.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle_for_row_bytes(kp.store_cols * 2), CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+      set_error("conv: cuTensorMapEncodeTiled (output) failed with CUresult %d", static_cast<int>(cr));
+      delete op;
+      return YB_ERR_CUDA;
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         220 * 1024);
+                                         static_cast<int>(kSmemBudget));
     if (e != cudaSuccess) {
       set_error("conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       delete op;
@@ -416,7 +507,8 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
 }
 
 int conv_op_launch(const ConvOp* op, cudaStream_t stream) {
-  conv_umma_kernel<<<op->grid, kThreads, op->smem_bytes, stream>>>(op->tmap_a, op->tmap_b, op->kp);
+  conv_umma_kernel<<<op->grid, kThreads, op->smem_bytes, stream>>>(op->tmap_a, op->tmap_b, op->tmap_out,
+                                                                  op->kp);
   YB_CHECK_CUDA(cudaGetLastError());
   return YB_OK;
 }

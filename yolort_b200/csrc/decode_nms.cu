@@ -27,7 +27,8 @@
 namespace yb {
 namespace {
 
-constexpr int kNmsThreads = 1024;
+constexpr int kNmsThreads = 512;
+constexpr int kSweep = 512;       // candidates consumed per sweep round (== threads)
 constexpr int kSmallSort = 4096;  // keys sorted in shared memory
 
 __device__ __forceinline__ uint32_t orderable_desc(float f) {
@@ -84,57 +85,91 @@ struct Workspace {
   long long* status;   // [4] scratch status block (used when the caller passes none)
 };
 
+// One thread tests one anchor's objectness; the warp then scans the classes of every passing anchor
+// cooperatively (lane k <-> class k, coalesced 2-byte/4-byte loads) and appends candidates with one
+// aggregated atomic per 32 classes.
 template <typename T>
 __global__ void decode_candidates_kernel(const __grid_constant__ DecodeParams p, Workspace ws) {
   const long long gid = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(p.n_images) * p.anchors_per_image;
-  if (gid >= total) return;
-  const int img = static_cast<int>(gid / p.anchors_per_image);
-  const int anchor = static_cast<int>(gid - static_cast<long long>(img) * p.anchors_per_image);
-  int l = 0;
+  const int lane = threadIdx.x & 31;
+  bool pass = false;
+  int img = 0, anchor = 0, l = 0, x = 0, y = 0, a = 0;
+  long long off = 0;
+  float obj = 0.f;
+  if (gid < total) {
+    img = static_cast<int>(gid / p.anchors_per_image);
+    anchor = static_cast<int>(gid - static_cast<long long>(img) * p.anchors_per_image);
 #pragma unroll
-  for (int i = 1; i < YB_MAX_LEVELS; ++i)
-    if (i < p.n_levels && anchor >= p.lvl_start[i]) l = i;
-  const yb_head_level& L = p.lvl[l];
-  int r = anchor - p.lvl_start[l];
-  const int x = r % L.W;
-  r /= L.W;
-  const int y = r % L.H;
-  const int a = r / L.H;
-  const long long off = img * L.stride_n + a * L.stride_a + y * L.stride_y + x * L.stride_x;
-
-  const float obj = sigmoidf_ref(ld_logit<T>(L.logits, off + 4));
-  if (!(obj > p.score_thresh)) return;  // score = cls*obj <= obj
-
-  bool have_box = false;
-  for (int k = 0; k < p.n_classes; ++k) {
-    const float cls = sigmoidf_ref(ld_logit<T>(L.logits, off + 5 + k));
-    const float score = __fmul_rn(cls, obj);
-    if (!(score > p.score_thresh)) continue;
-    if (!have_box) {
-      have_box = true;
-      const float sx = sigmoidf_ref(ld_logit<T>(L.logits, off + 0));
-      const float sy = sigmoidf_ref(ld_logit<T>(L.logits, off + 1));
-      const float sw = sigmoidf_ref(ld_logit<T>(L.logits, off + 2));
-      const float sh = sigmoidf_ref(ld_logit<T>(L.logits, off + 3));
-      // _utils.py:59-60 in the reference's op order: (y*2 - 0.5 + grid) * stride ; (y*2)**2 * anchor
-      const float cx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.0f), 0.5f), static_cast<float>(x)), L.stride_px);
-      const float cy = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.0f), 0.5f), static_cast<float>(y)), L.stride_px);
-      const float tw = __fmul_rn(sw, 2.0f), th = __fmul_rn(sh, 2.0f);
-      const float w = __fmul_rn(__fmul_rn(tw, tw), L.anchors_px[2 * a]);
-      const float h = __fmul_rn(__fmul_rn(th, th), L.anchors_px[2 * a + 1]);
-      // torchvision box_convert cxcywh -> xyxy
-      const float hw = __fmul_rn(0.5f, w), hh = __fmul_rn(0.5f, h);
-      const float4 b = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
-      ws.boxes[static_cast<long long>(img) * p.anchors_per_image + anchor] = b;
-      const float m = fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w));
-      atomicMax(&ws.img_maxc[img], float_to_ordered_int(m));
+    for (int i = 1; i < YB_MAX_LEVELS; ++i)
+      if (i < p.n_levels && anchor >= p.lvl_start[i]) l = i;
+    const yb_head_level& L = p.lvl[l];
+    int r = anchor - p.lvl_start[l];
+    x = r % L.W;
+    r /= L.W;
+    y = r % L.H;
+    a = r / L.H;
+    off = img * L.stride_n + a * L.stride_a + y * L.stride_y + x * L.stride_x;
+    obj = sigmoidf_ref(ld_logit<T>(L.logits, off + 4));
+    pass = obj > p.score_thresh;  // score = cls*obj <= obj, so failing anchors cannot yield candidates
+  }
+  uint32_t todo = __ballot_sync(0xffffffffu, pass);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int s_img = __shfl_sync(0xffffffffu, img, src);
+    const int s_anchor = __shfl_sync(0xffffffffu, anchor, src);
+    const int s_l = __shfl_sync(0xffffffffu, l, src);
+    const int s_x = __shfl_sync(0xffffffffu, x, src);
+    const int s_y = __shfl_sync(0xffffffffu, y, src);
+    const int s_a = __shfl_sync(0xffffffffu, a, src);
+    const long long s_off = __shfl_sync(0xffffffffu, off, src);
+    const float s_obj = __shfl_sync(0xffffffffu, obj, src);
+    const yb_head_level& L = p.lvl[s_l];
+    bool any = false;
+    for (int k0 = 0; k0 < p.n_classes; k0 += 32) {
+      const int k = k0 + lane;
+      float score = 0.f;
+      bool cand = false;
+      if (k < p.n_classes) {
+        const float cls = sigmoidf_ref(ld_logit<T>(L.logits, s_off + 5 + k));
+        score = __fmul_rn(cls, s_obj);
+        cand = score > p.score_thresh;
+      }
+      const uint32_t cm = __ballot_sync(0xffffffffu, cand);
+      if (cm == 0) continue;
+      any = true;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&ws.img_count[s_img], __popc(cm));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (cand) {
+        const int slot = base + __popc(cm & ((1u << lane) - 1u));
+        if (slot < p.cap_per_image) {
+          const uint64_t key = (static_cast<uint64_t>(orderable_desc(score)) << 32) |
+                               static_cast<uint32_t>(s_anchor * p.n_classes + k);
+          ws.keys_a[static_cast<long long>(s_img) * p.cap_per_image + slot] = key;
+        }
+      }
     }
-    const int slot = atomicAdd(&ws.img_count[img], 1);
-    if (slot < p.cap_per_image) {
-      const uint64_t key = (static_cast<uint64_t>(orderable_desc(score)) << 32) |
-                           static_cast<uint32_t>(anchor * p.n_classes + k);
-      ws.keys_a[static_cast<long long>(img) * p.cap_per_image + slot] = key;
+    if (any) {
+      // box of this anchor: lanes 0..3 fetch tx,ty,tw,th
+      float t = 0.f;
+      if (lane < 4) t = sigmoidf_ref(ld_logit<T>(L.logits, s_off + lane));
+      const float sx = __shfl_sync(0xffffffffu, t, 0), sy = __shfl_sync(0xffffffffu, t, 1);
+      const float sw = __shfl_sync(0xffffffffu, t, 2), sh = __shfl_sync(0xffffffffu, t, 3);
+      if (lane == 0) {
+        // _utils.py:59-60 in the reference's op order: (y*2 - 0.5 + grid) * stride ; (y*2)**2 * anchor
+        const float cx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.0f), 0.5f), static_cast<float>(s_x)), L.stride_px);
+        const float cy = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.0f), 0.5f), static_cast<float>(s_y)), L.stride_px);
+        const float tw = __fmul_rn(sw, 2.0f), th = __fmul_rn(sh, 2.0f);
+        const float w = __fmul_rn(__fmul_rn(tw, tw), L.anchors_px[2 * s_a]);
+        const float h = __fmul_rn(__fmul_rn(th, th), L.anchors_px[2 * s_a + 1]);
+        // torchvision box_convert cxcywh -> xyxy
+        const float hw = __fmul_rn(0.5f, w), hh = __fmul_rn(0.5f, h);
+        const float4 b = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+        ws.boxes[static_cast<long long>(s_img) * p.anchors_per_image + s_anchor] = b;
+        atomicMax(&ws.img_maxc[s_img], float_to_ordered_int(fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
+      }
     }
   }
 }
@@ -204,7 +239,8 @@ __device__ uint64_t* block_radix_sort(uint64_t* a, uint64_t* b, int count, uint3
   __shared__ int s_skip;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  for (int i = tid; i < 32 * 256; i += blockDim.x) wcnt[i] = 0;
+  const int nwarps = blockDim.x >> 5;
+  for (int i = tid; i < nwarps * 256; i += blockDim.x) wcnt[i] = 0;
   for (int pass = 0; pass < 8; ++pass) {
     const int shift = pass * 8;
     if (tid < 256) hist[tid] = 0;
@@ -249,9 +285,9 @@ __device__ uint64_t* block_radix_sort(uint64_t* a, uint64_t* b, int count, uint3
       const bool leader = valid && rank == 0;
       if (leader) wcnt[warp * 256 + d] = __popc(peers);
       __syncthreads();
-      if (tid < 256) {  // per-digit exclusive scan across the 32 warps, continuing the running base
+      if (tid < 256) {  // per-digit exclusive scan across the warps, continuing the running base
         uint32_t run = base[tid];
-        for (int w = 0; w < 32; ++w) {
+        for (int w = 0; w < nwarps; ++w) {
           const uint32_t t = wcnt[w * 256 + tid];
           wcnt[w * 256 + tid] = run;
           run += t;
@@ -262,7 +298,7 @@ __device__ uint64_t* block_radix_sort(uint64_t* a, uint64_t* b, int count, uint3
       if (valid) b[wcnt[warp * 256 + d] + rank] = key;
       __syncthreads();
       if (tid < 256) {
-        for (int w = 0; w < 32; ++w) wcnt[w * 256 + tid] = 0;
+        for (int w = 0; w < nwarps; ++w) wcnt[w * 256 + tid] = 0;
       }
       __syncthreads();
     }
@@ -274,24 +310,35 @@ __device__ uint64_t* block_radix_sort(uint64_t* a, uint64_t* b, int count, uint3
   return a;
 }
 
+// Greedy sweep of one image.  Candidates (already sorted) are consumed kSweep at a time:
+//   A. every thread tests its candidate against the kept list (<= max_det boxes, shared memory);
+//   B. survivors are compacted in order and their pairwise suppression bit-matrix is built in parallel;
+//   C. warp 0 walks the survivors in order with the bit-matrix (one 32-bit word of the "removed" set per
+//      lane, warp shuffles only) -- the sequential part costs ~20 cycles per survivor;
+//   D. kept survivors are appended to the kept list / written out in parallel.
 __global__ void __launch_bounds__(kNmsThreads)
 nms_image_kernel(const NmsParams p, Workspace ws) {
   extern __shared__ __align__(16) uint8_t dyn_smem[];
-  // layout: [sort region 36 KB: 4096 keys | radix scratch] [kept boxes max_det*16] [kept areas] [kept labels]
+  // layout: [sort region 36 KB: 4096 keys | radix scratch] [survivors] [bit matrix] [kept list]
   uint64_t* s_keys = reinterpret_cast<uint64_t*>(dyn_smem);
   uint32_t* s_scratch = reinterpret_cast<uint32_t*>(dyn_smem);
-  float4* k_box = reinterpret_cast<float4*>(dyn_smem + 36 * 1024);
+  float4* sv_box = reinterpret_cast<float4*>(dyn_smem + 36 * 1024);          // [kSweep] (offset) boxes
+  float4* sv_obox = sv_box + kSweep;                                          // [kSweep] original boxes
+  float* sv_area = reinterpret_cast<float*>(sv_obox + kSweep);                // [kSweep]
+  float* sv_score = sv_area + kSweep;                                         // [kSweep]
+  int* sv_label = reinterpret_cast<int*>(sv_score + kSweep);                  // [kSweep]
+  uint32_t* sv_cidx = reinterpret_cast<uint32_t*>(sv_label + kSweep);         // [kSweep]
+  uint32_t* s_mask = sv_cidx + kSweep;                                        // [kSweep][kSweep/32]
+  float4* k_box = reinterpret_cast<float4*>(s_mask + kSweep * (kSweep / 32)); // [max_det]
   float* k_area = reinterpret_cast<float*>(k_box + p.max_det);
   int* k_label = reinterpret_cast<int*>(k_area + p.max_det);
-  __shared__ int s_kcount, s_first, s_warp_first[32];
-  __shared__ float4 s_pick_box;
-  __shared__ float s_pick_area;
-  __shared__ int s_pick_label;
+  __shared__ int s_kcount, s_warp_tot[kNmsThreads / 32], s_nsurv, s_newkept;
+  __shared__ uint32_t s_keep[kSweep / 32];
 
   const int img = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long raw_count = ws.img_count[img];
-  int count = static_cast<int>(raw_count < p.cap_per_image ? raw_count : p.cap_per_image);
+  const int count = static_cast<int>(raw_count < p.cap_per_image ? raw_count : p.cap_per_image);
   if (tid == 0) {
     atomicAdd(reinterpret_cast<unsigned long long*>(&p.status[0]), static_cast<unsigned long long>(raw_count));
     atomicMax(reinterpret_cast<unsigned long long*>(&p.status[2]), static_cast<unsigned long long>(raw_count));
@@ -318,7 +365,6 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
   }
   __syncthreads();
 
-  // semantics for this image
   bool trick;
   if (p.semantics == YB_NMS_TV_AUTO)
     trick = static_cast<long long>(count) * 4 <= 4000;  // torchvision: boxes.numel() > 4000 -> per-class
@@ -333,8 +379,10 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
     padx = p.rescale[img * 3 + 1];
     pady = p.rescale[img * 3 + 2];
   }
+  const uint32_t lt_mask = (1u << lane) - 1u;
 
-  for (int base = 0; base < count; base += blockDim.x) {
+  for (int base = 0; base < count; base += kSweep) {
+    // ---- A: fetch + test against the kept list ----
     const int j = base + tid;
     bool alive = j < count;
     float4 box = make_float4(0.f, 0.f, 0.f, 0.f), nbox = box;
@@ -368,54 +416,91 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
         }
       }
     }
-    // resolve the survivors of this batch in candidate order
-    while (true) {
-      const uint32_t bal = __ballot_sync(0xffffffffu, alive);
-      if (lane == 0) s_warp_first[warp] = bal ? (warp * 32 + __ffs(bal) - 1) : 0x7fffffff;
-      __syncthreads();
-      if (warp == 0) {
-        int v = s_warp_first[lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
-        if (lane == 0) s_first = v;
-      }
-      __syncthreads();
-      const int first = s_first;
-      if (first == 0x7fffffff) break;
-      if (tid == first) {
-        const int slot = s_kcount;
-        k_box[slot] = nbox;
-        k_area[slot] = area;
-        k_label[slot] = label;
-        s_pick_box = nbox;
-        s_pick_area = area;
-        s_pick_label = label;
-        // emit the detection
-        const long long o = static_cast<long long>(img) * p.max_det + slot;
-        if (p.explicit_mode) {
-          p.out_keep[slot] = static_cast<int64_t>(cidx);
-        } else {
-          float4 ob = box;
-          if (p.rescale) {  // transform.py:362-365: (x - pad) / gain, fp32, no clipping
-            ob.x = __fdiv_rn(__fsub_rn(box.x, padx), gain);
-            ob.z = __fdiv_rn(__fsub_rn(box.z, padx), gain);
-            ob.y = __fdiv_rn(__fsub_rn(box.y, pady), gain);
-            ob.w = __fdiv_rn(__fsub_rn(box.w, pady), gain);
-          }
-          reinterpret_cast<float4*>(p.out_boxes)[o] = ob;
-          p.out_scores[o] = score;
-          p.out_labels[o] = static_cast<int64_t>(label);
-        }
-        s_kcount = slot + 1;
-        alive = false;
-      }
-      __syncthreads();
-      if (s_kcount >= p.max_det) break;
-      if (alive && (trick || s_pick_label == label) &&
-          iou_over(s_pick_box, s_pick_area, nbox, area, p.iou_thresh))
-        alive = false;
-      __syncthreads();
+    // ---- B: order-preserving compaction of the survivors ----
+    const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0) s_warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    int pos = __popc(bal & lt_mask);
+    for (int w = 0; w < warp; ++w) pos += s_warp_tot[w];
+    if (tid == 0) {
+      int t = 0;
+      for (int w = 0; w < kNmsThreads / 32; ++w) t += s_warp_tot[w];
+      s_nsurv = t;
     }
+    if (alive) {
+      sv_box[pos] = nbox;
+      sv_obox[pos] = box;
+      sv_area[pos] = area;
+      sv_score[pos] = score;
+      sv_label[pos] = label;
+      sv_cidx[pos] = cidx;
+    }
+    if (tid < kSweep / 32) s_keep[tid] = 0;
+    __syncthreads();
+    const int S = s_nsurv;
+    const int nwords = (S + 31) >> 5;
+    // suppression bit-matrix: bit j of row i set iff survivor i (if kept) suppresses survivor j > i
+    if (tid < S) {
+      const float4 bi = sv_box[tid];
+      const float ai = sv_area[tid];
+      const int li = sv_label[tid];
+      for (int w = 0; w < nwords; ++w) {
+        uint32_t bits = 0;
+        const int j0 = w << 5;
+        if (j0 + 31 > tid) {
+          const int jend = min(32, S - j0);
+          for (int b = 0; b < jend; ++b) {
+            const int jj = j0 + b;
+            if (jj > tid && (trick || sv_label[jj] == li) && iou_over(bi, ai, sv_box[jj], sv_area[jj], p.iou_thresh))
+              bits |= 1u << b;
+          }
+        }
+        s_mask[tid * (kSweep / 32) + w] = bits;
+      }
+    }
+    __syncthreads();
+    // ---- C: sequential resolution by warp 0 ----
+    if (warp == 0) {
+      uint32_t removed = 0, keep = 0;   // lane l owns word l of both sets (S <= 512 -> 16 words)
+      int kc = s_kcount;
+      const int kc0 = kc;
+      for (int i = 0; i < S; ++i) {
+        const uint32_t word = __shfl_sync(0xffffffffu, removed, i >> 5);
+        if ((word >> (i & 31)) & 1u) continue;
+        if (lane == (i >> 5)) keep |= 1u << (i & 31);
+        if (lane < nwords) removed |= s_mask[i * (kSweep / 32) + lane];
+        if (++kc >= p.max_det) break;
+      }
+      if (lane < kSweep / 32) s_keep[lane] = keep;
+      if (lane == 0) s_newkept = kc - kc0;
+    }
+    __syncthreads();
+    // ---- D: append the kept survivors ----
+    if (tid < S && ((s_keep[tid >> 5] >> (tid & 31)) & 1u)) {
+      int rank = __popc(s_keep[tid >> 5] & ((1u << (tid & 31)) - 1u));
+      for (int w = 0; w < (tid >> 5); ++w) rank += __popc(s_keep[w]);
+      const int slot = s_kcount + rank;
+      k_box[slot] = sv_box[tid];
+      k_area[slot] = sv_area[tid];
+      k_label[slot] = sv_label[tid];
+      const long long o = static_cast<long long>(img) * p.max_det + slot;
+      if (p.explicit_mode) {
+        p.out_keep[slot] = static_cast<int64_t>(sv_cidx[tid]);
+      } else {
+        float4 ob = sv_obox[tid];
+        if (p.rescale) {  // transform.py:362-365: (x - pad) / gain, fp32, no clipping
+          ob.x = __fdiv_rn(__fsub_rn(ob.x, padx), gain);
+          ob.z = __fdiv_rn(__fsub_rn(ob.z, padx), gain);
+          ob.y = __fdiv_rn(__fsub_rn(ob.y, pady), gain);
+          ob.w = __fdiv_rn(__fsub_rn(ob.w, pady), gain);
+        }
+        reinterpret_cast<float4*>(p.out_boxes)[o] = ob;
+        p.out_scores[o] = sv_score[tid];
+        p.out_labels[o] = static_cast<int64_t>(sv_label[tid]);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_kcount += s_newkept;
     __syncthreads();
     if (s_kcount >= p.max_det) break;
   }
@@ -461,7 +546,10 @@ size_t carve(Workspace& ws, uint8_t* base, int n, long long cap, long long ancho
   return off;
 }
 
-size_t nms_smem_bytes(int max_det) { return 36 * 1024 + static_cast<size_t>(max_det) * (16 + 4 + 4); }
+size_t nms_smem_bytes(int max_det) {
+  return 36 * 1024 + static_cast<size_t>(kSweep) * (16 + 16 + 4 + 4 + 4 + 4) + static_cast<size_t>(kSweep) * (kSweep / 32) * 4 +
+         static_cast<size_t>(max_det) * (16 + 4 + 4);
+}
 
 int ensure_nms_smem(size_t bytes) {
   static size_t configured = 0;

@@ -66,6 +66,53 @@ __global__ void spp_pool_kernel(const uint16_t* __restrict__ in, int in_cs, uint
   *reinterpret_cast<uint4*>(o + 2 * C) = m13;
 }
 
+// SPPF-style cascade in shared memory: mp9 = mp5(mp5(x)), mp13 = mp5(mp9) (exactly equal to the direct
+// windows with -inf padding, yolort/v5/models/common.py:196).  One CTA owns one (image, channel-octet)
+// plane: 3 planes of H*W 16-byte pixels in shared memory, separable 5-tap max (rows then columns).
+template <bool kBf16>
+__global__ void spp_pool_cascade_kernel(const uint16_t* __restrict__ in, int in_cs, uint16_t* __restrict__ out,
+                                        int out_cs, int H, int W, int C) {
+  extern __shared__ __align__(16) uint8_t pool_smem[];
+  const int c8n = C >> 3;
+  const int n = blockIdx.x / c8n;
+  const int c8 = blockIdx.x - n * c8n;
+  const int HW = H * W;
+  uint4* cur = reinterpret_cast<uint4*>(pool_smem);
+  uint4* tmp = cur + HW;
+  uint4* nxt = tmp + HW;
+  const uint16_t* src = in + static_cast<long long>(n) * HW * in_cs + c8 * 8;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x)
+    cur[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(i) * in_cs));
+  __syncthreads();
+  uint16_t* dst = out + static_cast<long long>(n) * HW * out_cs + c8 * 8;
+  for (int level = 0; level < 3; ++level) {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {  // horizontal 5-tap
+      const int y = i / W, x = i - y * W;
+      uint4 m = cur[i];
+      for (int dx = -2; dx <= 2; ++dx) {
+        const int xx = x + dx;
+        if (dx != 0 && xx >= 0 && xx < W) max8<kBf16>(m, cur[y * W + xx]);
+      }
+      tmp[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {  // vertical 5-tap
+      const int y = i / W, x = i - y * W;
+      uint4 m = tmp[i];
+      for (int dy = -2; dy <= 2; ++dy) {
+        const int yy = y + dy;
+        if (dy != 0 && yy >= 0 && yy < H) max8<kBf16>(m, tmp[yy * W + x]);
+      }
+      nxt[i] = m;
+      *reinterpret_cast<uint4*>(dst + static_cast<long long>(i) * out_cs + level * C) = m;
+    }
+    __syncthreads();
+    uint4* t = cur;
+    cur = nxt;
+    nxt = t;
+  }
+}
+
 __global__ void upsample2x_kernel(const uint16_t* __restrict__ in, int in_cs, uint16_t* __restrict__ out,
                                   int out_cs, int N, int H, int W, int C) {
   const int c8n = C >> 3;
@@ -101,6 +148,30 @@ int validate_pool_or_upsample(const yb_op_desc& d) {
 }
 
 int spp_pool_launch(const yb_op_desc& d, cudaStream_t stream) {
+  const size_t plane_smem = static_cast<size_t>(d.H) * d.W * 16 * 3;
+  if (plane_smem <= 200 * 1024) {
+    static size_t configured[2] = {48 * 1024, 48 * 1024};
+    const int bf = d.dtype == YB_BF16 ? 1 : 0;
+    if (plane_smem > configured[bf]) {
+      if (bf)
+        YB_CHECK_CUDA(cudaFuncSetAttribute(spp_pool_cascade_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(plane_smem)));
+      else
+        YB_CHECK_CUDA(cudaFuncSetAttribute(spp_pool_cascade_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(plane_smem)));
+      configured[bf] = plane_smem;
+    }
+    const unsigned blocks = static_cast<unsigned>(d.N) * (d.Cin >> 3);
+    if (bf)
+      spp_pool_cascade_kernel<true><<<blocks, 256, plane_smem, stream>>>(
+          static_cast<const uint16_t*>(d.in), d.in_cstride, static_cast<uint16_t*>(d.out), d.out_cstride, d.H, d.W, d.Cin);
+    else
+      spp_pool_cascade_kernel<false><<<blocks, 256, plane_smem, stream>>>(
+          static_cast<const uint16_t*>(d.in), d.in_cstride, static_cast<uint16_t*>(d.out), d.out_cstride, d.H, d.W, d.Cin);
+    YB_CHECK_CUDA(cudaGetLastError());
+    return YB_OK;
+  }
+  // very large planes: direct 13x13 window per thread
   const long long total = static_cast<long long>(d.N) * d.H * d.W * (d.Cin >> 3);
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((total + threads - 1) / threads);
