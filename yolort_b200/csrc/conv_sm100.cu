@@ -29,7 +29,7 @@ namespace yb {
 namespace {
 
 constexpr int kBlockM = 128;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
 constexpr int kEpiGroups = 2;
 constexpr int kThreads = 64 + kEpiGroups * 128;
 constexpr int kStageBufBytes = 128 * 128;  // 128 rows x (up to) 64 columns x 2 B
@@ -42,6 +42,9 @@ struct ConvKernelParams {
   int mode;  // 0: 2-D tiled rows (1x1 stride 1), 1: 4-D im2col
   int HoWo, Wo, stride, pad;
   int stages;
+  int kpg;         // k-iterations (A/B sub-tiles) carried by one pipeline stage
+  int b_resident;  // weights of the (single) N tile stay in shared memory for the CTA's lifetime
+  uint32_t b_res_bytes;
   int n_tiles, num_tiles;
   int store_cols;  // columns per TMA store box: 64 / 32 / 16
   int bias_len;    // length of the (padded) bias vector
@@ -123,14 +126,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t acc_full[kEpiGroups];
   __shared__ __align__(8) uint64_t acc_empty[kEpiGroups];
+  __shared__ __align__(8) uint64_t b_full;
   __shared__ uint32_t tmem_base_slot;
   __shared__ float s_bias[kEpiGroups][kMaxBlockN];
 
   // Swizzled tiles need 1024-byte alignment.
   uint8_t* tiles = reinterpret_cast<uint8_t*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const uint32_t stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
-  uint8_t* staging = tiles + static_cast<size_t>(p.stages) * stage_bytes;  // [kEpiGroups][2][kStageBufBytes]
+  // stage = kpg A sub-tiles followed (unless the weights are resident) by kpg B sub-tiles
+  const uint32_t stage_bytes = p.kpg * (p.a_stage_bytes + (p.b_resident ? 0u : p.b_stage_bytes));
+  uint8_t* b_res = tiles + static_cast<size_t>(p.stages) * stage_bytes;   // resident weights (optional)
+  uint8_t* staging = b_res + p.b_res_bytes;                                // [kEpiGroups][2][kStageBufBytes]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -143,6 +149,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    mbar_init(&b_full, 1);
     for (int g = 0; g < kEpiGroups; ++g) {
       mbar_init(&acc_full[g], 1);
       mbar_init(&acc_empty[g], 4);  // one arrival per epilogue warp of the group
@@ -161,7 +168,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      const uint32_t tx_bytes = kBlockM * p.block_k * 2 + p.block_n * p.block_k * 2;
+      const uint32_t a_bytes = kBlockM * p.block_k * 2, b_bytes = p.block_n * p.block_k * 2;
+      if (p.b_resident) {
+        mbar_expect_tx(&b_full, p.num_k_iters * b_bytes);
+        for (int it = 0; it < p.num_k_iters; ++it)
+          tma_load_2d(&tmap_b, &b_full, b_res + it * p.b_stage_bytes, it * p.block_k, 0);
+      }
       int kit = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles;
@@ -176,24 +188,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           ch = ho * p.stride - p.pad;
           cw = wo * p.stride - p.pad;
         }
-        for (int it = 0; it < p.num_k_iters; ++it, ++kit) {
+        for (int it0 = 0; it0 < p.num_k_iters; it0 += p.kpg, ++kit) {
+          const int cnt = min(p.kpg, p.num_k_iters - it0);
           const int s = kit % p.stages;
           const uint32_t ph = (kit / p.stages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* a_dst = tiles + s * stage_bytes;
-          uint8_t* b_dst = a_dst + p.a_stage_bytes;
-          mbar_expect_tx(&full_bar[s], tx_bytes);
-          const int tap = it / p.chunks;
-          const int chunk = it - tap * p.chunks;
-          if (p.mode == 0) {
-            tma_load_2d(&tmap_a, &full_bar[s], a_dst, chunk * p.block_k, m0);
-          } else {
-            const int r = tap / p.ksize;
-            const int sx = tap - r * p.ksize;
-            tma_load_im2col_4d(&tmap_a, &full_bar[s], a_dst, chunk * p.block_k, cw, ch, cn,
-                               static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+          uint8_t* b_dst = a_dst + p.kpg * p.a_stage_bytes;
+          mbar_expect_tx(&full_bar[s], cnt * (a_bytes + (p.b_resident ? 0u : b_bytes)));
+          for (int j = 0; j < cnt; ++j) {
+            const int it = it0 + j;
+            const int tap = it / p.chunks;
+            const int chunk = it - tap * p.chunks;
+            if (p.mode == 0) {
+              tma_load_2d(&tmap_a, &full_bar[s], a_dst + j * p.a_stage_bytes, chunk * p.block_k, m0);
+            } else {
+              const int r = tap / p.ksize;
+              const int sx = tap - r * p.ksize;
+              tma_load_im2col_4d(&tmap_a, &full_bar[s], a_dst + j * p.a_stage_bytes, chunk * p.block_k, cw, ch, cn,
+                                 static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+            }
+            if (!p.b_resident) tma_load_2d(&tmap_b, &full_bar[s], b_dst + j * p.b_stage_bytes, it * p.block_k, n0);
           }
-          tma_load_2d(&tmap_b, &full_bar[s], b_dst, it * p.block_k, n0);
         }
       }
     }
@@ -202,6 +218,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       const uint32_t row_bytes = p.block_k * 2;
       const int kk = p.block_k >> 4;
+      if (p.b_resident) {
+        mbar_wait(&b_full, 0);
+        tc_fence_after();
+      }
+      const uint32_t b_res_addr = smem_u32(b_res);
       int kit = 0, lt = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
         const int as = lt & 1;
@@ -209,17 +230,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_wait(&acc_empty[as], aph ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * p.block_n;
-        for (int it = 0; it < p.num_k_iters; ++it, ++kit) {
+        for (int it0 = 0; it0 < p.num_k_iters; it0 += p.kpg, ++kit) {
+          const int cnt = min(p.kpg, p.num_k_iters - it0);
           const int s = kit % p.stages;
           const uint32_t ph = (kit / p.stages) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(tiles + s * stage_bytes);
-          const uint32_t b_addr = a_addr + p.a_stage_bytes;
-          for (int k = 0; k < kk; ++k) {
-            const uint64_t da = make_kmajor_desc(a_addr + k * 32, row_bytes);
-            const uint64_t db = make_kmajor_desc(b_addr + k * 32, row_bytes);
-            umma_f16(tmem_d, da, db, p.idesc, (it | k) != 0 ? 1u : 0u);
+          const uint32_t a_base = smem_u32(tiles + s * stage_bytes);
+          const uint32_t b_base = a_base + p.kpg * p.a_stage_bytes;
+          for (int j = 0; j < cnt; ++j) {
+            const uint32_t a_addr = a_base + j * p.a_stage_bytes;
+            const uint32_t b_addr = p.b_resident ? b_res_addr + (it0 + j) * p.b_stage_bytes : b_base + j * p.b_stage_bytes;
+            for (int k = 0; k < kk; ++k) {
+              const uint64_t da = make_kmajor_desc(a_addr + k * 32, row_bytes);
+              const uint64_t db = make_kmajor_desc(b_addr + k * 32, row_bytes);
+              umma_f16(tmem_d, da, db, p.idesc, (it0 | j | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
         }
@@ -399,9 +425,24 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
   kp.bias_len = d.Cout_pad;
   kp.a_stage_bytes = kBlockM * kp.block_k * 2;
   kp.b_stage_bytes = (static_cast<uint32_t>(kp.block_n * kp.block_k * 2) + 1023u) & ~1023u;
-  const uint32_t stage_bytes = kp.a_stage_bytes + kp.b_stage_bytes;
   const size_t fixed = static_cast<size_t>(kEpiGroups) * 2 * kStageBufBytes + 1024;
-  int stages = static_cast<int>((kSmemBudget - fixed) / stage_bytes);
+  // Weights stay resident in shared memory when the layer has a single N tile and they are small:
+  // the persistent CTA then streams only activations (halves the L2->SM traffic of the shallow layers).
+  const size_t b_total = static_cast<size_t>(kp.num_k_iters) * kp.b_stage_bytes;
+  kp.b_resident = (n_tiles == 1 && b_total <= 80 * 1024) ? 1 : 0;
+  kp.b_res_bytes = kp.b_resident ? static_cast<uint32_t>(b_total) : 0u;
+  // k-iterations per pipeline stage: aim at ~32 KB per stage so that one mbarrier round trip moves
+  // enough bytes (a 16-channel tap is only 4 KB), in near-equal groups.
+  const uint32_t per_iter = kp.a_stage_bytes + (kp.b_resident ? 0u : kp.b_stage_bytes);
+  const size_t avail = kSmemBudget - fixed - kp.b_res_bytes;
+  size_t target = avail / 3 < 32 * 1024 ? avail / 3 : 32 * 1024;   // keep at least three stages in flight
+  int kpg_max = static_cast<int>(target / per_iter);
+  if (kpg_max < 1) kpg_max = 1;
+  if (kpg_max > kp.num_k_iters) kpg_max = kp.num_k_iters;
+  const int groups = (kp.num_k_iters + kpg_max - 1) / kpg_max;
+  kp.kpg = (kp.num_k_iters + groups - 1) / groups;
+  const uint32_t stage_bytes = kp.kpg * per_iter;
+  int stages = static_cast<int>((kSmemBudget - fixed - kp.b_res_bytes) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   kp.stages = stages;
@@ -416,7 +457,7 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
   kp.res_cstride = d.res_cstride;
   op->grid = dim3(kp.num_tiles < sms ? kp.num_tiles : sms, 1, 1);
   // >= 120 KB so that two CTAs can never share an SM (each owns up to all 512 TMEM columns)
-  size_t smem = static_cast<size_t>(stages) * stage_bytes + fixed;
+  size_t smem = static_cast<size_t>(stages) * stage_bytes + kp.b_res_bytes + fixed;
   if (smem < 120 * 1024) smem = 120 * 1024;
   op->smem_bytes = smem;
 

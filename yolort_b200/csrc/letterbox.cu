@@ -76,15 +76,21 @@ __device__ __forceinline__ void sample_rgb(const ImgGeom& g, const float* lut, i
   const float wy0 = 1.f - ly, wx0 = 1.f - lx;
   const SrcT* base = static_cast<const SrcT*>(g.src);
   const size_t plane = static_cast<size_t>(g.src_h) * g.src_w;
+  // Taps with zero weight are not fetched (w*p + 0*q == w*p exactly for finite q): an identity resize
+  // (the 640x640 headline case) touches one source texel per output pixel instead of four.
+  const bool need_x1 = lx != 0.f, need_y1 = ly != 0.f;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const SrcT* p = base + c * plane;
     const float p00 = load_src<SrcT>(p + static_cast<size_t>(y0) * g.src_w + x0, lut);
-    const float p01 = load_src<SrcT>(p + static_cast<size_t>(y0) * g.src_w + x1, lut);
-    const float p10 = load_src<SrcT>(p + static_cast<size_t>(y1) * g.src_w + x0, lut);
-    const float p11 = load_src<SrcT>(p + static_cast<size_t>(y1) * g.src_w + x1, lut);
+    const float p01 = need_x1 ? load_src<SrcT>(p + static_cast<size_t>(y0) * g.src_w + x1, lut) : p00;
+    float bot = 0.f;
+    if (need_y1) {
+      const float p10 = load_src<SrcT>(p + static_cast<size_t>(y1) * g.src_w + x0, lut);
+      const float p11 = need_x1 ? load_src<SrcT>(p + static_cast<size_t>(y1) * g.src_w + x1, lut) : p10;
+      bot = __fadd_rn(__fmul_rn(wx0, p10), __fmul_rn(lx, p11));
+    }
     const float top = __fadd_rn(__fmul_rn(wx0, p00), __fmul_rn(lx, p01));
-    const float bot = __fadd_rn(__fmul_rn(wx0, p10), __fmul_rn(lx, p11));
     rgb[c] = __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(ly, bot));
   }
 }
