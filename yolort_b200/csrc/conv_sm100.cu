@@ -165,6 +165,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
 
+  // Programmatic dependent launch: everything above overlapped the tail of the previous kernel in the
+  // stream; from here on we touch memory it produced.  Let our own dependent start its prologue too.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -548,9 +553,17 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
 }
 
 int conv_op_launch(const ConvOp* op, cudaStream_t stream) {
-  conv_umma_kernel<<<op->grid, kThreads, op->smem_bytes, stream>>>(op->tmap_a, op->tmap_b, op->tmap_out,
-                                                                  op->kp);
-  YB_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = op->grid;
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = op->smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel, op->tmap_a, op->tmap_b, op->tmap_out, op->kp));
   return YB_OK;
 }
 
