@@ -93,3 +93,29 @@ def test_predict_and_shapes_yolov5s_default_weights():
     for d in out:
         assert d["boxes"].shape[1:] == (4,) and d["labels"].dtype == torch.int64 and d["scores"].dtype == torch.float32
         assert d["boxes"].shape[0] == d["scores"].shape[0] == d["labels"].shape[0] <= 300
+
+
+def test_mixed_size_batch_vs_oracle():
+    """Dynamic-shape batch (BASELINE.json configs[3] in miniature): different aspect ratios in one batch, the
+    canvas is the batch maximum rounded up to 32; boxes come back in each image's own pixel frame."""
+    m, sd = _model_n()
+    ims = [util.synth_image_u8(h, w, 40 + i) for i, (h, w) in enumerate([(97, 128), (128, 64), (75, 75), (50, 117), (128, 128)])]
+    ref = R.detect(sd, ims, score_thresh=0.15, size=(128, 128))
+    out = m([im.to(DEV) for im in ims])
+    for got, want, im in zip(out, ref, ims):
+        got = util.to_np(got)
+        frac = util.match_fraction(got, want, iou_thr=0.9)
+        print("mixed batch", tuple(im.shape[1:]), "matched", frac, len(got["scores"]), len(want["scores"]))
+        assert frac >= 0.8
+
+
+def test_bf16_model_end_to_end():
+    m, sd = _model_n()
+    m = m.to(torch.bfloat16)
+    z = util.load_npz("e2e_n.npz")
+    ims = [torch.from_numpy(z["img0"]).to(DEV), torch.from_numpy(z["img1"]).to(DEV)]
+    out = m(ims)
+    for got, ref in zip(out, util.dets_from_npz(z, 2)):
+        frac = util.match_fraction(util.to_np(got), ref, iou_thr=0.8)
+        print("bf16 e2e matched fraction:", frac)
+        assert frac >= 0.5      # bf16 activations: 8 mantissa bits through ~25 layers
