@@ -108,3 +108,28 @@ def test_rejects_unsupported():
     d.kind = 99
     with pytest.raises(_C.NativeLibraryError):
         _C.Plan([d], DEV)
+
+
+# ---- halo-patch 3x3 kernel (conv3x3_patch_sm100.cu) -------------------------------------------------------
+import os
+
+
+@pytest.mark.parametrize("mode", ["0", "1", "2"])
+@pytest.mark.parametrize("cin,cout", [(64, 64), (16, 32), (32, 32), (128, 128), (256, 256)])
+def test_patch_conv_view_modes(cin, cout, mode, monkeypatch):
+    """All three ways of addressing the taps inside the staged patch must give the same convolution."""
+    monkeypatch.setenv("YB_PATCH_MODE", mode)
+    run_conv(2, 32, 40, cin, cout, 3, 1, 1, seed=3)
+
+
+def test_patch_conv_ragged_edges_residual_and_windows():
+    run_conv(3, 40, 44, 64, 64, 3, 1, 1, residual=True, in_pad=32, out_pad=64)   # W=44: last column tile half empty
+    run_conv(1, 48, 24, 128, 128, 3, 1, 1, dtype=torch.bfloat16)
+
+
+def test_patch_conv_matches_im2col_kernel(monkeypatch):
+    """Same layer through both kernels (the generic im2col path is forced with YB_DISABLE_PATCH_CONV=1)."""
+    monkeypatch.setenv("YB_DISABLE_PATCH_CONV", "1")
+    run_conv(2, 32, 32, 64, 64, 3, 1, 1, seed=11)
+    monkeypatch.delenv("YB_DISABLE_PATCH_CONV")
+    run_conv(2, 32, 32, 64, 64, 3, 1, 1, seed=11)

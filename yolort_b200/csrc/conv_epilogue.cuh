@@ -1,0 +1,79 @@
+// Epilogue helpers shared by the convolution kernels (bias + SiLU + residual + pack, swizzled staging).
+#pragma once
+#include "common.cuh"
+
+namespace yb {
+
+// fields of the kernel parameter block the epilogue needs
+struct EpilogueParams {
+  int Cout;
+  int act, is_bf16;
+  const void* residual;
+  int res_cstride;
+};
+
+__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+template <bool kBf16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if constexpr (kBf16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+template <bool kBf16>
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+  if constexpr (kBf16) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  } else {
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
+  }
+}
+
+// 16 accumulator columns -> bias, activation, residual, convert; result as two 16-byte chunks.
+template <bool kBf16>
+__device__ __forceinline__ void finish16(const EpilogueParams& p, const uint32_t (&acc)[16],
+                                         const float* __restrict__ s_bias, long long row, bool row_ok,
+                                         int col, uint4& o0, uint4& o1) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    v[j] = __uint_as_float(acc[j]) + s_bias[j];
+    if (p.act == YB_ACT_SILU) v[j] = silu(v[j]);
+  }
+  if (p.residual != nullptr && row_ok && col < p.Cout) {
+    const uint4* r = reinterpret_cast<const uint4*>(
+        reinterpret_cast<const uint16_t*>(p.residual) + row * p.res_cstride + col);
+    const uint4 r0 = __ldg(r);
+    const uint4 r1 = (col + 8 < p.Cout) ? __ldg(r + 1) : make_uint4(0, 0, 0, 0);
+    const uint32_t ru[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 f = unpack2<kBf16>(ru[j]);
+      v[2 * j] += f.x;
+      v[2 * j + 1] += f.y;
+    }
+  }
+  o0.x = pack2<kBf16>(v[0], v[1]);
+  o0.y = pack2<kBf16>(v[2], v[3]);
+  o0.z = pack2<kBf16>(v[4], v[5]);
+  o0.w = pack2<kBf16>(v[6], v[7]);
+  o1.x = pack2<kBf16>(v[8], v[9]);
+  o1.y = pack2<kBf16>(v[10], v[11]);
+  o1.z = pack2<kBf16>(v[12], v[13]);
+  o1.w = pack2<kBf16>(v[14], v[15]);
+}
+
+// Physical 16-byte chunk index of logical chunk `j` in row `r` of a tile whose rows are `row_bytes`
+// long, under the TMA/UMMA swizzle of the same width (address bits [4,7) ^= bits [7,10), truncated).
+__device__ __forceinline__ int swizzle_chunk(int r, int j, int row_bytes) {
+  if (row_bytes == 128) return j ^ (r & 7);
+  if (row_bytes == 64) return j ^ ((r >> 1) & 3);
+  return j ^ ((r >> 2) & 1);
+}
+
+
+}  // namespace yb

@@ -23,6 +23,7 @@
 //                by the TMA unit).
 #include "common.cuh"
 #include "conv_sm100.h"
+#include "conv_epilogue.cuh"
 
 namespace yb {
 
@@ -37,7 +38,7 @@ constexpr int kMaxBlockN = 256;
 constexpr size_t kSmemBudget = 222 * 1024;  // dynamic shared memory per CTA (227 KB limit minus static)
 
 struct ConvKernelParams {
-  int M, Cout, block_n, block_k;
+  int M, block_n, block_k;
   int ksize, chunks, num_k_iters;
   int mode;  // 0: 2-D tiled rows (1x1 stride 1), 1: 4-D im2col
   int HoWo, Wo, stride, pad;
@@ -49,74 +50,9 @@ struct ConvKernelParams {
   int store_cols;  // columns per TMA store box: 64 / 32 / 16
   int bias_len;    // length of the (padded) bias vector
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, idesc;
-  int act, is_bf16;
   const float* bias;
-  const void* residual;
-  int res_cstride;
+  EpilogueParams ep;
 };
-
-__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
-
-template <bool kBf16>
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-  if constexpr (kBf16) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  } else {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
-}
-template <bool kBf16>
-__device__ __forceinline__ float2 unpack2(uint32_t u) {
-  if constexpr (kBf16) {
-    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
-  } else {
-    return __half22float2(*reinterpret_cast<__half2*>(&u));
-  }
-}
-
-// 16 accumulator columns -> bias, activation, residual, convert; result as two 16-byte chunks.
-template <bool kBf16>
-__device__ __forceinline__ void finish16(const ConvKernelParams& p, const uint32_t (&acc)[16],
-                                         const float* __restrict__ s_bias, long long row, bool row_ok,
-                                         int col, uint4& o0, uint4& o1) {
-  float v[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    v[j] = __uint_as_float(acc[j]) + s_bias[j];
-    if (p.act == YB_ACT_SILU) v[j] = silu(v[j]);
-  }
-  if (p.residual != nullptr && row_ok && col < p.Cout) {
-    const uint4* r = reinterpret_cast<const uint4*>(
-        reinterpret_cast<const uint16_t*>(p.residual) + row * p.res_cstride + col);
-    const uint4 r0 = __ldg(r);
-    const uint4 r1 = (col + 8 < p.Cout) ? __ldg(r + 1) : make_uint4(0, 0, 0, 0);
-    const uint32_t ru[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float2 f = unpack2<kBf16>(ru[j]);
-      v[2 * j] += f.x;
-      v[2 * j + 1] += f.y;
-    }
-  }
-  o0.x = pack2<kBf16>(v[0], v[1]);
-  o0.y = pack2<kBf16>(v[2], v[3]);
-  o0.z = pack2<kBf16>(v[4], v[5]);
-  o0.w = pack2<kBf16>(v[6], v[7]);
-  o1.x = pack2<kBf16>(v[8], v[9]);
-  o1.y = pack2<kBf16>(v[10], v[11]);
-  o1.z = pack2<kBf16>(v[12], v[13]);
-  o1.w = pack2<kBf16>(v[14], v[15]);
-}
-
-// Physical 16-byte chunk index of logical chunk `j` in row `r` of a tile whose rows are `row_bytes`
-// long, under the TMA/UMMA swizzle of the same width (address bits [4,7) ^= bits [7,10), truncated).
-__device__ __forceinline__ int swizzle_chunk(int r, int j, int row_bytes) {
-  if (row_bytes == 128) return j ^ (r & 7);
-  if (row_bytes == 64) return j ^ ((r >> 1) & 3);
-  return j ^ ((r >> 2) & 1);
-}
 
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -292,10 +228,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tmem_ld_32x32b_x16(taddr + c0 + c, acc);
           tmem_ld_wait();
           uint4 o0, o1;
-          if (p.is_bf16)
-            finish16<true>(p, acc, bias_s + c0 + c, row, row_ok, n0 + c0 + c, o0, o1);
+          if (p.ep.is_bf16)
+            finish16<true>(p.ep, acc, bias_s + c0 + c, row, row_ok, n0 + c0 + c, o0, o1);
           else
-            finish16<false>(p, acc, bias_s + c0 + c, row, row_ok, n0 + c0 + c, o0, o1);
+            finish16<false>(p.ep, acc, bias_s + c0 + c, row, row_ok, n0 + c0 + c, o0, o1);
           const int j = c >> 3;
           *reinterpret_cast<uint4*>(my_row + swizzle_chunk(row_in_tile, j, row_bytes) * 16) = o0;
           *reinterpret_cast<uint4*>(my_row + swizzle_chunk(row_in_tile, j + 1, row_bytes) * 16) = o1;
@@ -309,7 +245,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
         if (issuer) {
-          if (n0 + c0 < p.Cout) tma_store_2d(&tmap_out, buf, n0 + c0, m0);
+          if (n0 + c0 < p.ep.Cout) tma_store_2d(&tmap_out, buf, n0 + c0, m0);
           tma_store_commit();
         }
       }
@@ -326,10 +262,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                    const cuuint64_t*, const cuuint64_t*, const int*, const int*,
                                    cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
@@ -369,6 +301,7 @@ uint32_t pow2_cols(int n) {
 }  // namespace
 
 struct ConvOp {
+  PatchConvOp* patch = nullptr;  // non-null: this conv runs on the halo-patch kernel
   CUtensorMap tmap_a, tmap_b, tmap_out;
   ConvKernelParams kp;
   dim3 grid;
@@ -401,9 +334,18 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
   YB_REQUIRE(M_ll > 0 && M_ll < (1ll << 31), "conv: M out of range");
 
   ConvOp* op = new ConvOp();
+  if (patch_conv_eligible(d)) {
+    rc = patch_conv_create(d, g_encode_tiled, &op->patch);
+    if (rc != YB_OK) {
+      delete op;
+      return rc;
+    }
+    *out = op;
+    return YB_OK;
+  }
   ConvKernelParams& kp = op->kp;
   kp.M = static_cast<int>(M_ll);
-  kp.Cout = d.Cout;
+  kp.ep.Cout = d.Cout;
   const int m_tiles = (kp.M + kBlockM - 1) / kBlockM;
   const int sms = num_sms();
   // N tile: the whole Cout up to 256 columns (fewest A re-reads); halve it when that leaves fewer
@@ -452,14 +394,14 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
   if (stages < 2) stages = 2;
   kp.stages = stages;
   kp.tmem_cols = pow2_cols(2 * kp.block_n);
-  kp.is_bf16 = d.dtype == YB_BF16;
-  const uint32_t fmt = kp.is_bf16 ? 1u : 0u;
+  kp.ep.is_bf16 = d.dtype == YB_BF16;
+  const uint32_t fmt = kp.ep.is_bf16 ? 1u : 0u;
   kp.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(kp.block_n >> 3) << 17) |
              (static_cast<uint32_t>(kBlockM >> 4) << 24);
-  kp.act = d.act;
+  kp.ep.act = d.act;
   kp.bias = d.bias;
-  kp.residual = d.residual;
-  kp.res_cstride = d.res_cstride;
+  kp.ep.residual = d.residual;
+  kp.ep.res_cstride = d.res_cstride;
   op->grid = dim3(kp.num_tiles < sms ? kp.num_tiles : sms, 1, 1);
   // >= 120 KB so that two CTAs can never share an SM (each owns up to all 512 TMEM columns)
   size_t smem = static_cast<size_t>(stages) * stage_bytes + kp.b_res_bytes + fixed;
@@ -467,7 +409,7 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
   op->smem_bytes = smem;
 
   const CUtensorMapDataType dt =
-      kp.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+      kp.ep.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUtensorMapSwizzle sw = swizzle_for_row_bytes(kp.block_k * 2);
   CUresult cr;
   if (kp.mode == 0) {
@@ -553,6 +495,7 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
 }
 
 int conv_op_launch(const ConvOp* op, cudaStream_t stream) {
+  if (op->patch) return patch_conv_launch(op->patch, stream);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = op->grid;
   cfg.blockDim = dim3(kThreads, 1, 1);
@@ -567,6 +510,9 @@ int conv_op_launch(const ConvOp* op, cudaStream_t stream) {
   return YB_OK;
 }
 
-void conv_op_destroy(ConvOp* op) { delete op; }
+void conv_op_destroy(ConvOp* op) {
+  if (op && op->patch) patch_conv_destroy(op->patch);
+  delete op;
+}
 
 }  // namespace yb

@@ -408,13 +408,13 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
       }
       area = box_area(nbox);
       const int kc = s_kcount;
-      for (int i = 0; i < kc; ++i) {
-        if (!trick && k_label[i] != label) continue;
-        if (iou_over(k_box[i], k_area[i], nbox, area, p.iou_thresh)) {
-          alive = false;
-          break;
-        }
+      bool hit = false;
+#pragma unroll 4
+      for (int i = 0; i < kc; ++i) {   // no early exit: independent iterations pipeline their loads
+        const bool same = trick || k_label[i] == label;
+        hit |= same && iou_over(k_box[i], k_area[i], nbox, area, p.iou_thresh);
       }
+      alive = !hit;
     }
     // ---- B: order-preserving compaction of the survivors ----
     const uint32_t bal = __ballot_sync(0xffffffffu, alive);
@@ -444,10 +444,10 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
       const float4 bi = sv_box[tid];
       const float ai = sv_area[tid];
       const int li = sv_label[tid];
-      for (int w = 0; w < nwords; ++w) {
+      for (int w = 0; w < kSweep / 32; ++w) {
         uint32_t bits = 0;
         const int j0 = w << 5;
-        if (j0 + 31 > tid) {
+        if (w < nwords && j0 + 31 > tid) {
           const int jend = min(32, S - j0);
           for (int b = 0; b < jend; ++b) {
             const int jj = j0 + b;
@@ -459,20 +459,36 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
       }
     }
     __syncthreads();
-    // ---- C: sequential resolution by warp 0 ----
-    if (warp == 0) {
-      uint32_t removed = 0, keep = 0;   // lane l owns word l of both sets (S <= 512 -> 16 words)
+    // ---- C: sequential resolution ----
+    // One thread walks the survivors in order; the "removed" set (<= 512 bits) lives in 16 registers, so the
+    // only memory traffic is 16 independent shared-memory loads per KEPT survivor (no cross-lane exchange on
+    // the critical path).
+    if (tid == 0) {
+      uint32_t removed[kSweep / 32], keep[kSweep / 32];
+#pragma unroll
+      for (int w = 0; w < kSweep / 32; ++w) removed[w] = keep[w] = 0;
       int kc = s_kcount;
       const int kc0 = kc;
-      for (int i = 0; i < S; ++i) {
-        const uint32_t word = __shfl_sync(0xffffffffu, removed, i >> 5);
-        if ((word >> (i & 31)) & 1u) continue;
-        if (lane == (i >> 5)) keep |= 1u << (i & 31);
-        if (lane < nwords) removed |= s_mask[i * (kSweep / 32) + lane];
-        if (++kc >= p.max_det) break;
+      bool full = false;
+#pragma unroll
+      for (int w = 0; w < kSweep / 32; ++w) {
+        if (full || (w << 5) >= S) continue;
+        const int lim = min(32, S - (w << 5));
+        for (int b = 0; b < lim; ++b) {
+          if ((removed[w] >> b) & 1u) continue;
+          keep[w] |= 1u << b;
+          const uint32_t* row = s_mask + ((w << 5) + b) * (kSweep / 32);
+#pragma unroll
+          for (int v = 0; v < kSweep / 32; ++v) removed[v] |= row[v];
+          if (++kc >= p.max_det) {
+            full = true;
+            break;
+          }
+        }
       }
-      if (lane < kSweep / 32) s_keep[lane] = keep;
-      if (lane == 0) s_newkept = kc - kc0;
+#pragma unroll
+      for (int w = 0; w < kSweep / 32; ++w) s_keep[w] = keep[w];
+      s_newkept = kc - kc0;
     }
     __syncthreads();
     // ---- D: append the kept survivors ----
