@@ -21,7 +21,7 @@ for r in rows[a:b]:
     t = float(r['Metric Value'].replace(',', '')) / 1e3
     alltot += t
     extra = ''
-    if 'conv_umma' in name or 'spp_pool' in name or 'upsample' in name:
+    if 'conv_umma' in name or 'conv3x3_patch' in name or 'spp_pool' in name or 'upsample' in name:
         op = ops[k]; k += 1
         hw = 640 // op.dst.buf.div
         if op.kind == 0:

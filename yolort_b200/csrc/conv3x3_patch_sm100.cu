@@ -40,6 +40,7 @@ struct PatchParams {
   int block_n, block_k, chunks;
   int a_stages, b_stages, b_resident;
   int store_cols, store_bufs, bias_len;
+  int dbg;                // ablation knobs (YB_CONV_DBG), see conv_sm100.cu
   int view_mode;          // 0/1: one 18x16 patch, taps are shifted views (1 = also set the descriptor's base-offset
                           // field); 2: three 18x8 patches, one per dx (every view starts on a swizzle-atom boundary)
   uint32_t a_bytes, b_sub_bytes, b_res_bytes, tmem_cols, idesc;
@@ -216,7 +217,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             for (int k = 0; k < kk; ++k) {
               const uint64_t da = make_view_desc(a_addr + k * 32, row_bytes, sbo, p.view_mode);
               const uint64_t db = make_kmajor_desc(b_addr + k * 32, row_bytes);
-              umma_f16(tmem_d, da, db, p.idesc, (c | tap | k) != 0 ? 1u : 0u);
+              if (!(p.dbg & 2)) umma_f16(tmem_d, da, db, p.idesc, (c | tap | k) != 0 ? 1u : 0u);
             }
             if (!p.b_resident) {
               umma_commit(&b_empty[sb]);
@@ -266,7 +267,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
         named_bar_sync(bar_id, 128);
         uint8_t* my_row = buf + row_in_tile * row_bytes;
-        for (int c = 0; c < p.store_cols; c += 16) {
+        for (int c = 0; c < p.store_cols && !(p.dbg & 1); c += 16) {
           uint32_t acc[16];
           tmem_ld_32x32b_x16(taddr + c0 + c, acc);
           tmem_ld_wait();
@@ -287,7 +288,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
         if (issuer) {
-          if (n0 + c0 < p.ep.Cout) tma_store_4d(&tmap_out, buf, n0 + c0, tx * kTileW, ty * kTileH, n_img);
+          if (n0 + c0 < p.ep.Cout && !(p.dbg & 5)) tma_store_4d(&tmap_out, buf, n0 + c0, tx * kTileW, ty * kTileH, n_img);
           tma_store_commit();
         }
       }
@@ -351,6 +352,10 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
   kp.store_cols = (block_n % 64 == 0) ? 64 : ((block_n % 32 == 0) ? 32 : 16);
   kp.store_bufs = block_n > kp.store_cols ? 2 : 1;
   kp.bias_len = d.Cout_pad;
+  {
+    const char* e = getenv("YB_CONV_DBG");
+    kp.dbg = e ? atoi(e) : 0;
+  }
   const size_t staging = static_cast<size_t>(kEpiGroups) * kp.store_bufs * kStageBufBytes;
   const size_t b_total = static_cast<size_t>(9) * kp.chunks * kp.b_sub_bytes;
   const size_t avail = kSmemBudget - staging - 1024;

@@ -21,6 +21,8 @@
 //                -> swizzled shared-memory staging -> TMA store into the NHWC destination view (a
 //                channel window of a concat buffer is just a strided tensor map; ragged M is clipped
 //                by the TMA unit).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "conv_sm100.h"
 #include "conv_epilogue.cuh"
@@ -49,6 +51,7 @@ struct ConvKernelParams {
   int n_tiles, num_tiles;
   int store_cols;  // columns per TMA store box: 64 / 32 / 16
   int bias_len;    // length of the (padded) bias vector
+  int dbg;         // ablation knobs (YB_CONV_DBG): 1 = no epilogue math/stores, 2 = no MMA, 4 = no TMA stores, 8 = no loads
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, idesc;
   const float* bias;
   EpilogueParams ep;
@@ -185,7 +188,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int k = 0; k < kk; ++k) {
               const uint64_t da = make_kmajor_desc(a_addr + k * 32, row_bytes);
               const uint64_t db = make_kmajor_desc(b_addr + k * 32, row_bytes);
-              umma_f16(tmem_d, da, db, p.idesc, (it0 | j | k) != 0 ? 1u : 0u);
+              if (!(p.dbg & 2)) umma_f16(tmem_d, da, db, p.idesc, (it0 | j | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
@@ -223,7 +226,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (issuer) tma_store_wait_read<1>();  // the store that used this buffer two boxes ago has read it
         named_bar_sync(bar_id, 128);
         uint8_t* my_row = buf + row_in_tile * row_bytes;
-        for (int c = 0; c < p.store_cols; c += 16) {
+        for (int c = 0; c < p.store_cols && !(p.dbg & 1); c += 16) {
           uint32_t acc[16];
           tmem_ld_32x32b_x16(taddr + c0 + c, acc);
           tmem_ld_wait();
@@ -245,7 +248,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
         if (issuer) {
-          if (n0 + c0 < p.ep.Cout) tma_store_2d(&tmap_out, buf, n0 + c0, m0);
+          if (n0 + c0 < p.ep.Cout && !(p.dbg & 5)) tma_store_2d(&tmap_out, buf, n0 + c0, m0);
           tma_store_commit();
         }
       }
@@ -370,6 +373,10 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
   kp.pad = d.pad;
   kp.store_cols = (block_n % 64 == 0) ? 64 : ((block_n % 32 == 0) ? 32 : 16);
   kp.bias_len = d.Cout_pad;
+  {
+    const char* e = getenv("YB_CONV_DBG");
+    kp.dbg = e ? atoi(e) : 0;
+  }
   kp.a_stage_bytes = kBlockM * kp.block_k * 2;
   kp.b_stage_bytes = (static_cast<uint32_t>(kp.block_n * kp.block_k * 2) + 1023u) & ~1023u;
   const size_t fixed = static_cast<size_t>(kEpiGroups) * 2 * kStageBufBytes + 1024;
