@@ -28,7 +28,8 @@ constexpr int kTileH = 16, kTileW = 8;           // output tile (pixels)
 constexpr int kPatchH = 18, kPatchW = 16;        // TMA box (pixels): halo + padding of the row pitch to 16
 constexpr int kMaxA = 4, kMaxB = 12;
 constexpr int kEpiGroups = 2;
-constexpr int kFirstEpiWarp = 3;
+constexpr int kFirstLoadWarp = 3, kLoadWarps = 4;   // cooperative cp.async patch loaders
+constexpr int kFirstEpiWarp = kFirstLoadWarp + kLoadWarps;
 constexpr int kThreads = 32 * kFirstEpiWarp + kEpiGroups * 128;
 constexpr int kStageBufBytes = 128 * 128;
 constexpr int kMaxBlockN = 256;
@@ -41,6 +42,9 @@ struct PatchParams {
   int a_stages, b_stages, b_resident;
   int store_cols, store_bufs, bias_len;
   int dbg;                // ablation knobs (YB_CONV_DBG), see conv_sm100.cu
+  int a_loader;           // 0: TMA box loads, 1: cooperative cp.async loads (4 warps)
+  const void* in;         // NHWC input view (cp.async loader)
+  int in_cstride, Cin;
   int view_mode;          // 0/1: one 18x16 patch, taps are shifted views (1 = also set the descriptor's base-offset
                           // field); 2: three 18x8 patches, one per dx (every view starts on a swizzle-atom boundary)
   uint32_t a_bytes, b_sub_bytes, b_res_bytes, tmem_cols, idesc;
@@ -102,7 +106,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     tma_prefetch_desc(&tmap_b);
     tma_prefetch_desc(&tmap_out);
     for (int s = 0; s < p.a_stages; ++s) {
-      mbar_init(&a_full[s], 1);
+      mbar_init(&a_full[s], p.a_loader ? kLoadWarps * 32 : 1);
       mbar_init(&a_empty[s], 1);
     }
     for (int s = 0; s < kMaxB; ++s) {
@@ -129,8 +133,8 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
-    // ===================== patch (A) producer =====================
-    if (lane == 0) {
+    // ===================== patch (A) producer, TMA variant =====================
+    if (lane == 0 && p.a_loader == 0) {
       int ka = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles;
@@ -229,6 +233,56 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         umma_commit(&acc_full[as]);
       }
     }
+  } else if (warp >= kFirstLoadWarp && warp < kFirstEpiWarp) {
+    // ===================== patch (A) producer, cooperative cp.async variant =====================
+    // The TMA unit handles a box row by row (measured ~19 clk per 128-byte row for these 4-D boxes, ~15 clk
+    // even for 32-byte rows); 128 threads issuing 16-byte cp.async copies move the same patch several times
+    // faster.  Each thread writes its chunks to the swizzled position the UMMA descriptor expects and
+    // zero-fills the halo (src-size 0).  Completion: wait_group -> proxy fence -> mbarrier arrive.
+    if (p.a_loader == 1) {
+      const int ltid = threadIdx.x - 32 * kFirstLoadWarp;
+      const int row_bytes = p.block_k * 2;
+      const int cpr = row_bytes >> 4;                    // 16-byte chunks per pixel-row
+      const int total = kPatchH * kPatchW * cpr;
+      const uint16_t* in = reinterpret_cast<const uint16_t*>(p.in);
+      int ka = 0;
+      int pending_stage = -1;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        const int n_img = m_tile / tiles_per_img;
+        const int t = m_tile - n_img * tiles_per_img;
+        const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
+        const int y_base = ty * kTileH - 1, x_base = tx * kTileW - 1;
+        for (int c = 0; c < p.chunks; ++c, ++ka) {
+          const int s = ka % p.a_stages;
+          const uint32_t ph = (ka / p.a_stages) & 1;
+          mbar_wait(&a_empty[s], ph ^ 1);
+          const uint32_t dst_base = smem_u32(a_buf + static_cast<size_t>(s) * p.a_bytes);
+          for (int i = ltid; i < total; i += kLoadWarps * 32) {
+            const int row = i / cpr, ch = i - row * cpr;
+            const int hh = row / kPatchW, ww = row - hh * kPatchW;
+            const int gy = y_base + hh, gx = x_base + ww;
+            const int ce = c * p.block_k + ch * 8;                   // first channel of this chunk
+            const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W && ce < p.Cin;
+            const uint16_t* src = ok ? in + ((static_cast<long long>(n_img) * p.H + gy) * p.W + gx) * p.in_cstride + ce : in;
+            const uint32_t dst = dst_base + row * row_bytes + swizzle_chunk(row, ch, row_bytes) * 16;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          if (pending_stage >= 0) {   // publish the previous patch while this one is in flight
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            fence_proxy_async_smem();
+            mbar_arrive(&a_full[pending_stage]);
+          }
+          pending_stage = s;
+        }
+      }
+      if (pending_stage >= 0) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        fence_proxy_async_smem();
+        mbar_arrive(&a_full[pending_stage]);
+      }
+    }
   } else if (warp >= kFirstEpiWarp) {
     // ===================== epilogue groups =====================
     const int g = (warp - kFirstEpiWarp) >> 2;
@@ -267,18 +321,11 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
         named_bar_sync(bar_id, 128);
         uint8_t* my_row = buf + row_in_tile * row_bytes;
-        for (int c = 0; c < p.store_cols && !(p.dbg & 1); c += 16) {
-          uint32_t acc[16];
-          tmem_ld_32x32b_x16(taddr + c0 + c, acc);
-          tmem_ld_wait();
-          uint4 o0, o1;
+        if (!(p.dbg & 1)) {
           if (p.ep.is_bf16)
-            finish16<true>(p.ep, acc, bias_s + c0 + c, row, row_ok, n0 + c0 + c, o0, o1);
+            epilogue_box_dispatch<true>(p.ep, p.store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
           else
-            finish16<false>(p.ep, acc, bias_s + c0 + c, row, row_ok, n0 + c0 + c, o0, o1);
-          const int j = c >> 3;
-          *reinterpret_cast<uint4*>(my_row + swizzle_chunk(row_in_tile, j, row_bytes) * 16) = o0;
-          *reinterpret_cast<uint4*>(my_row + swizzle_chunk(row_in_tile, j + 1, row_bytes) * 16) = o1;
+            epilogue_box_dispatch<false>(p.ep, p.store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
         }
         if (c0 + p.store_cols >= p.block_n) {
           tc_fence_before();
@@ -389,6 +436,14 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
   kp.ep.residual = d.residual;
   kp.ep.res_cstride = d.res_cstride;
   kp.bias = d.bias;
+  kp.in = d.in;
+  kp.in_cstride = d.in_cstride;
+  kp.Cin = d.Cin;
+  {
+    const char* e = getenv("YB_PATCH_LOADER");
+    kp.a_loader = e ? atoi(e) : 1;
+    if (kp.view_mode == 2) kp.a_loader = 0;   // the dx-split layout exists only for the TMA variant
+  }
   const uint32_t fmt = kp.ep.is_bf16 ? 1u : 0u;
   kp.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(block_n >> 3) << 17) | (8u << 24);
   op->grid = dim3(kp.num_tiles < sms ? kp.num_tiles : sms, 1, 1);

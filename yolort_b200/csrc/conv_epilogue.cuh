@@ -76,4 +76,77 @@ __device__ __forceinline__ int swizzle_chunk(int r, int j, int row_bytes) {
 }
 
 
+// One TMA-store box (kCols = 16/32/64 accumulator columns of this thread's output pixel), handled in batches
+// of up to 32 columns: the TMEM loads and residual loads of a batch are issued up front (one exposed latency
+// per 32 columns instead of one per 16), then bias + SiLU (+ residual) + pack and the swizzled smem writes.
+template <bool kBf16, int kCols>
+__device__ __forceinline__ void epilogue_box(const EpilogueParams& p, uint32_t taddr, const float* __restrict__ s_bias,
+                                             long long row, bool row_ok, int col0, uint8_t* my_row, int row_in_tile) {
+  constexpr int kBatch = kCols < 32 ? kCols : 32;
+  constexpr int kChunks = kBatch / 16;
+  constexpr int kRowBytes = kCols * 2;
+  const bool has_res = p.residual != nullptr && row_ok;
+  const uint16_t* rbase = reinterpret_cast<const uint16_t*>(p.residual) + row * p.res_cstride + col0;
+#pragma unroll
+  for (int b0 = 0; b0 < kCols; b0 += kBatch) {
+    uint32_t acc[kChunks][16];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) tmem_ld_32x32b_x16(taddr + b0 + c * 16, acc[c]);
+    uint4 res[kChunks][2];
+    if (has_res) {
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        const int col = col0 + b0 + c * 16;
+        const uint4* r = reinterpret_cast<const uint4*>(rbase + b0 + c * 16);
+        res[c][0] = (col < p.Cout) ? __ldg(r) : make_uint4(0, 0, 0, 0);
+        res[c][1] = (col + 8 < p.Cout) ? __ldg(r + 1) : make_uint4(0, 0, 0, 0);
+      }
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v[j] = __uint_as_float(acc[c][j]) + s_bias[b0 + c * 16 + j];
+        if (p.act == YB_ACT_SILU) v[j] = silu(v[j]);
+      }
+      if (has_res) {
+        const uint32_t ru[8] = {res[c][0].x, res[c][0].y, res[c][0].z, res[c][0].w,
+                                res[c][1].x, res[c][1].y, res[c][1].z, res[c][1].w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 f = unpack2<kBf16>(ru[j]);
+          v[2 * j] += f.x;
+          v[2 * j + 1] += f.y;
+        }
+      }
+      uint4 o0, o1;
+      o0.x = pack2<kBf16>(v[0], v[1]);
+      o0.y = pack2<kBf16>(v[2], v[3]);
+      o0.z = pack2<kBf16>(v[4], v[5]);
+      o0.w = pack2<kBf16>(v[6], v[7]);
+      o1.x = pack2<kBf16>(v[8], v[9]);
+      o1.y = pack2<kBf16>(v[10], v[11]);
+      o1.z = pack2<kBf16>(v[12], v[13]);
+      o1.w = pack2<kBf16>(v[14], v[15]);
+      const int j0 = (b0 >> 3) + 2 * c;
+      *reinterpret_cast<uint4*>(my_row + swizzle_chunk(row_in_tile, j0, kRowBytes) * 16) = o0;
+      *reinterpret_cast<uint4*>(my_row + swizzle_chunk(row_in_tile, j0 + 1, kRowBytes) * 16) = o1;
+    }
+  }
+}
+
+template <bool kBf16>
+__device__ __forceinline__ void epilogue_box_dispatch(const EpilogueParams& p, int store_cols, uint32_t taddr,
+                                                      const float* s_bias, long long row, bool row_ok, int col0,
+                                                      uint8_t* my_row, int row_in_tile) {
+  if (store_cols == 64)
+    epilogue_box<kBf16, 64>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
+  else if (store_cols == 32)
+    epilogue_box<kBf16, 32>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
+  else
+    epilogue_box<kBf16, 16>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
+}
+
 }  // namespace yb

@@ -226,18 +226,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (issuer) tma_store_wait_read<1>();  // the store that used this buffer two boxes ago has read it
         named_bar_sync(bar_id, 128);
         uint8_t* my_row = buf + row_in_tile * row_bytes;
-        for (int c = 0; c < p.store_cols && !(p.dbg & 1); c += 16) {
-          uint32_t acc[16];
-          tmem_ld_32x32b_x16(taddr + c0 + c, acc);
-          tmem_ld_wait();
-          uint4 o0, o1;
+        if (!(p.dbg & 1)) {
           if (p.ep.is_bf16)
-            finish16<true>(p.ep, acc, bias_s + c0 + c, row, row_ok, n0 + c0 + c, o0, o1);
+            epilogue_box_dispatch<true>(p.ep, p.store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
           else
-            finish16<false>(p.ep, acc, bias_s + c0 + c, row, row_ok, n0 + c0 + c, o0, o1);
-          const int j = c >> 3;
-          *reinterpret_cast<uint4*>(my_row + swizzle_chunk(row_in_tile, j, row_bytes) * 16) = o0;
-          *reinterpret_cast<uint4*>(my_row + swizzle_chunk(row_in_tile, j + 1, row_bytes) * 16) = o1;
+            epilogue_box_dispatch<false>(p.ep, p.store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
         }
         if (c0 + p.store_cols >= p.block_n) {
           // all TMEM reads of this tile are done: hand the accumulator stage back to the MMA warp
