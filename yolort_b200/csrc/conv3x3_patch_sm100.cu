@@ -441,7 +441,7 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
   kp.Cin = d.Cin;
   {
     const char* e = getenv("YB_PATCH_LOADER");
-    kp.a_loader = e ? atoi(e) : 1;
+    kp.a_loader = e ? atoi(e) : 0;
     if (kp.view_mode == 2) kp.a_loader = 0;   // the dx-split layout exists only for the TMA variant
   }
   const uint32_t fmt = kp.ep.is_bf16 ? 1u : 0u;

@@ -12,7 +12,18 @@ struct EpilogueParams {
   int res_cstride;
 };
 
-__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// SiLU(v) = v / (1 + 2^(-v*log2 e)); both transcendental steps on the MUFU pipe.
+__device__ __forceinline__ float silu(float v) { return v * rcp_approx(1.0f + ex2_approx(v * -1.4426950408889634f)); }
 
 template <bool kBf16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -103,33 +114,51 @@ __device__ __forceinline__ void epilogue_box(const EpilogueParams& p, uint32_t t
       }
     }
     tmem_ld_wait();
+    // Staged so that the kBatch independent SiLU chains overlap (ptxas otherwise emits them one element at a
+    // time: LDS -> EX2 -> RCP back to back, exposing ~80 cycles of latency per element).
+    float v[kBatch];
 #pragma unroll
-    for (int c = 0; c < kChunks; ++c) {
-      float v[16];
+    for (int j = 0; j < kBatch; j += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(s_bias + b0 + j);
+      v[j + 0] = __uint_as_float(acc[j >> 4][(j & 15) + 0]) + b4.x;
+      v[j + 1] = __uint_as_float(acc[j >> 4][(j & 15) + 1]) + b4.y;
+      v[j + 2] = __uint_as_float(acc[j >> 4][(j & 15) + 2]) + b4.z;
+      v[j + 3] = __uint_as_float(acc[j >> 4][(j & 15) + 3]) + b4.w;
+    }
+    if (p.act == YB_ACT_SILU) {
+      float e[kBatch];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        v[j] = __uint_as_float(acc[c][j]) + s_bias[b0 + c * 16 + j];
-        if (p.act == YB_ACT_SILU) v[j] = silu(v[j]);
-      }
-      if (has_res) {
+      for (int j = 0; j < kBatch; ++j) e[j] = ex2_approx(v[j] * -1.4426950408889634f);
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) e[j] = rcp_approx(1.0f + e[j]);
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) v[j] *= e[j];
+    }
+    if (has_res) {
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
         const uint32_t ru[8] = {res[c][0].x, res[c][0].y, res[c][0].z, res[c][0].w,
                                 res[c][1].x, res[c][1].y, res[c][1].z, res[c][1].w};
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float2 f = unpack2<kBf16>(ru[j]);
-          v[2 * j] += f.x;
-          v[2 * j + 1] += f.y;
+          v[c * 16 + 2 * j] += f.x;
+          v[c * 16 + 2 * j + 1] += f.y;
         }
       }
+    }
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
       uint4 o0, o1;
-      o0.x = pack2<kBf16>(v[0], v[1]);
-      o0.y = pack2<kBf16>(v[2], v[3]);
-      o0.z = pack2<kBf16>(v[4], v[5]);
-      o0.w = pack2<kBf16>(v[6], v[7]);
-      o1.x = pack2<kBf16>(v[8], v[9]);
-      o1.y = pack2<kBf16>(v[10], v[11]);
-      o1.z = pack2<kBf16>(v[12], v[13]);
-      o1.w = pack2<kBf16>(v[14], v[15]);
+      const float* w = v + c * 16;
+      o0.x = pack2<kBf16>(w[0], w[1]);
+      o0.y = pack2<kBf16>(w[2], w[3]);
+      o0.z = pack2<kBf16>(w[4], w[5]);
+      o0.w = pack2<kBf16>(w[6], w[7]);
+      o1.x = pack2<kBf16>(w[8], w[9]);
+      o1.y = pack2<kBf16>(w[10], w[11]);
+      o1.z = pack2<kBf16>(w[12], w[13]);
+      o1.w = pack2<kBf16>(w[14], w[15]);
       const int j0 = (b0 >> 3) + 2 * c;
       *reinterpret_cast<uint4*>(my_row + swizzle_chunk(row_in_tile, j0, kRowBytes) * 16) = o0;
       *reinterpret_cast<uint4*>(my_row + swizzle_chunk(row_in_tile, j0 + 1, kRowBytes) * 16) = o1;
