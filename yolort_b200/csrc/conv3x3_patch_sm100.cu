@@ -90,7 +90,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   __shared__ __align__(8) uint64_t b_full[kMaxB], b_empty[kMaxB];
   __shared__ __align__(8) uint64_t acc_full[kEpiGroups], acc_empty[kEpiGroups];
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_bias[kEpiGroups][kMaxBlockN];
+  __shared__ __align__(16) float s_bias[kEpiGroups][kMaxBlockN];
 
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_buf = base;                                                      // [a_stages][a_bytes]

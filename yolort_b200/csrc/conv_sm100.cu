@@ -67,7 +67,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __shared__ __align__(8) uint64_t acc_empty[kEpiGroups];
   __shared__ __align__(8) uint64_t b_full;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float s_bias[kEpiGroups][kMaxBlockN];
+  __shared__ __align__(16) float s_bias[kEpiGroups][kMaxBlockN];
 
   // Swizzled tiles need 1024-byte alignment.
   uint8_t* tiles = reinterpret_cast<uint8_t*>(
