@@ -25,7 +25,7 @@ for r in rows[a:b]:
         op = ops[k]; k += 1
         hw = 640 // op.dst.buf.div
         if op.kind == 0:
-            fl = 32 * hw * hw * op.flops_per_pixel
+            fl = 32 * hw * hw * op.flops_per_pixel // op.pack
             byts = 32 * ((640 // op.src.buf.div) ** 2 * op.src.C + hw * hw * op.dst.C) * 2
             extra = f"{op.name:32s} {op.src.C:4d}->{op.dst.C:4d} k{op.ksize}s{op.stride} out{hw:3d}  {fl/t/1e6:7.1f} TF/s {byts/t/1e3:7.1f} GB/s"
             tot += t

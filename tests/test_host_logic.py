@@ -139,7 +139,7 @@ def test_lowering_carries_the_reference_work(name, ctor, gflop, n_convs):
     convs = [op for op in L.ops if op.kind == _C.YB_OP_CONV]
     n_c3 = sum(1 for op in convs if op.name.endswith("cv1+cv2"))
     assert len(convs) + n_c3 == n_convs          # each fused cv1||cv2 launch covers two reference convs
-    total = sum(op.flops_per_pixel * (640 // op.dst.buf.div) ** 2 for op in convs)
+    total = sum(op.flops_per_pixel * (640 // op.dst.buf.div) ** 2 // op.pack for op in convs)
     assert total / 1e9 == pytest.approx(gflop, rel=2e-3)
     assert sum(1 for op in L.ops if op.kind == _C.YB_OP_UPSAMPLE2X) == 2
     assert sum(1 for op in L.ops if op.kind == _C.YB_OP_SPP_POOL) == 1

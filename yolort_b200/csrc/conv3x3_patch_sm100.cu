@@ -25,7 +25,7 @@ namespace yb {
 namespace {
 
 constexpr int kTileH = 16, kTileW = 8;           // output tile (pixels)
-constexpr int kPatchH = 18, kPatchW = 16;        // TMA box (pixels): halo + padding of the row pitch to 16
+constexpr int kPatchH = 18, kPatchW = 10;        // TMA box (pixels): the tile plus its 1-pixel halo
 constexpr int kMaxA = 4, kMaxB = 12;
 constexpr int kEpiGroups = 2;
 constexpr int kFirstLoadWarp = 3, kLoadWarps = 4;   // cooperative cp.async patch loaders
@@ -47,7 +47,7 @@ struct PatchParams {
   int in_cstride, Cin;
   int view_mode;          // 0/1: one 18x16 patch, taps are shifted views (1 = also set the descriptor's base-offset
                           // field); 2: three 18x8 patches, one per dx (every view starts on a swizzle-atom boundary)
-  uint32_t a_bytes, b_sub_bytes, b_res_bytes, tmem_cols, idesc;
+  uint32_t a_bytes, a_stride, b_sub_bytes, b_res_bytes, tmem_cols, idesc;   // a_stride: a_bytes rounded up to 1 KB
   const float* bias;
   EpilogueParams ep;
 };
@@ -94,7 +94,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_buf = base;                                                      // [a_stages][a_bytes]
-  uint8_t* b_buf = a_buf + static_cast<size_t>(p.a_stages) * p.a_bytes;       // resident [9*chunks] or ring [b_stages]
+  uint8_t* b_buf = a_buf + static_cast<size_t>(p.a_stages) * p.a_stride;       // resident [9*chunks] or ring [b_stages]
   const size_t b_region = p.b_resident ? p.b_res_bytes : static_cast<size_t>(p.b_stages) * p.b_sub_bytes;
   uint8_t* staging = b_buf + b_region;                                        // [kEpiGroups][store_bufs][16 KB]
 
@@ -146,7 +146,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           const uint32_t ph = (ka / p.a_stages) & 1;
           mbar_wait(&a_empty[s], ph ^ 1);
           mbar_expect_tx(&a_full[s], p.a_bytes);
-          uint8_t* dst = a_buf + static_cast<size_t>(s) * p.a_bytes;
+          uint8_t* dst = a_buf + static_cast<size_t>(s) * p.a_stride;
           if (p.view_mode == 2) {
             for (int dx = 0; dx < 3; ++dx)
               tma_load_tiled_4d(&tmap_a, &a_full[s], dst + dx * (p.a_bytes / 3), c * p.block_k, tx * kTileW - 1 + dx,
@@ -203,7 +203,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           const int sa = ka % p.a_stages;
           mbar_wait(&a_full[sa], (ka / p.a_stages) & 1);
           tc_fence_after();
-          const uint32_t patch = smem_u32(a_buf + static_cast<size_t>(sa) * p.a_bytes);
+          const uint32_t patch = smem_u32(a_buf + static_cast<size_t>(sa) * p.a_stride);
           for (int tap = 0; tap < 9; ++tap) {
             uint32_t b_addr;
             int sb = 0;
@@ -218,9 +218,9 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const int dy = tap / 3, dx = tap - dy * 3;
             const uint32_t a_addr = p.view_mode == 2 ? patch + dx * (p.a_bytes / 3) + dy * pitch * row_bytes
                                                      : patch + (dy * pitch + dx) * row_bytes;
-            for (int k = 0; k < kk; ++k) {
-              const uint64_t da = make_view_desc(a_addr + k * 32, row_bytes, sbo, p.view_mode);
-              const uint64_t db = make_kmajor_desc(b_addr + k * 32, row_bytes);
+            uint64_t da = make_view_desc(a_addr, row_bytes, sbo, p.view_mode);
+            uint64_t db = make_kmajor_desc(b_addr, row_bytes);
+            for (int k = 0; k < kk; ++k, da += 2, db += 2) {
               if (!(p.dbg & 2)) umma_f16(tmem_d, da, db, p.idesc, (c | tap | k) != 0 ? 1u : 0u);
             }
             if (!p.b_resident) {
@@ -257,7 +257,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           const int s = ka % p.a_stages;
           const uint32_t ph = (ka / p.a_stages) & 1;
           mbar_wait(&a_empty[s], ph ^ 1);
-          const uint32_t dst_base = smem_u32(a_buf + static_cast<size_t>(s) * p.a_bytes);
+          const uint32_t dst_base = smem_u32(a_buf + static_cast<size_t>(s) * p.a_stride);
           for (int i = ltid; i < total; i += kLoadWarps * 32) {
             const int row = i / cpr, ch = i - row * cpr;
             const int hh = row / kPatchW, ww = row - hh * kPatchW;
@@ -395,6 +395,7 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
   kp.view_mode = env_mode ? atoi(env_mode) : 0;
   if (kp.view_mode < 0 || kp.view_mode > 2) kp.view_mode = 0;
   kp.a_bytes = (kp.view_mode == 2 ? 3 * kPatchH * kTileW : kPatchH * kPatchW) * kp.block_k * 2;
+  kp.a_stride = (kp.a_bytes + 1023u) & ~1023u;
   kp.b_sub_bytes = (static_cast<uint32_t>(block_n * kp.block_k * 2) + 1023u) & ~1023u;
   kp.store_cols = (block_n % 64 == 0) ? 64 : ((block_n % 32 == 0) ? 32 : 16);
   kp.store_bufs = block_n > kp.store_cols ? 2 : 1;
@@ -406,18 +407,18 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
   const size_t staging = static_cast<size_t>(kEpiGroups) * kp.store_bufs * kStageBufBytes;
   const size_t b_total = static_cast<size_t>(9) * kp.chunks * kp.b_sub_bytes;
   const size_t avail = kSmemBudget - staging - 1024;
-  kp.b_resident = (n_tiles == 1 && b_total + 2 * kp.a_bytes <= avail) ? 1 : 0;
+  kp.b_resident = (n_tiles == 1 && b_total + 2 * kp.a_stride <= avail) ? 1 : 0;
   kp.b_res_bytes = kp.b_resident ? static_cast<uint32_t>(b_total) : 0u;
   if (kp.b_resident) {
-    int a_st = static_cast<int>((avail - b_total) / kp.a_bytes);
+    int a_st = static_cast<int>((avail - b_total) / kp.a_stride);
     kp.a_stages = a_st > kMaxA ? kMaxA : a_st;
     kp.b_stages = 1;
   } else {
     kp.a_stages = 2;
-    size_t rem = avail - 2 * kp.a_bytes;
-    if (rem >= static_cast<size_t>(kp.a_bytes) + 6 * kp.b_sub_bytes) {
+    size_t rem = avail - 2 * kp.a_stride;
+    if (rem >= static_cast<size_t>(kp.a_stride) + 6 * kp.b_sub_bytes) {
       kp.a_stages = 3;
-      rem -= kp.a_bytes;
+      rem -= kp.a_stride;
     }
     int b_st = static_cast<int>(rem / kp.b_sub_bytes);
     kp.b_stages = b_st > kMaxB ? kMaxB : b_st;
@@ -448,7 +449,7 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
   kp.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(block_n >> 3) << 17) | (8u << 24);
   op->grid = dim3(kp.num_tiles < sms ? kp.num_tiles : sms, 1, 1);
   const size_t b_region = kp.b_resident ? kp.b_res_bytes : static_cast<size_t>(kp.b_stages) * kp.b_sub_bytes;
-  size_t smem = static_cast<size_t>(kp.a_stages) * kp.a_bytes + b_region + staging + 1024;
+  size_t smem = static_cast<size_t>(kp.a_stages) * kp.a_stride + b_region + staging + 1024;
   if (smem < 120 * 1024) smem = 120 * 1024;
   op->smem_bytes = smem;
 

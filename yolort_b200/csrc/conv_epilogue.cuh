@@ -126,13 +126,20 @@ __device__ __forceinline__ void epilogue_box(const EpilogueParams& p, uint32_t t
       v[j + 3] = __uint_as_float(acc[j >> 4][(j & 15) + 3]) + b4.w;
     }
     if (p.act == YB_ACT_SILU) {
-      float e[kBatch];
+      // SiLU(v) = h + h*tanh(h), h = v/2.  tanh.approx.f16x2 evaluates two elements per MUFU op (0.5 op per
+      // element instead of the 2 of exp+rcp, which made 1x1 layers MUFU-bound: 16 ops/clk/SM).  Its ~2^-11
+      // absolute error is below the fp16 rounding of the stored activation for |v| < ~4 (measured network
+      // rel-RMS error 6.4e-4 vs 4.6e-4 with an exact SiLU).
 #pragma unroll
-      for (int j = 0; j < kBatch; ++j) e[j] = ex2_approx(v[j] * -1.4426950408889634f);
-#pragma unroll
-      for (int j = 0; j < kBatch; ++j) e[j] = rcp_approx(1.0f + e[j]);
-#pragma unroll
-      for (int j = 0; j < kBatch; ++j) v[j] *= e[j];
+      for (int j = 0; j < kBatch; j += 2) {
+        const float h0 = 0.5f * v[j], h1 = 0.5f * v[j + 1];
+        const uint32_t hp = pack2<false>(h0, h1);
+        uint32_t tp;
+        asm("tanh.approx.f16x2 %0, %1;" : "=r"(tp) : "r"(hp));
+        const float2 t = unpack2<false>(tp);
+        v[j] = fmaf(h0, t.x, h0);
+        v[j + 1] = fmaf(h1, t.y, h1);
+      }
     }
     if (has_res) {
 #pragma unroll

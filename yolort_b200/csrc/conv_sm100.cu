@@ -185,9 +185,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int j = 0; j < cnt; ++j) {
             const uint32_t a_addr = a_base + j * p.a_stage_bytes;
             const uint32_t b_addr = p.b_resident ? b_res_addr + (it0 + j) * p.b_stage_bytes : b_base + j * p.b_stage_bytes;
-            for (int k = 0; k < kk; ++k) {
-              const uint64_t da = make_kmajor_desc(a_addr + k * 32, row_bytes);
-              const uint64_t db = make_kmajor_desc(b_addr + k * 32, row_bytes);
+            // descriptors differ only in the 14-bit start-address field: build once, then add 2 (= 32 B) per K step
+            uint64_t da = make_kmajor_desc(a_addr, row_bytes);
+            uint64_t db = make_kmajor_desc(b_addr, row_bytes);
+            for (int k = 0; k < kk; ++k, da += 2, db += 2) {
               if (!(p.dbg & 2)) umma_f16(tmem_d, da, db, p.idesc, (it0 | j | k) != 0 ? 1u : 0u);
             }
           }

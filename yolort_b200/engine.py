@@ -59,6 +59,7 @@ class _Op:
     residual: Optional[_View] = None
     name: str = ""
     flops_per_pixel: int = 0               # 2*MACs per output pixel of the REFERENCE conv (algorithmic work)
+    pack: int = 1                          # horizontally adjacent pixels treated as ONE pixel with pack x channels
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -86,6 +87,27 @@ def stem_to_s2d(w: torch.Tensor) -> torch.Tensor:
                     q = (dy * 2 + dx) * 4
                     out[:, q:q + 3, a, b] = w[:, :, 2 * a + dy, 2 * b + dx]
     return out
+
+
+def stem_superpixel(w: torch.Tensor, b: torch.Tensor, pack: int = 4) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Rewrite a 3x3/s1/p1 conv over C-channel pixels as a 3x3/s1/p1 conv over "super-pixels" of `pack`
+    horizontally adjacent pixels (pack*C input channels, pack*Co output channels, width / pack).
+
+    Exact: output pixel x = pack*X + po reads input pixels x + b - 1 = pack*(X + S - 1) + pi, i.e. column tap
+    b = pack*(S-1) + pi - po + 1 when that lies in {0,1,2}; all other entries of the expanded kernel are zero.
+    The memory layouts do not change (NHWC rows are contiguous), only the GEMM's shape does: the 16-channel
+    space-to-depth stem input would otherwise be fetched by the TMA unit in 32-byte rows (measured 372 us for
+    the loads alone); as 128-byte super-pixels the stem runs like an ordinary 64->128 3x3 layer."""
+    co, ci, kh, kw = w.shape
+    assert (kh, kw) == (3, 3)
+    out = torch.zeros((pack * co, pack * ci, 3, 3), dtype=w.dtype)
+    for po in range(pack):
+        for pi in range(pack):
+            for S in range(3):
+                bcol = pack * (S - 1) + pi - po + 1
+                if 0 <= bcol <= 2:
+                    out[po * co:(po + 1) * co, pi * ci:(pi + 1) * ci, :, S] = w[:, :, :, bcol]
+    return out, b.repeat(pack)
 
 
 def pack_weight(w: torch.Tensor, dtype: torch.dtype, device: torch.device) -> Tuple[torch.Tensor, int, int]:
@@ -118,13 +140,15 @@ class _Lowering:
         self.bufs.append(b)
         return b
 
-    def conv(self, name, w, b, src: _View, dst: _View, k, s, p, act, residual=None, ref_flops_per_pixel=None):
-        assert w.shape[1] == src.C and w.shape[0] <= dst.C, (name, tuple(w.shape), src.C, dst.C)
+    def conv(self, name, w, b, src: _View, dst: _View, k, s, p, act, residual=None, ref_flops_per_pixel=None, pack=1):
+        assert w.shape[1] == src.C * pack and w.shape[0] <= dst.C * pack, (name, tuple(w.shape), src.C, dst.C)
+        if pack > 1:
+            assert src.ch0 == 0 and src.C == src.buf.C and dst.ch0 == 0 and dst.C == dst.buf.C and residual is None
         wp, _, co_pad = pack_weight(w, self.dtype, self.device)
         bp = pack_bias(b, co_pad, self.device)
         if ref_flops_per_pixel is None:
             ref_flops_per_pixel = 2 * w.shape[0] * w.shape[1] * k * k
-        self.ops.append(_Op(_C.YB_OP_CONV, src, dst, k, s, p, act, wp, bp, residual, name, ref_flops_per_pixel))
+        self.ops.append(_Op(_C.YB_OP_CONV, src, dst, k, s, p, act, wp, bp, residual, name, ref_flops_per_pixel, pack))
 
     def conv_module(self, name, m: Conv, src: _View, dst: _View, residual=None):
         w, b = fold_conv_bn(m)
@@ -179,8 +203,9 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
         raise NotImplementedError("stem must be the r6.0 6x6/s2/p2 convolution")
     w, b = fold_conv_bn(stem)
     t0 = L.buf("body.0", 2, w.shape[0])
-    L.conv("body.0(stem as 3x3 over s2d)", stem_to_s2d(w), b, _View(x0, 0, 16), _View(t0, 0, w.shape[0]), 3, 1, 1,
-           _C.YB_ACT_SILU, ref_flops_per_pixel=2 * w.shape[0] * 3 * 36)
+    w_sp, b_sp = stem_superpixel(stem_to_s2d(w), b, 4)
+    L.conv("body.0(stem: 3x3 over s2d super-pixels)", w_sp, b_sp, _View(x0, 0, 16), _View(t0, 0, w.shape[0]), 3, 1, 1,
+           _C.YB_ACT_SILU, ref_flops_per_pixel=4 * 2 * w.shape[0] * 3 * 36, pack=4)
 
     # concat buffers of the neck (path_aggregation_network.py:215-237)
     cat1 = L.buf("pan.cat1[up(lat1)|f6]", 16, 2 * c4)
@@ -270,10 +295,14 @@ class PlanInstance:
             hi, wi = H // op.src.buf.div, W // op.src.buf.div
             ho, wo = H // op.dst.buf.div, W // op.dst.buf.div
             d.kind, d.dtype = op.kind, code
+            k = op.pack
+            if wi % k or wo % k:
+                raise ValueError(f"{op.name}: width {wi} not divisible by the pixel packing {k}")
+            wi, wo = wi // k, wo // k
             d.N, d.H, d.W = N, hi, wi
-            d.Cin, d.in_cstride, d.in_ = op.src.C, op.src.buf.C, ptr(op.src)
+            d.Cin, d.in_cstride, d.in_ = op.src.C * k, op.src.buf.C * k, ptr(op.src)
             d.Ho, d.Wo = ho, wo
-            d.Cout, d.out_cstride, d.out = op.dst.C, op.dst.buf.C, ptr(op.dst)
+            d.Cout, d.out_cstride, d.out = op.dst.C * k, op.dst.buf.C * k, ptr(op.dst)
             d.ksize, d.stride, d.pad, d.act = op.ksize, op.stride, op.pad, op.act
             flops = 0
             if op.kind == _C.YB_OP_CONV:
