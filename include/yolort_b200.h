@@ -100,7 +100,7 @@ typedef struct {
   const float* bias;            /* [Cout_pad] fp32 (folded BN shift, or the head's conv bias)     */
   const void* residual;         /* optional NHWC view added after the activation (Bottleneck)    */
   int32_t res_cstride;
-  int32_t reserved;
+  int32_t reserved;             /* bit 0: keep a 3x3/s1 conv on the generic im2col kernel          */
 } yb_op_desc;
 
 typedef struct yb_plan yb_plan;

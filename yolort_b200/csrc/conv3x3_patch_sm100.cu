@@ -363,6 +363,7 @@ struct PatchConvOp {
 // Eligibility: 3x3 / stride 1 / pad 1 and a feature map that 16x8 tiles cover with little waste.
 bool patch_conv_eligible(const yb_op_desc& d) {
   if (d.kind != YB_OP_CONV || d.ksize != 3 || d.stride != 1 || d.pad != 1) return false;
+  if (d.reserved & 1) return false;   // caller asked for the generic im2col kernel
   const char* env = getenv("YB_DISABLE_PATCH_CONV");
   if (env && env[0] == '1') return false;
   const int ty = (d.H + kTileH - 1) / kTileH, tx = (d.W + kTileW - 1) / kTileW;

@@ -60,6 +60,7 @@ class _Op:
     name: str = ""
     flops_per_pixel: int = 0               # 2*MACs per output pixel of the REFERENCE conv (algorithmic work)
     pack: int = 1                          # horizontally adjacent pixels treated as ONE pixel with pack x channels
+    force_im2col: bool = False             # keep this 3x3/s1 conv on the generic im2col kernel
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -140,7 +141,7 @@ class _Lowering:
         self.bufs.append(b)
         return b
 
-    def conv(self, name, w, b, src: _View, dst: _View, k, s, p, act, residual=None, ref_flops_per_pixel=None, pack=1):
+    def conv(self, name, w, b, src: _View, dst: _View, k, s, p, act, residual=None, ref_flops_per_pixel=None, pack=1, force_im2col=False):
         assert w.shape[1] == src.C * pack and w.shape[0] <= dst.C * pack, (name, tuple(w.shape), src.C, dst.C)
         if pack > 1:
             assert src.ch0 == 0 and src.C == src.buf.C and dst.ch0 == 0 and dst.C == dst.buf.C and residual is None
@@ -148,7 +149,7 @@ class _Lowering:
         bp = pack_bias(b, co_pad, self.device)
         if ref_flops_per_pixel is None:
             ref_flops_per_pixel = 2 * w.shape[0] * w.shape[1] * k * k
-        self.ops.append(_Op(_C.YB_OP_CONV, src, dst, k, s, p, act, wp, bp, residual, name, ref_flops_per_pixel, pack))
+        self.ops.append(_Op(_C.YB_OP_CONV, src, dst, k, s, p, act, wp, bp, residual, name, ref_flops_per_pixel, pack, force_im2col))
 
     def conv_module(self, name, m: Conv, src: _View, dst: _View, residual=None):
         w, b = fold_conv_bn(m)
@@ -203,9 +204,12 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
         raise NotImplementedError("stem must be the r6.0 6x6/s2/p2 convolution")
     w, b = fold_conv_bn(stem)
     t0 = L.buf("body.0", 2, w.shape[0])
-    w_sp, b_sp = stem_superpixel(stem_to_s2d(w), b, 4)
+    import os
+    spk = int(os.environ.get("YB_STEM_PACK", "4"))
+    w_sp, b_sp = stem_superpixel(stem_to_s2d(w), b, spk)
     L.conv("body.0(stem: 3x3 over s2d super-pixels)", w_sp, b_sp, _View(x0, 0, 16), _View(t0, 0, w.shape[0]), 3, 1, 1,
-           _C.YB_ACT_SILU, ref_flops_per_pixel=4 * 2 * w.shape[0] * 3 * 36, pack=4)
+           _C.YB_ACT_SILU, ref_flops_per_pixel=spk * 2 * w.shape[0] * 3 * 36, pack=spk,
+           force_im2col=os.environ.get("YB_STEM_IM2COL", "1") == "1")
 
     # concat buffers of the neck (path_aggregation_network.py:215-237)
     cat1 = L.buf("pan.cat1[up(lat1)|f6]", 16, 2 * c4)
@@ -309,6 +313,7 @@ class PlanInstance:
                 d.weight, d.bias = op.weight.data_ptr(), op.bias.data_ptr()
                 d.Cout_pad, _, d.Cin_pad = op.weight.shape
                 flops = N * ho * wo * op.flops_per_pixel
+            d.reserved = 1 if op.force_im2col else 0
             if op.residual is not None:
                 d.residual, d.res_cstride = ptr(op.residual), op.residual.buf.C
             descs.append(d)
