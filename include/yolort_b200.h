@@ -145,6 +145,9 @@ typedef struct {
 } yb_nms_params;
 
 size_t yb_decode_nms_workspace_bytes(const yb_nms_params* p, const yb_head_level* levels);
+/* Debug aid: byte offset inside the workspace of 16 int64 words; words [4,10) hold the clock counts of the
+ * NMS kernel's phases for image 0 of the last call (sort, kept-list test, compaction, bit-matrix, resolve, rest). */
+size_t yb_decode_nms_debug_offset(const yb_nms_params* p, const yb_head_level* levels);
 
 /* Outputs are padded to max_det per image: boxes [n][max_det][4] fp32 (xyxy, rescaled to the
  * original image if rescale_dev != NULL: [n][3] = gain, pad_x, pad_y), scores [n][max_det],

@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = (
     "yb_plan_num_launches",
     "yb_plan_destroy",
     "yb_decode_nms_workspace_bytes",
+    "yb_decode_nms_debug_offset",
     "yb_decode_nms",
     "yb_batched_nms_workspace_bytes",
     "yb_batched_nms",
@@ -124,6 +125,8 @@ def lib() -> ctypes.CDLL:
     L.yb_plan_destroy.argtypes = [ctypes.c_void_p]
     L.yb_decode_nms_workspace_bytes.restype = ctypes.c_size_t
     L.yb_decode_nms_workspace_bytes.argtypes = [ctypes.POINTER(NmsParams), ctypes.POINTER(HeadLevel)]
+    L.yb_decode_nms_debug_offset.restype = ctypes.c_size_t
+    L.yb_decode_nms_debug_offset.argtypes = [ctypes.POINTER(NmsParams), ctypes.POINTER(HeadLevel)]
     L.yb_decode_nms.argtypes = [
         ctypes.POINTER(NmsParams), ctypes.POINTER(HeadLevel), ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -322,7 +325,15 @@ def decode_nms_padded(head_outputs: List[torch.Tensor], layout: str, strides: Se
                               boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), counts.data_ptr(),
                               status.data_ptr(), arena.ws.data_ptr(), arena.ws.numel(), current_stream_ptr(dev)),
           "yb_decode_nms")
+    arena.debug_offset = lib().yb_decode_nms_debug_offset(ctypes.byref(p), levels)
     return boxes, scores, labels, counts, status
+
+
+def nms_phase_clocks(device) -> list:
+    """Debug: clock counts of the NMS kernel phases for image 0 of the last decode_nms call on `device`."""
+    arena = _arenas[torch.device(device)]
+    off = arena.debug_offset
+    return arena.ws[off: off + 128].view(torch.int64)[4:10].cpu().tolist()
 
 
 def decode_nms(head_outputs: List[torch.Tensor], layout: str, strides, anchors_px, score_thresh: float,

@@ -337,6 +337,16 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
 
   const int img = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long t_prev = clock64();
+  int t_slot = 4;
+#define YB_NMS_TICK()                                            \
+  do {                                                           \
+    if (img == 0 && tid == 0 && t_slot < 16) {                   \
+      const long long t_now = clock64();                         \
+      ws.status[t_slot++] += t_now - t_prev;                     \
+      t_prev = t_now;                                            \
+    }                                                            \
+  } while (0)
   const long long raw_count = ws.img_count[img];
   const int count = static_cast<int>(raw_count < p.cap_per_image ? raw_count : p.cap_per_image);
   if (tid == 0) {
@@ -364,6 +374,7 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
     sorted = block_radix_sort(keys_g, ws.keys_b + static_cast<long long>(img) * p.cap_per_image, count, s_scratch);
   }
   __syncthreads();
+  YB_NMS_TICK();  // slot 4: load + sort
 
   bool trick;
   if (p.semantics == YB_NMS_TV_AUTO)
@@ -416,6 +427,7 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
       }
       alive = !hit;
     }
+    if (base == 0) YB_NMS_TICK();  // slot 5: phase A (first batch)
     // ---- B: order-preserving compaction of the survivors ----
     const uint32_t bal = __ballot_sync(0xffffffffu, alive);
     if (lane == 0) s_warp_tot[warp] = __popc(bal);
@@ -439,6 +451,7 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
     __syncthreads();
     const int S = s_nsurv;
     const int nwords = (S + 31) >> 5;
+    if (base == 0) YB_NMS_TICK();  // slot 6: compaction
     // suppression bit-matrix: bit j of row i set iff survivor i (if kept) suppresses survivor j > i
     if (tid < S) {
       const float4 bi = sv_box[tid];
@@ -459,6 +472,7 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
       }
     }
     __syncthreads();
+    if (base == 0) YB_NMS_TICK();  // slot 7: bit-matrix (includes the barrier before)
     // ---- C: sequential resolution ----
     // One thread walks the survivors in order; the "removed" set (<= 512 bits) lives in 16 registers, so the
     // only memory traffic is 16 independent shared-memory loads per KEPT survivor (no cross-lane exchange on
@@ -491,6 +505,7 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
       s_newkept = kc - kc0;
     }
     __syncthreads();
+    if (base == 0) YB_NMS_TICK();  // slot 8: resolve
     // ---- D: append the kept survivors ----
     if (tid < S && ((s_keep[tid >> 5] >> (tid & 31)) & 1u)) {
       int rank = __popc(s_keep[tid >> 5] & ((1u << (tid & 31)) - 1u));
@@ -521,7 +536,9 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
     if (s_kcount >= p.max_det) break;
   }
   __syncthreads();
+  YB_NMS_TICK();  // slot 9: append + remaining batches
   if (tid == 0) p.out_counts[img] = s_kcount;
+#undef YB_NMS_TICK
 }
 
 // explicit-candidate key builder for yb_batched_nms
@@ -541,6 +558,7 @@ __global__ void init_counters_kernel(Workspace ws, int n, long long* status, int
     ws.img_maxc[i] = float_to_ordered_int(-INFINITY);
   }
   if (i < 4 && status) status[i] = 0;
+  if (i < 16) ws.status[i] = 0;
 }
 
 size_t align256(size_t v) { return (v + 255) & ~static_cast<size_t>(255); }
@@ -558,7 +576,7 @@ size_t carve(Workspace& ws, uint8_t* base, int n, long long cap, long long ancho
   ws.img_maxc = reinterpret_cast<int*>(base + off);
   off += align256(static_cast<size_t>(n) * 4);
   ws.status = reinterpret_cast<long long*>(base + off);
-  off += align256(4 * sizeof(long long));
+  off += align256(16 * sizeof(long long));   // [0,4) status, [4,16) phase timers of image 0 (debug)
   return off;
 }
 
@@ -593,6 +611,15 @@ extern "C" size_t yb_decode_nms_workspace_bytes(const yb_nms_params* p, const yb
   Workspace ws;
   const long long cap = (p->max_candidates + p->n_images - 1) / p->n_images;
   return carve(ws, nullptr, p->n_images, cap > 0 ? cap : 1, anchors_per_image(p, levels));
+}
+
+// debug: byte offset, inside the workspace, of 16 int64 words: [4..10) = per-phase clock counts of image 0
+extern "C" size_t yb_decode_nms_debug_offset(const yb_nms_params* p, const yb_head_level* levels) {
+  if (!p || !levels || p->n_images <= 0) return 0;
+  Workspace ws;
+  const long long cap = (p->max_candidates + p->n_images - 1) / p->n_images;
+  carve(ws, nullptr, p->n_images, cap > 0 ? cap : 1, anchors_per_image(p, levels));
+  return reinterpret_cast<size_t>(ws.status);
 }
 
 extern "C" int yb_decode_nms(const yb_nms_params* p, const yb_head_level* levels, const float* rescale_dev,
