@@ -206,6 +206,10 @@ __device__ __forceinline__ bool iou_over(const float4& a, float area_a, const fl
   const float w = fmaxf(0.f, __fsub_rn(xx2, xx1));
   const float h = fmaxf(0.f, __fsub_rn(yy2, yy1));
   const float inter = __fmul_rn(w, h);
+  // inter == 0 gives ovr = +-0 or NaN (0/0): never "> thr" for thr >= 0, so the IEEE division (a ~40
+  // instruction slow path, and the common case: most pairs are disjoint) can be skipped without changing
+  // any decision; for thr < 0 fall through to the exact expression.
+  if (!(inter > 0.f) && thr >= 0.f) return false;
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
   return ovr > thr;
 }
@@ -461,11 +465,21 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
         uint32_t bits = 0;
         const int j0 = w << 5;
         if (w < nwords && j0 + 31 > tid) {
+          // step 1: which later survivors can this one suppress at all (same class, or any in offset-trick mode)
+          uint32_t cand;
           const int jend = min(32, S - j0);
-          for (int b = 0; b < jend; ++b) {
-            const int jj = j0 + b;
-            if (jj > tid && (trick || sv_label[jj] == li) && iou_over(bi, ai, sv_box[jj], sv_area[jj], p.iou_thresh))
-              bits |= 1u << b;
+          if (trick) {
+            cand = jend == 32 ? 0xffffffffu : ((1u << jend) - 1u);
+          } else {
+            cand = 0;
+            for (int b = 0; b < jend; ++b) cand |= (sv_label[j0 + b] == li ? 1u : 0u) << b;
+          }
+          if (j0 <= tid) cand &= ~((2u << (tid - j0)) - 1u);   // only j > i
+          // step 2: IoU only for those (a warp now iterates max-popcount times instead of 32)
+          while (cand) {
+            const int b = __ffs(cand) - 1;
+            cand &= cand - 1;
+            if (iou_over(bi, ai, sv_box[j0 + b], sv_area[j0 + b], p.iou_thresh)) bits |= 1u << b;
           }
         }
         s_mask[tid * (kSweep / 32) + w] = bits;
@@ -477,32 +491,19 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
     // One thread walks the survivors in order; the "removed" set (<= 512 bits) lives in 16 registers, so the
     // only memory traffic is 16 independent shared-memory loads per KEPT survivor (no cross-lane exchange on
     // the critical path).
-    if (tid == 0) {
-      uint32_t removed[kSweep / 32], keep[kSweep / 32];
-#pragma unroll
-      for (int w = 0; w < kSweep / 32; ++w) removed[w] = keep[w] = 0;
+    if (warp == 0) {
+      uint32_t removed = 0, keep = 0;   // lane l owns word l of both sets (S <= 512 -> 16 words)
       int kc = s_kcount;
       const int kc0 = kc;
-      bool full = false;
-#pragma unroll
-      for (int w = 0; w < kSweep / 32; ++w) {
-        if (full || (w << 5) >= S) continue;
-        const int lim = min(32, S - (w << 5));
-        for (int b = 0; b < lim; ++b) {
-          if ((removed[w] >> b) & 1u) continue;
-          keep[w] |= 1u << b;
-          const uint32_t* row = s_mask + ((w << 5) + b) * (kSweep / 32);
-#pragma unroll
-          for (int v = 0; v < kSweep / 32; ++v) removed[v] |= row[v];
-          if (++kc >= p.max_det) {
-            full = true;
-            break;
-          }
-        }
+      for (int i = 0; i < S; ++i) {
+        const bool mine = lane == (i >> 5);
+        if (__any_sync(0xffffffffu, mine && ((removed >> (i & 31)) & 1u))) continue;
+        if (mine) keep |= 1u << (i & 31);
+        if (lane < nwords) removed |= s_mask[i * (kSweep / 32) + lane];
+        if (++kc >= p.max_det) break;
       }
-#pragma unroll
-      for (int w = 0; w < kSweep / 32; ++w) s_keep[w] = keep[w];
-      s_newkept = kc - kc0;
+      if (lane < kSweep / 32) s_keep[lane] = keep;
+      if (lane == 0) s_newkept = kc - kc0;
     }
     __syncthreads();
     if (base == 0) YB_NMS_TICK();  // slot 8: resolve

@@ -18,6 +18,7 @@ namespace yb {
 namespace {
 
 constexpr int kMaxImagesPerLaunch = 64;
+constexpr int kRowsPerBlock = 8;   // s2d rows per CTA (amortises the 1 KB LUT staging)
 
 struct ImgGeom {
   const void* src;
@@ -32,7 +33,7 @@ template <typename SrcT>
 __device__ __forceinline__ float load_src(const SrcT* p, const float* lut);
 template <>
 __device__ __forceinline__ float load_src<uint8_t>(const uint8_t* p, const float* lut) {
-  return lut[__ldg(p)];
+  return lut[__ldg(p)];   // `lut` points to the shared-memory copy staged by the kernel
 }
 template <>
 __device__ __forceinline__ float load_src<float>(const float* p, const float*) {
@@ -113,7 +114,13 @@ __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) {
 // NCHW destination (reference layout): thread per (y, x), three planes.
 template <typename SrcT, typename DstT>
 __global__ void letterbox_nchw_kernel(const __grid_constant__ BatchGeom bg, int img0, int Hb, int Wb,
-                                      float fill, const float* __restrict__ lut, DstT* __restrict__ dst) {
+                                      float fill, const float* lut, DstT* __restrict__ dst) {
+  __shared__ float s_lut[256];
+  if (lut != nullptr) {   // uint8 sources: one coalesced 1 KB read per CTA instead of a global lookup per texel
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut[i];
+    __syncthreads();
+    lut = s_lut;
+  }
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   const int li = blockIdx.z;
@@ -129,29 +136,36 @@ __global__ void letterbox_nchw_kernel(const __grid_constant__ BatchGeom bg, int 
 // Space-to-depth NHWC destination [N, Hb/2, Wb/2, 16]: thread per 2x2 pixel block, one 32-byte store.
 template <typename SrcT, typename DstT>
 __global__ void letterbox_s2d_kernel(const __grid_constant__ BatchGeom bg, int img0, int Hb, int Wb,
-                                     float fill, const float* __restrict__ lut, DstT* __restrict__ dst) {
+                                     float fill, const float* lut, DstT* __restrict__ dst) {
+  __shared__ float s_lut[256];
+  if (lut != nullptr) {   // uint8 sources: one coalesced 1 KB read per CTA instead of a global lookup per texel
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_lut[i] = lut[i];
+    __syncthreads();
+    lut = s_lut;
+  }
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
-  const int Y = blockIdx.y;
   const int li = blockIdx.z;
   const int W2 = Wb >> 1, H2 = Hb >> 1;
   if (X >= W2) return;
-  __align__(16) DstT v[16];
+  for (int Y = blockIdx.y * kRowsPerBlock; Y < min(H2, (blockIdx.y + 1) * kRowsPerBlock); ++Y) {
+    __align__(16) DstT v[16];
 #pragma unroll
-  for (int dy = 0; dy < 2; ++dy) {
+    for (int dy = 0; dy < 2; ++dy) {
 #pragma unroll
-    for (int dx = 0; dx < 2; ++dx) {
-      float rgb[3];
-      sample_rgb<SrcT>(bg.img[li], lut, 2 * Y + dy, 2 * X + dx, fill, rgb);
-      const int q = (dy * 2 + dx) * 4;
-      v[q + 0] = cvt_out<DstT>(rgb[0]);
-      v[q + 1] = cvt_out<DstT>(rgb[1]);
-      v[q + 2] = cvt_out<DstT>(rgb[2]);
-      v[q + 3] = cvt_out<DstT>(0.f);
+      for (int dx = 0; dx < 2; ++dx) {
+        float rgb[3];
+        sample_rgb<SrcT>(bg.img[li], lut, 2 * Y + dy, 2 * X + dx, fill, rgb);
+        const int q = (dy * 2 + dx) * 4;
+        v[q + 0] = cvt_out<DstT>(rgb[0]);
+        v[q + 1] = cvt_out<DstT>(rgb[1]);
+        v[q + 2] = cvt_out<DstT>(rgb[2]);
+        v[q + 3] = cvt_out<DstT>(0.f);
+      }
     }
+    DstT* o = dst + ((static_cast<size_t>(img0 + li) * H2 + Y) * W2 + X) * 16;
+    reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(v)[0];
+    reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(v)[1];
   }
-  DstT* o = dst + ((static_cast<size_t>(img0 + li) * H2 + Y) * W2 + X) * 16;
-  reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(v)[0];
-  reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(v)[1];
 }
 
 template <typename SrcT, typename DstT>
@@ -163,7 +177,7 @@ int launch_typed(const BatchGeom& bg, int img0, int count, int Hb, int Wb, float
     letterbox_nchw_kernel<SrcT, DstT><<<grid, threads, 0, stream>>>(bg, img0, Hb, Wb, fill, lut,
                                                                     static_cast<DstT*>(dst));
   } else {
-    dim3 grid((Wb / 2 + threads - 1) / threads, Hb / 2, count);
+    dim3 grid((Wb / 2 + threads - 1) / threads, (Hb / 2 + kRowsPerBlock - 1) / kRowsPerBlock, count);
     letterbox_s2d_kernel<SrcT, DstT><<<grid, threads, 0, stream>>>(bg, img0, Hb, Wb, fill, lut,
                                                                    static_cast<DstT*>(dst));
   }

@@ -101,7 +101,8 @@ class YOLOv5(nn.Module):
         if isinstance(samples, Tensor):
             return [place(samples)]
         if isinstance(samples, (list, tuple)) and len(samples) > 0 and all(isinstance(s, Tensor) for s in samples):
-            return [place(s) for s in samples]
+            packed = self._place_packed(samples, p)
+            return packed if packed is not None else [place(s) for s in samples]
         if isinstance(samples, str):
             samples = [samples]
         if isinstance(samples, (list, tuple)) and all(isinstance(s, str) for s in samples):
@@ -109,6 +110,30 @@ class YOLOv5(nn.Module):
         raise NotImplementedError(
             f"The type of the sample is {type(samples)}, we currently don't support it now, the "
             "samples should be either a tensor, list of tensors, a image path or list of image paths.")
+
+    @staticmethod
+    def _place_packed(samples, p):
+        """Host images that sit back to back in ONE buffer (e.g. slices of a pinned batch tensor) cross PCIe as a
+        single asynchronous copy instead of one cudaMemcpy per image; returns None when that does not apply."""
+        first = samples[0]
+        if first.is_cuda or first.dtype != torch.uint8 and not first.is_floating_point():
+            return None
+        esz = first.element_size()
+        nxt = first.data_ptr()
+        for t in samples:
+            if t.is_cuda or t.dtype != first.dtype or not t.is_contiguous() or t.data_ptr() != nxt:
+                return None
+            nxt += t.numel() * esz
+        total = (nxt - first.data_ptr()) // esz
+        flat = torch.empty(0, dtype=first.dtype).set_(first.untyped_storage(), first.storage_offset(), (total,))
+        dev = flat.to(p.device, non_blocking=True)
+        if first.dtype != torch.uint8:
+            dev = dev.type_as(p)
+        out, off = [], 0
+        for t in samples:
+            out.append(dev[off: off + t.numel()].view(t.shape))
+            off += t.numel()
+        return out
 
     @classmethod
     def load_from_yolov5(cls, checkpoint_path: str, *, size: Tuple[int, int] = (640, 640), size_divisible: int = 32,
