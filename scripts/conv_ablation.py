@@ -40,7 +40,7 @@ def timeit(plans, reps=30):
     return e0.elapsed_time(e1) / reps * 1e3
 
 SHAPES = [  # name, H, W, Cin, Cout, k, s, p, residual
-    ("stem 16->32 k3 @320", 320, 320, 16, 32, 3, 1, 1, False),
+    ("stem sp4 64->128 k3 @320x80", 320, 80, 64, 128, 3, 1, 1, False),
     ("1x1 64->64 @160", 160, 160, 64, 64, 1, 1, 0, False),
     ("3x3 32->32 @160 +res", 160, 160, 32, 32, 3, 1, 1, True),
     ("1x1 128->128 @80", 80, 80, 128, 128, 1, 1, 0, False),
@@ -55,7 +55,8 @@ if __name__ == "__main__":
     for name, H, W, Cin, Cout, k, s, p, res in SHAPES:
         variants = [("default", {})]
         if k == 3 and s == 1:
-            variants.append(("im2col", {"YB_DISABLE_PATCH_CONV": "1"}))
+            variants = [("patch/tma", {"YB_PATCH_LOADER": "0"}), ("patch/cpasync", {"YB_PATCH_LOADER": "1"}),
+                        ("im2col", {"YB_DISABLE_PATCH_CONV": "1"})]
         for vname, env in variants:
             row = []
             for dbg in (0, 1, 4, 2, 3):

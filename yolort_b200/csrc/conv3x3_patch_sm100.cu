@@ -244,6 +244,27 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       const int row_bytes = p.block_k * 2;
       const int cpr = row_bytes >> 4;                    // 16-byte chunks per pixel-row
       const int total = kPatchH * kPatchW * cpr;
+      // The copy pattern of a patch is the same for every tile: each thread precomputes, once, the shared-memory
+      // offset (swizzled), the global element offset relative to the patch origin and the (row, column) of its
+      // <= kMaxOps chunks; per tile only the origin pointer and two validity bit-masks change.
+      constexpr int kMaxOps = (kPatchH * kPatchW * 8 + kLoadWarps * 32 - 1) / (kLoadWarps * 32);
+      uint32_t soff[kMaxOps];
+      int goff[kMaxOps];
+      uint32_t hw[kMaxOps];
+      int nops = 0;
+#pragma unroll
+      for (int k = 0; k < kMaxOps; ++k) {
+        const int i = ltid + k * kLoadWarps * 32;
+        soff[k] = 0; goff[k] = 0; hw[k] = 0;
+        if (i < total) {
+          const int row = i / cpr, ch = i - row * cpr;
+          const int hh = row / kPatchW, ww = row - hh * kPatchW;
+          soff[k] = row * row_bytes + swizzle_chunk(row, ch, row_bytes) * 16;
+          goff[k] = (hh * p.W + ww) * p.in_cstride + ch * 8;
+          hw[k] = (static_cast<uint32_t>(hh) << 8) | static_cast<uint32_t>(ww) | (static_cast<uint32_t>(ch) << 16);
+          nops = k + 1;
+        }
+      }
       const uint16_t* in = reinterpret_cast<const uint16_t*>(p.in);
       int ka = 0;
       int pending_stage = -1;
@@ -253,20 +274,26 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const int t = m_tile - n_img * tiles_per_img;
         const int ty = t / p.tiles_x, tx = t - ty * p.tiles_x;
         const int y_base = ty * kTileH - 1, x_base = tx * kTileW - 1;
+        // bit hh of rowmask: input row y_base+hh exists; bit ww of colmask: input column x_base+ww exists
+        uint32_t rowmask = 0, colmask = 0;
+        for (int hh = 0; hh < kPatchH; ++hh) rowmask |= (static_cast<unsigned>(y_base + hh) < static_cast<unsigned>(p.H) ? 1u : 0u) << hh;
+        for (int ww = 0; ww < kPatchW; ++ww) colmask |= (static_cast<unsigned>(x_base + ww) < static_cast<unsigned>(p.W) ? 1u : 0u) << ww;
+        const long long origin = ((static_cast<long long>(n_img) * p.H + y_base) * p.W + x_base) * p.in_cstride;
         for (int c = 0; c < p.chunks; ++c, ++ka) {
           const int s = ka % p.a_stages;
           const uint32_t ph = (ka / p.a_stages) & 1;
           mbar_wait(&a_empty[s], ph ^ 1);
           const uint32_t dst_base = smem_u32(a_buf + static_cast<size_t>(s) * p.a_stride);
-          for (int i = ltid; i < total; i += kLoadWarps * 32) {
-            const int row = i / cpr, ch = i - row * cpr;
-            const int hh = row / kPatchW, ww = row - hh * kPatchW;
-            const int gy = y_base + hh, gx = x_base + ww;
-            const int ce = c * p.block_k + ch * 8;                   // first channel of this chunk
-            const bool ok = gy >= 0 && gy < p.H && gx >= 0 && gx < p.W && ce < p.Cin;
-            const uint16_t* src = ok ? in + ((static_cast<long long>(n_img) * p.H + gy) * p.W + gx) * p.in_cstride + ce : in;
-            const uint32_t dst = dst_base + row * row_bytes + swizzle_chunk(row, ch, row_bytes) * 16;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+          const uint16_t* src0 = in + origin + c * p.block_k;
+          const int cmax = p.Cin - c * p.block_k;          // channels of this chunk that exist (zero-fill the rest)
+#pragma unroll
+          for (int k = 0; k < kMaxOps; ++k) {
+            if (k < nops) {
+              const uint32_t hh = (hw[k] >> 8) & 0xff, ww = hw[k] & 0xff, ch = hw[k] >> 16;
+              const bool ok = ((rowmask >> hh) & (colmask >> ww) & 1u) && static_cast<int>(ch * 8) < cmax;
+              const uint16_t* src = ok ? src0 + goff[k] : in;
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_base + soff[k]), "l"(src), "r"(ok ? 16 : 0) : "memory");
+            }
           }
           asm volatile("cp.async.commit_group;" ::: "memory");
           if (pending_stage >= 0) {   // publish the previous patch while this one is in flight
