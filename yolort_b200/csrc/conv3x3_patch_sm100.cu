@@ -145,6 +145,10 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           const int s = ka % p.a_stages;
           const uint32_t ph = (ka / p.a_stages) & 1;
           mbar_wait(&a_empty[s], ph ^ 1);
+          if (p.dbg & 8) {   // ablation: no loads at all, only the pipeline handshake
+            mbar_arrive(&a_full[s]);
+            continue;
+          }
           mbar_expect_tx(&a_full[s], p.a_bytes);
           uint8_t* dst = a_buf + static_cast<size_t>(s) * p.a_stride;
           if (p.view_mode == 2) {

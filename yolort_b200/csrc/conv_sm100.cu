@@ -139,6 +139,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* a_dst = tiles + s * stage_bytes;
           uint8_t* b_dst = a_dst + p.kpg * p.a_stage_bytes;
+          if (p.dbg & 8) {   // ablation: no loads at all, only the pipeline handshake
+            mbar_arrive(&full_bar[s]);
+            continue;
+          }
           mbar_expect_tx(&full_bar[s], cnt * (a_bytes + (p.b_resident ? 0u : b_bytes)));
           for (int j = 0; j < cnt; ++j) {
             const int it = it0 + j;
