@@ -171,6 +171,44 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, descriptors given as (lo, hi) 32-bit halves: only `lo` (the 14-bit start address) changes between
+// the MMAs of a stage, so the issuing thread spends one IADD per operand instead of 64-bit arithmetic.
+template <bool kAccumulate>
+__device__ __forceinline__ void umma_f16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                              uint32_t b_hi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "n"(kAccumulate ? 1 : 0)
+      : "memory");
+}
+// Issue KK consecutive K=16 steps of one (A sub-tile, B sub-tile) pair; `first` clears the accumulator.
+template <int KK>
+__device__ __forceinline__ void umma_ksteps(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, bool first) {
+  if (first)
+    umma_f16_lohi<false>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc);
+  else
+    umma_f16_lohi<true>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc);
+#pragma unroll
+  for (int k = 1; k < KK; ++k) umma_f16_lohi<true>(tmem_d, a_lo + 2 * k, a_hi, b_lo + 2 * k, b_hi, idesc);
+}
+__device__ __forceinline__ void umma_ksteps_rt(int kk, uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t idesc, bool first) {
+  if (kk == 4)
+    umma_ksteps<4>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, first);
+  else if (kk == 2)
+    umma_ksteps<2>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, first);
+  else
+    umma_ksteps<1>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, first);
+}
+
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(

@@ -196,6 +196,17 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         mbar_wait(&b_full[0], 0);
         tc_fence_after();
       }
+      // per-tap start-address offsets of the A views (16-byte units) and the constant descriptor halves
+      uint32_t tap_off16[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int dy = tap / 3, dx = tap - dy * 3;
+        tap_off16[tap] = (p.view_mode == 2 ? dx * (p.a_bytes / 3) + dy * pitch * row_bytes : (dy * pitch + dx) * row_bytes) >> 4;
+      }
+      const uint32_t a_hi = static_cast<uint32_t>(make_view_desc(0, row_bytes, sbo, p.view_mode == 1 ? 0 : p.view_mode) >> 32);
+      const uint32_t b_hi = static_cast<uint32_t>(make_kmajor_desc(0, row_bytes) >> 32);
+      const uint32_t b_res_lo0 = (smem_u32(b_buf) & 0x3FFFFu) >> 4;
+      const uint32_t b_step16 = p.b_sub_bytes >> 4;
       int ka = 0, kb = 0, lt = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
         const int as = lt & 1;
@@ -208,25 +219,21 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           mbar_wait(&a_full[sa], (ka / p.a_stages) & 1);
           tc_fence_after();
           const uint32_t patch = smem_u32(a_buf + static_cast<size_t>(sa) * p.a_stride);
+          const uint32_t a_lo0 = (patch & 0x3FFFFu) >> 4;
+#pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            uint32_t b_addr;
+            uint32_t b_lo;
             int sb = 0;
             if (p.b_resident) {
-              b_addr = smem_u32(b_buf + static_cast<size_t>(c * 9 + tap) * p.b_sub_bytes);
+              b_lo = b_res_lo0 + static_cast<uint32_t>(c * 9 + tap) * b_step16;
             } else {
               sb = kb % p.b_stages;
               mbar_wait(&b_full[sb], (kb / p.b_stages) & 1);
               tc_fence_after();
-              b_addr = smem_u32(b_buf + static_cast<size_t>(sb) * p.b_sub_bytes);
+              b_lo = b_res_lo0 + static_cast<uint32_t>(sb) * b_step16;
             }
-            const int dy = tap / 3, dx = tap - dy * 3;
-            const uint32_t a_addr = p.view_mode == 2 ? patch + dx * (p.a_bytes / 3) + dy * pitch * row_bytes
-                                                     : patch + (dy * pitch + dx) * row_bytes;
-            uint64_t da = make_view_desc(a_addr, row_bytes, sbo, p.view_mode);
-            uint64_t db = make_kmajor_desc(b_addr, row_bytes);
-            for (int k = 0; k < kk; ++k, da += 2, db += 2) {
-              if (!(p.dbg & 2)) umma_f16(tmem_d, da, db, p.idesc, (c | tap | k) != 0 ? 1u : 0u);
-            }
+            if (!(p.dbg & 2))
+              umma_ksteps_rt(kk, tmem_d, a_lo0 + tap_off16[tap], a_hi, b_lo, b_hi, p.idesc, (c | tap) == 0);
             if (!p.b_resident) {
               umma_commit(&b_empty[sb]);
               ++kb;
@@ -343,14 +350,9 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * p.block_n;
       for (int c0 = 0; c0 < p.block_n; c0 += p.store_cols, ++store_idx) {
-        uint8_t* buf = my_staging + (p.store_bufs == 2 ? (store_idx & 1) : 0) * kStageBufBytes;
-        if (issuer) {
-          if (p.store_bufs == 2)
-            tma_store_wait_read<1>();
-          else
-            tma_store_wait_read<0>();
-        }
-        named_bar_sync(bar_id, 128);
+        // Two staging buffers, one barrier per box: before the barrier below the issuer waits until the PREVIOUS
+        // store has finished reading its buffer, which is the one the next box will overwrite.
+        uint8_t* buf = my_staging + (store_idx & 1) * kStageBufBytes;
         uint8_t* my_row = buf + row_in_tile * row_bytes;
         if (!(p.dbg & 1)) {
           if (p.ep.is_bf16)
@@ -364,6 +366,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           if (lane == 0) mbar_arrive(&acc_empty[g]);
         }
         fence_proxy_async_smem();
+        if (issuer) tma_store_wait_read<0>();
         named_bar_sync(bar_id, 128);
         if (issuer) {
           if (n0 + c0 < p.ep.Cout && !(p.dbg & 5)) tma_store_4d(&tmap_out, buf, n0 + c0, tx * kTileW, ty * kTileH, n_img);
@@ -430,7 +433,7 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
   kp.a_stride = (kp.a_bytes + 1023u) & ~1023u;
   kp.b_sub_bytes = (static_cast<uint32_t>(block_n * kp.block_k * 2) + 1023u) & ~1023u;
   kp.store_cols = (block_n % 64 == 0) ? 64 : ((block_n % 32 == 0) ? 32 : 16);
-  kp.store_bufs = block_n > kp.store_cols ? 2 : 1;
+  kp.store_bufs = 2;
   kp.bias_len = d.Cout_pad;
   {
     const char* e = getenv("YB_CONV_DBG");

@@ -171,6 +171,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tc_fence_after();
       }
       const uint32_t b_res_addr = smem_u32(b_res);
+      const uint32_t desc_hi = static_cast<uint32_t>(make_kmajor_desc(0, row_bytes) >> 32);
+      const uint32_t a_step16 = p.a_stage_bytes >> 4, b_step16 = p.b_stage_bytes >> 4;
       int kit = 0, lt = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
         const int as = lt & 1;
@@ -186,15 +188,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tc_fence_after();
           const uint32_t a_base = smem_u32(tiles + s * stage_bytes);
           const uint32_t b_base = a_base + p.kpg * p.a_stage_bytes;
-          for (int j = 0; j < cnt; ++j) {
-            const uint32_t a_addr = a_base + j * p.a_stage_bytes;
-            const uint32_t b_addr = p.b_resident ? b_res_addr + (it0 + j) * p.b_stage_bytes : b_base + j * p.b_stage_bytes;
-            // descriptors differ only in the 14-bit start-address field: build once, then add 2 (= 32 B) per K step
-            uint64_t da = make_kmajor_desc(a_addr, row_bytes);
-            uint64_t db = make_kmajor_desc(b_addr, row_bytes);
-            for (int k = 0; k < kk; ++k, da += 2, db += 2) {
-              if (!(p.dbg & 2)) umma_f16(tmem_d, da, db, p.idesc, (it0 | j | k) != 0 ? 1u : 0u);
-            }
+          // descriptors differ only in their 14-bit start-address field (16-byte units)
+          const uint32_t a_lo0 = (a_base & 0x3FFFFu) >> 4;
+          const uint32_t b_lo0 = ((p.b_resident ? b_res_addr + it0 * p.b_stage_bytes : b_base) & 0x3FFFFu) >> 4;
+          if (!(p.dbg & 2)) {
+            for (int j = 0; j < cnt; ++j)
+              umma_ksteps_rt(kk, tmem_d, a_lo0 + j * a_step16, desc_hi, b_lo0 + j * b_step16, desc_hi, p.idesc,
+                             (it0 | j) == 0);
           }
           umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
         }
@@ -227,9 +227,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * p.block_n;
       for (int c0 = 0; c0 < p.block_n; c0 += p.store_cols, ++store_idx) {
+        // Two staging buffers, one barrier per box: before the barrier below the issuer waits until the PREVIOUS
+        // store has finished reading its buffer, which is the one the next box will overwrite.
         uint8_t* buf = my_staging + (store_idx & 1) * kStageBufBytes;
-        if (issuer) tma_store_wait_read<1>();  // the store that used this buffer two boxes ago has read it
-        named_bar_sync(bar_id, 128);
         uint8_t* my_row = buf + row_in_tile * row_bytes;
         if (!(p.dbg & 1)) {
           if (p.ep.is_bf16)
@@ -244,6 +244,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (lane == 0) mbar_arrive(&acc_empty[g]);
         }
         fence_proxy_async_smem();
+        if (issuer) tma_store_wait_read<0>();
         named_bar_sync(bar_id, 128);
         if (issuer) {
           if (n0 + c0 < p.ep.Cout && !(p.dbg & 5)) tma_store_2d(&tmap_out, buf, n0 + c0, m0);
