@@ -51,14 +51,14 @@ SHAPES = [  # name, H, W, Cin, Cout, k, s, p, residual
     ("3x3 256->256 @20", 20, 20, 256, 256, 3, 1, 1, False),
 ]
 if __name__ == "__main__":
-    print(f"{'layer':26s} {'variant':10s} " + " ".join(f"dbg{d:<2d}" .rjust(9) for d in (0, 1, 2, 3, 11)) + "   (us, 4 rotating buffers | same buffer for dbg0)")
+    print(f"{'layer':26s} {'variant':10s} " + " ".join(f"dbg{d:<2d}" .rjust(9) for d in (0, 1, 3, 11, 27)) + "   (us, 4 rotating buffers | same buffer for dbg0)")
     for name, H, W, Cin, Cout, k, s, p, res in SHAPES:
         variants = [("default", {})]
         if k == 3 and s == 1:
             variants = [("patch/tma", {"YB_PATCH_LOADER": "0"}), ("im2col", {"YB_DISABLE_PATCH_CONV": "1"})]
         for vname, env in variants:
             row = []
-            for dbg in (0, 1, 2, 3, 11):
+            for dbg in (0, 1, 3, 11, 27):
                 os.environ["YB_CONV_DBG"] = str(dbg)
                 for kk, vv in env.items(): os.environ[kk] = vv
                 plans, keep = build(32, H, W, Cin, Cout, k, s, p, res, 4)

@@ -344,6 +344,14 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       const int y = ty * kTileH + (row_in_tile >> 3), x = tx * kTileW + (row_in_tile & 7);
       const bool row_ok = y < p.H && x < p.W;
       const long long row = (static_cast<long long>(n_img) * p.H + y) * p.W + x;
+      if (p.dbg & 16) {   // ablation: accumulator handshake only
+        mbar_wait(&acc_full[g], aph);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[g]);
+        continue;
+      }
       for (int i = gtid; i < p.block_n; i += 128) bias_s[i] = (n0 + i < p.bias_len) ? __ldg(p.bias + n0 + i) : 0.f;
       named_bar_sync(bar_id, 128);
       mbar_wait(&acc_full[g], aph);

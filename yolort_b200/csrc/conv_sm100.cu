@@ -221,6 +221,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int m0 = m_tile * kBlockM;
       const long long row = static_cast<long long>(m0) + row_in_tile;
       const bool row_ok = row < p.M;
+      if (p.dbg & 16) {   // ablation: accumulator handshake only
+        mbar_wait(&acc_full[g], aph);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[g]);
+        continue;
+      }
       for (int i = gtid; i < p.block_n; i += 128) bias_s[i] = (n0 + i < p.bias_len) ? __ldg(p.bias + n0 + i) : 0.f;
       named_bar_sync(bar_id, 128);
       mbar_wait(&acc_full[g], aph);

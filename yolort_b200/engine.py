@@ -209,7 +209,7 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
     w_sp, b_sp = stem_superpixel(stem_to_s2d(w), b, spk)
     L.conv("body.0(stem: 3x3 over s2d super-pixels)", w_sp, b_sp, _View(x0, 0, 16), _View(t0, 0, w.shape[0]), 3, 1, 1,
            _C.YB_ACT_SILU, ref_flops_per_pixel=spk * 2 * w.shape[0] * 3 * 36, pack=spk,
-           force_im2col=os.environ.get("YB_STEM_IM2COL", "1") == "1")
+           force_im2col=os.environ.get("YB_STEM_IM2COL", "0") == "1")
 
     # concat buffers of the neck (path_aggregation_network.py:215-237)
     cat1 = L.buf("pan.cat1[up(lat1)|f6]", 16, 2 * c4)
