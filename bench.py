@@ -248,7 +248,9 @@ def main():
             torch.cuda.synchronize(dev)
 
     # ---- device-resident leg ------------------------------------------------------------------------
-    plan = model.model.engine().plan(BATCH, SIZE, SIZE)
+    plan = model.model.get_plan(BATCH, SIZE, SIZE)
+    run_attr = "run_fused" if plan.fused_post is not None else "run"
+    native_plan = plan.plan_fused if plan.fused_post is not None else plan.plan
     for i in range(args.warmup):
         out = step_device(i)
     sync_all()
@@ -257,17 +259,17 @@ def main():
         sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     plan_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    orig_run = plan.run
+    orig_run = getattr(plan, run_attr)
 
     step_idx = [0]
 
-    def timed_plan_run(first=0, count=None):
+    def timed_plan_run(*a_, **k_):
         a, b = plan_ev[step_idx[0]]
         a.record()
-        orig_run(first, count)
+        orig_run(*a_, **k_)
         b.record()
 
-    plan.run = timed_plan_run
+    setattr(plan, run_attr, timed_plan_run)
     sync_all()
     ev[0].record()
     for i in range(args.steps):
@@ -275,7 +277,7 @@ def main():
         out = step_device(i)
         ev[i + 1].record()
     sync_all()
-    plan.run = orig_run
+    setattr(plan, run_attr, orig_run)
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
@@ -329,10 +331,10 @@ def main():
                        "parallelism": f"dp{world}" + (" + nccl all_gather of padded detections" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": BATCH * 3 * SIZE * SIZE,
                     "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": (plan.plan.n_ops + 1 + 3) * args.steps,
+            "gpu_launches": (native_plan.n_ops + 1 + 2 + (0 if plan.fused_post is not None else 1)) * args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel": "conv_umma_kernel (all conv launches of one step)",
-                         "plan_ms": plan_ms, "launches_per_step": plan.plan.n_ops},
+                         "plan_ms": plan_ms, "launches_per_step": native_plan.n_ops},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

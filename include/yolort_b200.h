@@ -82,6 +82,24 @@ int yb_scale_coords_params(int Hb, int Wb, int src_h, int src_w, float* out3);
 #define YB_ACT_NONE 0
 #define YB_ACT_SILU 1
 
+/* Optional fused post-processing of a detection-head convolution (yolort/models/box_head.py:68-82 followed by
+ * :328-360,418): instead of storing the logits, the epilogue applies sigmoid / anchor decode / multi-label
+ * threshold to the fp32 accumulators and appends candidates straight into the NMS workspace (see
+ * yb_nms_layout).  The head must fit one N tile (n_anchors * (n_classes + 5) <= 256). */
+typedef struct {
+  int32_t n_anchors, n_classes;
+  int32_t level_start;        /* flat index of this level's first anchor inside an image     */
+  int32_t anchors_per_image;  /* over all levels                                             */
+  float stride_px;
+  float anchors_px[8];        /* (w, h) per anchor, pixels                                   */
+  float score_thresh;
+  int64_t cap_per_image;      /* candidate slots per image in `keys`                         */
+  uint64_t* keys;             /* [n][cap_per_image]                                          */
+  void* boxes;                /* float4 [n][anchors_per_image]                               */
+  int32_t* img_count;         /* [n]                                                         */
+  int32_t* img_maxc;          /* [n] ordered-int max box coordinate                          */
+} yb_head_decode;
+
 /* All activation tensors are NHWC views: element (n,y,x,c) at base[((n*H+y)*W+x)*cstride + c].
  * `cstride` >= channels lets a producer write straight into a slice of a concat buffer. */
 typedef struct {
@@ -101,6 +119,7 @@ typedef struct {
   const void* residual;         /* optional NHWC view added after the activation (Bottleneck)    */
   int32_t res_cstride;
   int32_t reserved;             /* bit 0: keep a 3x3/s1 conv on the generic im2col kernel          */
+  const yb_head_decode* decode; /* optional (host pointer, copied at plan creation): fused decode epilogue */
 } yb_op_desc;
 
 typedef struct yb_plan yb_plan;
@@ -157,6 +176,26 @@ size_t yb_decode_nms_debug_offset(const yb_nms_params* p, const yb_head_level* l
 int yb_decode_nms(const yb_nms_params* p, const yb_head_level* levels, const float* rescale_dev,
                   float* boxes_dev, float* scores_dev, int64_t* labels_dev, int32_t* counts_dev,
                   int64_t* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* The same pipeline in pieces, for plans whose head convolutions carry the fused decode epilogue:
+ * yb_nms_layout reports where inside `workspace_dev` the candidate arena lives (what yb_head_decode needs),
+ * yb_nms_begin zeroes the per-image counters, [the plan runs], yb_nms_finish sorts + suppresses + writes. */
+typedef struct {
+  uint64_t* keys;
+  void* boxes;
+  int32_t* img_count;
+  int32_t* img_maxc;
+  int64_t cap_per_image;
+  int32_t anchors_per_image;
+  int32_t level_start[YB_MAX_LEVELS];
+} yb_nms_layout_t;
+int yb_nms_layout(const yb_nms_params* p, const yb_head_level* levels, void* workspace_dev, size_t workspace_bytes,
+                  yb_nms_layout_t* out);
+int yb_nms_begin(const yb_nms_params* p, const yb_head_level* levels, int64_t* status_dev, void* workspace_dev,
+                 size_t workspace_bytes, void* stream);
+int yb_nms_finish(const yb_nms_params* p, const yb_head_level* levels, const float* rescale_dev, float* boxes_dev,
+                  float* scores_dev, int64_t* labels_dev, int32_t* counts_dev, int64_t* status_dev,
+                  void* workspace_dev, size_t workspace_bytes, void* stream);
 
 /* torchvision.ops.batched_nms on explicit candidates (one image), first `max_keep` survivors in
  * score-descending order (ties: lower index first).  keep_dev [max_keep] int64, n_keep_dev [1]. */

@@ -29,8 +29,11 @@ def test_features_and_heads_vs_reference_fixture():
     z = util.load_npz("network_n.npz")
     m, sd = _model_n()
     x = torch.from_numpy(z["x"]).to(DEV)
-    dets = m.model(x)   # YOLO.forward on a pre-letterboxed NCHW batch
-    plan = m.model.engine().plan(1, 96, 128)
+    dets = m.model(x)   # YOLO.forward on a pre-letterboxed NCHW batch (fused decode epilogue in the heads)
+    plan = m.model.get_plan(1, 96, 128)
+    assert plan.fused_post is not None
+    m.model.run_plan(plan)   # same plan with the heads storing their logits
+    torch.cuda.synchronize()
     for key, name in (("p3", "p3"), ("p4", "p4"), ("p5", "p5")):
         got = plan.features[name].float().permute(0, 3, 1, 2).cpu().numpy()
         mx, rr = _stats(key, got, z[key])
@@ -54,7 +57,7 @@ def test_per_layer_stagewise_parity_yolov5n():
     g = torch.Generator().manual_seed(3)
     x = torch.rand(2, 3, 64, 96, generator=g)
     m.model(x.to(DEV))
-    plan = m.model.engine().plan(2, 64, 96)
+    plan = m.model.get_plan(2, 64, 96)
     net = R.Net(sd)
     with torch.no_grad():
         xr = x.half().float()
@@ -119,3 +122,18 @@ def test_bf16_model_end_to_end():
         frac = util.match_fraction(util.to_np(got), ref, iou_thr=0.8)
         print("bf16 e2e matched fraction:", frac)
         assert frac >= 0.5      # bf16 activations: 8 mantissa bits through ~25 layers
+
+
+def test_fused_head_decode_equals_unfused(monkeypatch):
+    """Heads with the decode epilogue (fp32 accumulators -> candidates) vs stored fp16 logits + stand-alone decode."""
+    m, sd = _model_n()
+    z = util.load_npz("e2e_n.npz")
+    ims = [torch.from_numpy(z["img0"]).to(DEV), torch.from_numpy(z["img1"]).to(DEV)]
+    fused = m(ims)
+    monkeypatch.setenv("YB_DISABLE_FUSED_DECODE", "1")
+    plain = m(ims)
+    for a, b in zip(fused, plain):
+        assert abs(len(a["scores"]) - len(b["scores"])) <= 3
+        frac = util.match_fraction(util.to_np(a), util.to_np(b), iou_thr=0.95)
+        print("fused vs unfused matched:", frac)
+        assert frac >= 0.97      # logits rounded to fp16 in the unfused path move scores by <= 1e-3

@@ -35,6 +35,9 @@ EXPORTED_SYMBOLS = (
     "yb_decode_nms_workspace_bytes",
     "yb_decode_nms_debug_offset",
     "yb_decode_nms",
+    "yb_nms_layout",
+    "yb_nms_begin",
+    "yb_nms_finish",
     "yb_batched_nms_workspace_bytes",
     "yb_batched_nms",
 )
@@ -65,6 +68,28 @@ class OpDesc(ctypes.Structure):
         ("bias", ctypes.c_void_p),
         ("residual", ctypes.c_void_p),
         ("res_cstride", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("decode", ctypes.c_void_p),
+    ]
+
+
+class HeadDecode(ctypes.Structure):
+    _fields_ = [
+        ("n_anchors", ctypes.c_int32), ("n_classes", ctypes.c_int32),
+        ("level_start", ctypes.c_int32), ("anchors_per_image", ctypes.c_int32),
+        ("stride_px", ctypes.c_float), ("anchors_px", ctypes.c_float * 8),
+        ("score_thresh", ctypes.c_float),
+        ("cap_per_image", ctypes.c_int64),
+        ("keys", ctypes.c_void_p), ("boxes", ctypes.c_void_p),
+        ("img_count", ctypes.c_void_p), ("img_maxc", ctypes.c_void_p),
+    ]
+
+
+class NmsLayout(ctypes.Structure):
+    _fields_ = [
+        ("keys", ctypes.c_void_p), ("boxes", ctypes.c_void_p),
+        ("img_count", ctypes.c_void_p), ("img_maxc", ctypes.c_void_p),
+        ("cap_per_image", ctypes.c_int64), ("anchors_per_image", ctypes.c_int32),
+        ("level_start", ctypes.c_int32 * YB_MAX_LEVELS),
     ]
 
 
@@ -131,6 +156,13 @@ def lib() -> ctypes.CDLL:
         ctypes.POINTER(NmsParams), ctypes.POINTER(HeadLevel), ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_size_t, ctypes.c_void_p]
+    L.yb_nms_layout.argtypes = [ctypes.POINTER(NmsParams), ctypes.POINTER(HeadLevel), ctypes.c_void_p, ctypes.c_size_t,
+                                ctypes.POINTER(NmsLayout)]
+    L.yb_nms_begin.argtypes = [ctypes.POINTER(NmsParams), ctypes.POINTER(HeadLevel), ctypes.c_void_p, ctypes.c_void_p,
+                               ctypes.c_size_t, ctypes.c_void_p]
+    L.yb_nms_finish.argtypes = [ctypes.POINTER(NmsParams), ctypes.POINTER(HeadLevel), ctypes.c_void_p, ctypes.c_void_p,
+                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                ctypes.c_size_t, ctypes.c_void_p]
     L.yb_batched_nms_workspace_bytes.restype = ctypes.c_size_t
     L.yb_batched_nms_workspace_bytes.argtypes = [ctypes.c_int64]
     L.yb_batched_nms.argtypes = [
@@ -364,6 +396,62 @@ def decode_nms(head_outputs: List[torch.Tensor], layout: str, strides, anchors_p
         c = int(host[i])
         out.append({"scores": scores[i, :c], "labels": labels[i, :c], "boxes": boxes[i, :c]})
     return out
+
+
+class FusedPost:
+    """Post-processing state of a plan whose head convolutions decode in their epilogue: a fixed candidate arena
+    (the heads hold raw pointers into it), the NMS parameters, and begin()/finish() around the plan run."""
+
+    def __init__(self, n_images: int, level_hw: Sequence[Tuple[int, int]], strides: Sequence[float],
+                 anchors_px: Sequence[Sequence[float]], num_classes: int, score_thresh: float, nms_thresh: float,
+                 detections_per_img: int, semantics: int, device: torch.device, cap_per_image: int = 32768):
+        self.device = device
+        self.n_images, self.D = n_images, int(detections_per_img)
+        n_levels, n_anchors = len(level_hw), len(anchors_px[0]) // 2
+        self.levels = (HeadLevel * n_levels)()
+        for i, (h, w) in enumerate(level_hw):
+            self.levels[i].H, self.levels[i].W = int(h), int(w)
+            self.levels[i].dtype = YB_F16
+            self.levels[i].stride_px = float(strides[i])
+            for j, v in enumerate(anchors_px[i]):
+                self.levels[i].anchors_px[j] = float(v)
+        self.params = NmsParams(n_images, n_levels, n_anchors, int(num_classes), float(score_thresh), float(nms_thresh),
+                                self.D, int(semantics), int(cap_per_image) * n_images)
+        need = lib().yb_decode_nms_workspace_bytes(ctypes.byref(self.params), self.levels)
+        self.ws = torch.empty((need,), dtype=torch.uint8, device=device)
+        self.layout = NmsLayout()
+        check(lib().yb_nms_layout(ctypes.byref(self.params), self.levels, self.ws.data_ptr(), self.ws.numel(),
+                                  ctypes.byref(self.layout)), "yb_nms_layout")
+        self.head_decode = []
+        for i in range(n_levels):
+            hd = HeadDecode()
+            hd.n_anchors, hd.n_classes = n_anchors, int(num_classes)
+            hd.level_start, hd.anchors_per_image = int(self.layout.level_start[i]), int(self.layout.anchors_per_image)
+            hd.stride_px = float(strides[i])
+            for j, v in enumerate(anchors_px[i]):
+                hd.anchors_px[j] = float(v)
+            hd.score_thresh = float(score_thresh)
+            hd.cap_per_image = int(self.layout.cap_per_image)
+            hd.keys, hd.boxes = self.layout.keys, self.layout.boxes
+            hd.img_count, hd.img_maxc = self.layout.img_count, self.layout.img_maxc
+            self.head_decode.append(hd)
+        self.status = torch.empty((4,), dtype=torch.int64, device=device)
+
+    def begin(self) -> None:
+        check(lib().yb_nms_begin(ctypes.byref(self.params), self.levels, self.status.data_ptr(), self.ws.data_ptr(),
+                                 self.ws.numel(), current_stream_ptr(self.device)), "yb_nms_begin")
+
+    def finish(self, rescale: Optional[torch.Tensor]):
+        n, D, dev = self.n_images, self.D, self.device
+        boxes = torch.empty((n, D, 4), dtype=torch.float32, device=dev)
+        scores = torch.empty((n, D), dtype=torch.float32, device=dev)
+        labels = torch.empty((n, D), dtype=torch.int64, device=dev)
+        counts = torch.empty((n,), dtype=torch.int32, device=dev)
+        check(lib().yb_nms_finish(ctypes.byref(self.params), self.levels,
+                                  rescale.data_ptr() if rescale is not None else None, boxes.data_ptr(),
+                                  scores.data_ptr(), labels.data_ptr(), counts.data_ptr(), self.status.data_ptr(),
+                                  self.ws.data_ptr(), self.ws.numel(), current_stream_ptr(dev)), "yb_nms_finish")
+        return boxes, scores, labels, counts, self.status
 
 
 def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, labels: torch.Tensor, iou_threshold: float,

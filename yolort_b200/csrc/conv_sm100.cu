@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "conv_sm100.h"
 #include "conv_epilogue.cuh"
+#include "decode_common.cuh"
 
 namespace yb {
 
@@ -34,7 +35,8 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kMaxStages = 12;
 constexpr int kEpiGroups = 2;
-constexpr int kThreads = 64 + kEpiGroups * 128;
+constexpr int kFirstEpiWarp = 3;                     // warp 0: TMA producer, warps 1-2: MMA issuers (one per accumulator stage)
+constexpr int kThreads = 32 * kFirstEpiWarp + kEpiGroups * 128;
 constexpr int kStageBufBytes = 128 * 128;  // 128 rows x (up to) 64 columns x 2 B
 constexpr int kMaxBlockN = 256;
 constexpr size_t kSmemBudget = 222 * 1024;  // dynamic shared memory per CTA (227 KB limit minus static)
@@ -55,6 +57,9 @@ struct ConvKernelParams {
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, idesc;
   const float* bias;
   EpilogueParams ep;
+  int decode_on;        // detection head with the fused decode epilogue (no logits are stored)
+  int dec_H, dec_W;     // level extent (output pixels)
+  yb_head_decode dec;   // copied from the op descriptor
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -161,8 +166,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 || warp == 2) {
+    // ===================== MMA issuers =====================
+    // Two issuing threads, one per accumulator stage (even / odd tiles): the per-tile chain of mbarrier waits and
+    // tcgen05.commit arrivals of one thread overlaps the other's, which matters for the small-K layers whose
+    // tiles carry only 4-8 MMAs.  Shared-memory stages are still consumed in order (each thread skips the
+    // stage indices of the other's tiles).
     if (lane == 0) {
       const uint32_t row_bytes = p.block_k * 2;
       const int kk = p.block_k >> 4;
@@ -173,9 +182,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t b_res_addr = smem_u32(b_res);
       const uint32_t desc_hi = static_cast<uint32_t>(make_kmajor_desc(0, row_bytes) >> 32);
       const uint32_t a_step16 = p.a_stage_bytes >> 4, b_step16 = p.b_stage_bytes >> 4;
+      const int my_stage = warp - 1;
+      const int groups_per_tile = (p.num_k_iters + p.kpg - 1) / p.kpg;
       int kit = 0, lt = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
         const int as = lt & 1;
+        if (as != my_stage) {
+          kit += groups_per_tile;
+          continue;
+        }
         const uint32_t aph = (lt >> 1) & 1;
         mbar_wait(&acc_empty[as], aph ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
@@ -202,10 +217,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else {
-    // ===================== epilogue groups (warps 2..9) =====================
-    const int g = (warp - 2) >> 2;   // group == accumulator stage it drains
+    // ===================== epilogue groups =====================
+    const int g = (warp - kFirstEpiWarp) >> 2;   // group == accumulator stage it drains
     const int q = warp & 3;          // TMEM lane quarter this warp may access
-    const int gtid = threadIdx.x - 64 - g * 128;
+    const int gtid = threadIdx.x - 32 * kFirstEpiWarp - g * 128;
     const int row_in_tile = q * 32 + lane;
     const bool issuer = (gtid == 0);
     const uint32_t bar_id = 1 + g;
@@ -234,6 +249,73 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_wait(&acc_full[g], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * p.block_n;
+      if (p.decode_on) {
+        // ---- fused post-processing front end (yolort/models/box_head.py:328-360,418) ----
+        // This thread owns one output pixel: all A*(nc+5) logits of its anchors sit in its TMEM lane.  Per anchor:
+        // objectness first (score = cls*obj <= obj, so most anchors stop there), then the classes in 16-column
+        // TMEM reads; candidates go straight into the NMS arena.  TMEM reads are warp-collective, so the class
+        // scan of an anchor runs whenever ANY pixel of the warp passed the objectness test.
+        const yb_head_decode& D = p.dec;
+        const int K = D.n_classes + 5;
+        const int hw = p.dec_H * p.dec_W;
+        const int n_img = static_cast<int>(row / hw);
+        const int rem = static_cast<int>(row - static_cast<long long>(n_img) * hw);
+        const int py = rem / p.dec_W, px = rem - py * p.dec_W;
+        for (int a = 0; a < D.n_anchors; ++a) {
+          const int base_col = a * K;
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(taddr + base_col, v);
+          tmem_ld_wait();
+          const float obj = sigmoidf_ref(__uint_as_float(v[4]) + bias_s[base_col + 4]);
+          const bool pass = row_ok && obj > D.score_thresh;
+          if (!__any_sync(0xffffffffu, pass)) continue;
+          const int anchor_flat = D.level_start + (a * p.dec_H + py) * p.dec_W + px;
+          bool any = false;
+          if (pass) {
+#pragma unroll
+            for (int j = 5; j < 16; ++j) {
+              const int k = j - 5;
+              if (k < D.n_classes) {
+                const float score = __fmul_rn(sigmoidf_ref(__uint_as_float(v[j]) + bias_s[base_col + j]), obj);
+                if (score > D.score_thresh) {
+                  emit_candidate(D.keys, D.img_count, D.cap_per_image, n_img, anchor_flat, D.n_classes, k, score);
+                  any = true;
+                }
+              }
+            }
+          }
+          const float tx = __uint_as_float(v[0]) + bias_s[base_col + 0], ty = __uint_as_float(v[1]) + bias_s[base_col + 1];
+          const float tw = __uint_as_float(v[2]) + bias_s[base_col + 2], th = __uint_as_float(v[3]) + bias_s[base_col + 3];
+          for (int c = 16; c < K; c += 16) {
+            uint32_t u[16];
+            tmem_ld_32x32b_x16(taddr + base_col + c, u);
+            tmem_ld_wait();
+            if (pass) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const int k = c + j - 5;
+                if (k < D.n_classes) {
+                  const float score = __fmul_rn(sigmoidf_ref(__uint_as_float(u[j]) + bias_s[base_col + c + j]), obj);
+                  if (score > D.score_thresh) {
+                    emit_candidate(D.keys, D.img_count, D.cap_per_image, n_img, anchor_flat, D.n_classes, k, score);
+                    any = true;
+                  }
+                }
+              }
+            }
+          }
+          if (any) {
+            const float4 b = decode_box(sigmoidf_ref(tx), sigmoidf_ref(ty), sigmoidf_ref(tw), sigmoidf_ref(th), px, py,
+                                        D.stride_px, D.anchors_px[2 * a], D.anchors_px[2 * a + 1]);
+            reinterpret_cast<float4*>(D.boxes)[static_cast<long long>(n_img) * D.anchors_per_image + anchor_flat] = b;
+            atomicMax(&D.img_maxc[n_img], float_to_ordered_int(fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[g]);
+        continue;
+      }
       for (int c0 = 0; c0 < p.block_n; c0 += p.store_cols, ++store_idx) {
         // Two staging buffers, one barrier per box: before the barrier below the issuer waits until the PREVIOUS
         // store has finished reading its buffer, which is the one the next box will overwrite.
@@ -378,6 +460,27 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
   kp.Wo = Wo;
   kp.stride = d.stride;
   kp.pad = d.pad;
+  kp.decode_on = 0;
+  if (d.decode != nullptr) {
+    const yb_head_decode& dd = *d.decode;
+    const int width = dd.n_anchors * (dd.n_classes + 5);
+    if (!(dd.n_anchors > 0 && dd.n_anchors <= 4 && width <= kMaxBlockN && width <= d.Cout_pad && d.ksize == 1 &&
+          dd.keys && dd.boxes && dd.img_count && dd.img_maxc)) {
+      set_error("conv: fused decode needs a 1x1 head with n_anchors*(n_classes+5) <= %d and a candidate arena", kMaxBlockN);
+      delete op;
+      return YB_ERR_INVALID;
+    }
+    // all anchors of a pixel must sit in one accumulator row: one N tile covering the whole head
+    n_tiles = 1;
+    block_n = (d.Cout + 15) / 16 * 16;
+    kp.block_n = block_n;
+    kp.n_tiles = 1;
+    kp.num_tiles = m_tiles;
+    kp.decode_on = 1;
+    kp.dec = dd;
+    kp.dec_H = Ho;
+    kp.dec_W = Wo;
+  }
   kp.store_cols = (block_n % 64 == 0) ? 64 : ((block_n % 32 == 0) ? 32 : 16);
   kp.bias_len = d.Cout_pad;
   {

@@ -23,6 +23,7 @@
 // IoU arithmetic mirrors torchvision's CPU nms kernel in fp32 with explicit non-fused operations so the
 // keep set is bit-identical on identical inputs.
 #include "common.cuh"
+#include "decode_common.cuh"
 
 namespace yb {
 namespace {
@@ -30,26 +31,6 @@ namespace {
 constexpr int kNmsThreads = 512;
 constexpr int kSweep = 512;       // candidates consumed per sweep round (== threads)
 constexpr int kSmallSort = 4096;  // keys sorted in shared memory
-
-__device__ __forceinline__ uint32_t orderable_desc(float f) {
-  uint32_t u = __float_as_uint(f);
-  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending order of floats
-  return ~u;                                       // descending
-}
-__device__ __forceinline__ float from_orderable_desc(uint32_t k) {
-  uint32_t u = ~k;
-  u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
-  return __uint_as_float(u);
-}
-__device__ __forceinline__ int float_to_ordered_int(float f) {
-  int i = __float_as_int(f);
-  return i >= 0 ? i : i ^ 0x7FFFFFFF;
-}
-__device__ __forceinline__ float ordered_int_to_float(int i) {
-  return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF);
-}
-
-__device__ __forceinline__ float sigmoidf_ref(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
 
 template <typename T>
 __device__ __forceinline__ float ld_logit(const void* base, long long off);
@@ -623,29 +604,110 @@ extern "C" size_t yb_decode_nms_debug_offset(const yb_nms_params* p, const yb_he
   return reinterpret_cast<size_t>(ws.status);
 }
 
-extern "C" int yb_decode_nms(const yb_nms_params* p, const yb_head_level* levels, const float* rescale_dev,
-                             float* boxes_dev, float* scores_dev, int64_t* labels_dev, int32_t* counts_dev,
-                             int64_t* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  YB_REQUIRE(p && levels && boxes_dev && scores_dev && labels_dev && counts_dev && status_dev && workspace_dev,
-             "decode_nms: null argument");
+namespace {
+// validates the arguments shared by the entry points below and carves the workspace
+int prepare(const yb_nms_params* p, const yb_head_level* levels, void* workspace_dev, size_t workspace_bytes,
+            Workspace& ws, long long& apm, long long& cap) {
+  YB_REQUIRE(p && levels && workspace_dev, "decode_nms: null argument");
   YB_REQUIRE(p->n_images > 0 && p->n_levels > 0 && p->n_levels <= YB_MAX_LEVELS, "decode_nms: n_images/n_levels");
   YB_REQUIRE(p->n_anchors > 0 && p->n_anchors <= YB_MAX_ANCHORS && p->n_classes > 0, "decode_nms: anchors/classes");
   YB_REQUIRE(p->max_det > 0 && p->max_det <= 4096, "decode_nms: max_det must be in [1, 4096]");
   YB_REQUIRE(p->semantics >= 0 && p->semantics <= 2, "decode_nms: bad semantics");
-  const long long apm = anchors_per_image(p, levels);
+  apm = anchors_per_image(p, levels);
   YB_REQUIRE(apm > 0, "decode_nms: no anchors");
   YB_REQUIRE(apm * p->n_classes < (1ll << 31), "decode_nms: anchors*classes overflows the candidate index");
-  const long long cap = (p->max_candidates + p->n_images - 1) / p->n_images;
+  cap = (p->max_candidates + p->n_images - 1) / p->n_images;
   YB_REQUIRE(cap >= 1, "decode_nms: max_candidates too small");
-  Workspace ws;
   const size_t need = carve(ws, static_cast<uint8_t*>(workspace_dev), p->n_images, cap, apm);
   if (need > workspace_bytes) {
     set_error("decode_nms: workspace of %zu bytes needed, %zu given", need, workspace_bytes);
     return YB_ERR_WORKSPACE;
   }
+  return YB_OK;
+}
+}  // namespace
+
+extern "C" int yb_nms_layout(const yb_nms_params* p, const yb_head_level* levels, void* workspace_dev,
+                             size_t workspace_bytes, yb_nms_layout_t* out) {
+  YB_REQUIRE(out != nullptr, "nms_layout: null output");
+  Workspace ws;
+  long long apm, cap;
+  int rc = prepare(p, levels, workspace_dev, workspace_bytes, ws, apm, cap);
+  if (rc != YB_OK) return rc;
+  out->keys = ws.keys_a;
+  out->boxes = ws.boxes;
+  out->img_count = ws.img_count;
+  out->img_maxc = ws.img_maxc;
+  out->cap_per_image = cap;
+  out->anchors_per_image = static_cast<int32_t>(apm);
+  int start = 0;
+  for (int l = 0; l < YB_MAX_LEVELS; ++l) {
+    out->level_start[l] = start;
+    if (l < p->n_levels) start += p->n_anchors * levels[l].H * levels[l].W;
+  }
+  return YB_OK;
+}
+
+extern "C" int yb_nms_begin(const yb_nms_params* p, const yb_head_level* levels, int64_t* status_dev,
+                            void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  YB_REQUIRE(status_dev != nullptr, "nms_begin: null status");
+  Workspace ws;
+  long long apm, cap;
+  int rc = prepare(p, levels, workspace_dev, workspace_bytes, ws, apm, cap);
+  if (rc != YB_OK) return rc;
+  init_counters_kernel<<<(p->n_images + 127) / 128 + 1, 128, 0, stream>>>(ws, p->n_images,
+                                                                          reinterpret_cast<long long*>(status_dev), 0);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+extern "C" int yb_nms_finish(const yb_nms_params* p, const yb_head_level* levels, const float* rescale_dev,
+                             float* boxes_dev, float* scores_dev, int64_t* labels_dev, int32_t* counts_dev,
+                             int64_t* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  YB_REQUIRE(boxes_dev && scores_dev && labels_dev && counts_dev && status_dev, "nms_finish: null output");
+  Workspace ws;
+  long long apm, cap;
+  int rc = prepare(p, levels, workspace_dev, workspace_bytes, ws, apm, cap);
+  if (rc != YB_OK) return rc;
+  NmsParams np;
+  np.n_classes = p->n_classes;
+  np.anchors_per_image = static_cast<int>(apm);
+  np.cap_per_image = cap;
+  np.iou_thresh = p->iou_thresh;
+  np.max_det = p->max_det;
+  np.semantics = p->semantics;
+  np.explicit_mode = 0;
+  np.x_boxes = nullptr;
+  np.x_labels = nullptr;
+  np.rescale = rescale_dev;
+  np.out_boxes = boxes_dev;
+  np.out_scores = scores_dev;
+  np.out_labels = labels_dev;
+  np.out_keep = nullptr;
+  np.out_counts = counts_dev;
+  np.status = reinterpret_cast<long long*>(status_dev);
+  const size_t smem = nms_smem_bytes(p->max_det);
+  rc = ensure_nms_smem(smem);
+  if (rc != YB_OK) return rc;
+  nms_image_kernel<<<p->n_images, kNmsThreads, smem, stream>>>(np, ws);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+extern "C" int yb_decode_nms(const yb_nms_params* p, const yb_head_level* levels, const float* rescale_dev,
+                             float* boxes_dev, float* scores_dev, int64_t* labels_dev, int32_t* counts_dev,
+                             int64_t* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int rc = yb_nms_begin(p, levels, status_dev, workspace_dev, workspace_bytes, stream_);
+  if (rc != YB_OK) return rc;
+  Workspace ws;
+  long long apm, cap;
+  rc = prepare(p, levels, workspace_dev, workspace_bytes, ws, apm, cap);
+  if (rc != YB_OK) return rc;
   DecodeParams dp;
-  int dtype = levels[0].dtype;
+  const int dtype = levels[0].dtype;
   dp.lvl_start[0] = 0;
   for (int l = 0; l < YB_MAX_LEVELS; ++l) {
     if (l < p->n_levels) {
@@ -665,9 +727,6 @@ extern "C" int yb_decode_nms(const yb_nms_params* p, const yb_head_level* levels
   dp.anchors_per_image = static_cast<int>(apm);
   dp.score_thresh = p->score_thresh;
   dp.cap_per_image = cap;
-
-  init_counters_kernel<<<(p->n_images + 127) / 128 + 1, 128, 0, stream>>>(ws, p->n_images, reinterpret_cast<long long*>(status_dev), 0);
-  YB_CHECK_CUDA(cudaGetLastError());
   const long long total = static_cast<long long>(p->n_images) * apm;
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
   switch (dtype) {
@@ -685,30 +744,8 @@ extern "C" int yb_decode_nms(const yb_nms_params* p, const yb_head_level* levels
       return YB_ERR_INVALID;
   }
   YB_CHECK_CUDA(cudaGetLastError());
-
-  NmsParams np;
-  np.n_classes = p->n_classes;
-  np.anchors_per_image = static_cast<int>(apm);
-  np.cap_per_image = cap;
-  np.iou_thresh = p->iou_thresh;
-  np.max_det = p->max_det;
-  np.semantics = p->semantics;
-  np.explicit_mode = 0;
-  np.x_boxes = nullptr;
-  np.x_labels = nullptr;
-  np.rescale = rescale_dev;
-  np.out_boxes = boxes_dev;
-  np.out_scores = scores_dev;
-  np.out_labels = labels_dev;
-  np.out_keep = nullptr;
-  np.out_counts = counts_dev;
-  np.status = reinterpret_cast<long long*>(status_dev);
-  const size_t smem = nms_smem_bytes(p->max_det);
-  int rc = ensure_nms_smem(smem);
-  if (rc != YB_OK) return rc;
-  nms_image_kernel<<<p->n_images, kNmsThreads, smem, stream>>>(np, ws);
-  YB_CHECK_CUDA(cudaGetLastError());
-  return YB_OK;
+  return yb_nms_finish(p, levels, rescale_dev, boxes_dev, scores_dev, labels_dev, counts_dev, status_dev, workspace_dev,
+                       workspace_bytes, stream_);
 }
 
 extern "C" size_t yb_batched_nms_workspace_bytes(int64_t n_boxes) {

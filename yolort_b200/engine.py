@@ -273,7 +273,8 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
 class PlanInstance:
     """Arena + native plan for one (N, H, W)."""
 
-    def __init__(self, L: _Lowering, x0: _Buf, head_bufs: List[_Buf], feats: Dict[str, _View], N: int, H: int, W: int):
+    def __init__(self, L: _Lowering, x0: _Buf, head_bufs: List[_Buf], feats: Dict[str, _View], N: int, H: int, W: int,
+                 post: Optional[dict] = None):
         if H % 32 or W % 32:
             raise ValueError(f"canvas {H}x{W} must be a multiple of 32")
         self.N, self.H, self.W = N, H, W
@@ -321,6 +322,23 @@ class PlanInstance:
             self.op_flops.append(flops)
         self._keepalive = [op.weight for op in L.ops] + [op.bias for op in L.ops]
         self.plan = _C.Plan(descs, L.device)
+        # Second launch list whose head convolutions decode + threshold in their epilogue and append candidates to a
+        # fixed NMS arena instead of storing logits (box_head.py:68-82 + :328-360,418 fused).
+        self.fused_post = None
+        self.plan_fused = None
+        n_heads = len(head_bufs)
+        if post is not None and post["n_anchors"] * (post["num_classes"] + 5) <= 256:
+            level_hw = [(H // b.div, W // b.div) for b in head_bufs]
+            self.fused_post = _C.FusedPost(N, level_hw, post["strides"], post["anchors_px"], post["num_classes"],
+                                           post["score_thresh"], post["nms_thresh"], post["detections_per_img"],
+                                           post["semantics"], L.device)
+            fused = list(descs[:-n_heads])
+            import ctypes as _ct
+            for d, hd in zip(descs[-n_heads:], self.fused_post.head_decode):
+                d2 = _C.OpDesc.from_buffer_copy(d)
+                d2.decode = _ct.addressof(hd)
+                fused.append(d2)
+            self.plan_fused = _C.Plan(fused, L.device)
 
         def nhwc(b: _Buf) -> torch.Tensor:
             h, w = H // b.div, W // b.div
@@ -333,7 +351,12 @@ class PlanInstance:
         self.buffers = {b.name: nhwc(b) for b in L.bufs}
 
     def run(self, first: int = 0, count: Optional[int] = None) -> None:
+        """Backbone + PAN + heads, logits stored in `self.heads`."""
         self.plan.run(first, count)
+
+    def run_fused(self) -> None:
+        """Backbone + PAN + heads with the decode epilogue (candidates land in `self.fused_post`'s arena)."""
+        self.plan_fused.run()
 
 
 class Engine:
@@ -347,14 +370,16 @@ class Engine:
             raise _C.NativeLibraryError(f"compute dtype must be float16 or bfloat16, got {dtype}")
         _C.lib()
         self.model, self.dtype, self.device = model, dtype, device
-        self._plans: Dict[Tuple[int, int, int], PlanInstance] = {}
+        self._plans: Dict[tuple, PlanInstance] = {}
 
-    def plan(self, N: int, H: int, W: int) -> PlanInstance:
-        key = (N, H, W)
+    def plan(self, N: int, H: int, W: int, post: Optional[dict] = None) -> PlanInstance:
+        pkey = None if post is None else (post["score_thresh"], post["nms_thresh"], post["detections_per_img"],
+                                          post["semantics"], post["num_classes"])
+        key = (N, H, W, pkey)
         inst = self._plans.get(key)
         if inst is None:
             with torch.cuda.device(self.device):
                 L, x0, head_bufs, feats = lower_yolo(self.model, self.dtype, self.device)
-                inst = PlanInstance(L, x0, head_bufs, feats, N, H, W)
+                inst = PlanInstance(L, x0, head_bufs, feats, N, H, W, post)
             self._plans[key] = inst
         return inst

@@ -5,6 +5,7 @@ factories `yolov5_darknet_pan_{n,s,m,l,x}_r60` (`:468-619`).  `forward(samples[N
 batch to the plan's input layout with the letterbox kernel (identity geometry), runs the plan and the
 decode+NMS kernels; nothing is computed by PyTorch ops.
 """
+import os
 from typing import Any, Callable, Dict, List, Optional
 
 import torch
@@ -89,17 +90,51 @@ class YOLO(nn.Module):
         return self._engine
 
     # -- stages --------------------------------------------------------------------------------------
+    def post_config(self) -> dict:
+        """Post-processing parameters baked into a plan's fused head epilogues / NMS arena."""
+        pp = self.post_process
+        ag = self.anchor_generator
+        return {"strides": list(pp.strides), "anchors_px": ag.anchors_px(), "n_anchors": ag.num_anchors,
+                "num_classes": self.num_classes, "score_thresh": float(pp.score_thresh),
+                "nms_thresh": float(pp.nms_thresh), "detections_per_img": int(pp.detections_per_img),
+                "semantics": int(getattr(pp, "nms_semantics", _C.NMS_TV_AUTO))}
+
+    def get_plan(self, N: int, H: int, W: int):
+        fuse = os.environ.get("YB_DISABLE_FUSED_DECODE", "0") != "1"
+        return self.engine().plan(N, H, W, self.post_config() if fuse else None)
+
     def run_plan(self, plan) -> List[Tensor]:
         """backbone + PAN + head on the prepared input canvas; returns the raw head logits (NHWC)."""
         plan.run()
         return plan.heads
 
-    def detect(self, plan, rescale: Optional[Tensor] = None) -> List[Dict[str, Tensor]]:
+    def detect_padded(self, plan, rescale: Optional[Tensor] = None):
+        """Runs the plan and the post-processing; padded device outputs, no host synchronisation."""
+        if plan.fused_post is not None:
+            fp = plan.fused_post
+            fp.begin()
+            plan.run_fused()
+            return fp.finish(rescale)
         heads = self.run_plan(plan)
-        pp = self.post_process
-        return _C.decode_nms(heads, "nhwc", pp.strides, self.anchor_generator.anchors_px(), pp.score_thresh,
-                             pp.nms_thresh, pp.detections_per_img, getattr(pp, "nms_semantics", _C.NMS_TV_AUTO),
-                             rescale=rescale, num_classes=self.num_classes)
+        pc = self.post_config()
+        return _C.decode_nms_padded(heads, "nhwc", pc["strides"], pc["anchors_px"], pc["num_classes"],
+                                    pc["score_thresh"], pc["nms_thresh"], pc["detections_per_img"], pc["semantics"],
+                                    rescale)
+
+    def detect(self, plan, rescale: Optional[Tensor] = None) -> List[Dict[str, Tensor]]:
+        pc = self.post_config()
+        if plan.fused_post is not None:
+            boxes, scores, labels, counts, status = self.detect_padded(plan, rescale)
+            n = counts.numel()
+            host = torch.cat([counts.to(torch.int64), status]).cpu()
+            if int(host[n + 1]) == 0:
+                return [{"scores": scores[i, :int(host[i])], "labels": labels[i, :int(host[i])],
+                         "boxes": boxes[i, :int(host[i])]} for i in range(n)]
+            # an image overflowed its share of the fixed arena: redo the post-processing on stored logits with the
+            # growable arena (never truncate)
+        heads = self.run_plan(plan)
+        return _C.decode_nms(heads, "nhwc", pc["strides"], pc["anchors_px"], pc["score_thresh"], pc["nms_thresh"],
+                             pc["detections_per_img"], pc["semantics"], rescale=rescale, num_classes=self.num_classes)
 
     def forward(self, samples: Tensor, targets: Optional[Tensor] = None):
         if self.training or targets is not None:
@@ -107,7 +142,7 @@ class YOLO(nn.Module):
         if samples.dim() != 4 or samples.shape[1] != 3:
             raise ValueError(f"samples must be [N,3,H,W], got {tuple(samples.shape)}")
         N, _, H, W = (int(v) for v in samples.shape)
-        plan = self.engine().plan(N, H, W)
+        plan = self.get_plan(N, H, W)
         geoms = (_C.LetterboxGeom * N)()
         for g in geoms:
             g.src_h, g.src_w, g.new_h, g.new_w, g.top, g.left = H, W, H, W, 0, 0

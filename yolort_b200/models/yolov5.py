@@ -54,7 +54,7 @@ class YOLOv5(nn.Module):
             raise ValueError("empty image list")
         original_image_sizes = [(int(im.shape[-2]), int(im.shape[-1])) for im in inputs]
         geoms, (Hb, Wb) = self.transform.geometry(inputs, batch_hw)
-        plan = self.model.engine().plan(len(inputs), Hb, Wb)
+        plan = self.model.get_plan(len(inputs), Hb, Wb)
         self.transform.letterbox_into(inputs, geoms, Hb, Wb, plan.input, _C.YB_LAYOUT_S2D16)
         rescale = self.transform.rescale_params((Hb, Wb), original_image_sizes).to(plan.device, non_blocking=True)
         return plan, rescale
@@ -71,12 +71,7 @@ class YOLOv5(nn.Module):
         `batch_hw` pins the canvas (multi-GPU shards must letterbox to the GLOBAL batch shape to
         reproduce single-GPU boxes: SURVEY.md section 8e)."""
         plan, rescale = self._prepare(inputs, batch_hw)
-        m = self.model
-        heads = m.run_plan(plan)
-        pp = m.post_process
-        return _C.decode_nms_padded(heads, "nhwc", pp.strides, m.anchor_generator.anchors_px(), m.num_classes,
-                                    pp.score_thresh, pp.nms_thresh, pp.detections_per_img,
-                                    getattr(pp, "nms_semantics", _C.NMS_TV_AUTO), rescale)
+        return self.model.detect_padded(plan, rescale)
 
     @torch.no_grad()
     def predict(self, x: Any, image_loader: Optional[Callable] = None) -> List[Dict[str, Tensor]]:
