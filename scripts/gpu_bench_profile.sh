@@ -2,7 +2,7 @@
 # Bench line + ncu launch list (+ optional full ncu captures).  Run under gpurun (1 GPU).
 #   bash scripts/gpu_bench_profile.sh [conv|post|all]
 mkdir -p gpurun_out
-python bench.py --steps 20 --warmup 5 > gpurun_out/bench.log 2>&1
+timeout -s KILL 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.log 2>&1
 tail -1 gpurun_out/bench.log > gpurun_out/bench.json
 cat gpurun_out/bench.json
 timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 240 --csv \

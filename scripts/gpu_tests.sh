@@ -12,7 +12,7 @@ run() { # name, timeout, cmd...
 }
 : > gpurun_out/summary.txt
 run letterbox 300 python -m pytest tests/test_gpu_letterbox.py -q -m gpu -s
-run postprocess 600 python -m pytest tests/test_gpu_postprocess.py -q -m gpu -s
+run postprocess 300 python -m pytest tests/test_gpu_postprocess.py -q -m gpu -s
 for m in 0 2; do
   run conv_patch_mode$m 240 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "test_patch_conv_view_modes and ${m}]"
 done
@@ -21,10 +21,10 @@ for t in test_conv1x1 test_conv1x1_ragged test_conv3x3 test_conv3x3_crosses test
   run conv_$t 240 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "$t"
 done
 run pool 300 python -m pytest tests/test_gpu_pool_upsample.py -q -m gpu -s
-run network 600 python -m pytest tests/test_gpu_network.py -q -m gpu -s
+run network 240 python -m pytest tests/test_gpu_network.py -q -m gpu -s
 run smoke 300 python __graft_entry__.py smoke
 if [ "$1" != "quick" ]; then
-  run bench 900 python bench.py --steps 20 --warmup 5
+  run bench 300 python bench.py --steps 20 --warmup 5
   tail -1 gpurun_out/bench.log > gpurun_out/bench.json
 fi
 cat gpurun_out/summary.txt

@@ -185,8 +185,8 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
       }
     }
-  } else if (warp == 1 || (warp == kFirstLoadWarp && p.a_loader == 0)) {
-    // ===================== MMA issuers (second one only when the loader warps are idle) =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t row_bytes = p.block_k * 2;
       const int pitch = p.view_mode == 2 ? kTileW : kPatchW;   // pixel-rows per patch row
@@ -207,16 +207,10 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       const uint32_t b_hi = static_cast<uint32_t>(make_kmajor_desc(0, row_bytes) >> 32);
       const uint32_t b_res_lo0 = (smem_u32(b_buf) & 0x3FFFFu) >> 4;
       const uint32_t b_step16 = p.b_sub_bytes >> 4;
-      const int n_issuers = p.a_loader == 0 ? 2 : 1;
-      const int my_stage = warp == 1 ? 0 : 1;
       int ka = 0, kb = 0, lt = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
         const int as = lt & 1;
-        if (n_issuers == 2 && as != my_stage) {   // the other issuing thread owns this tile
-          ka += p.chunks;
-          kb += 9 * p.chunks;
-          continue;
-        }
+
         const uint32_t aph = (lt >> 1) & 1;
         mbar_wait(&acc_empty[as], aph ^ 1);
         tc_fence_after();

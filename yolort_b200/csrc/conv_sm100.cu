@@ -166,12 +166,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
-  } else if (warp == 1 || warp == 2) {
-    // ===================== MMA issuers =====================
-    // Two issuing threads, one per accumulator stage (even / odd tiles): the per-tile chain of mbarrier waits and
-    // tcgen05.commit arrivals of one thread overlaps the other's, which matters for the small-K layers whose
-    // tiles carry only 4-8 MMAs.  Shared-memory stages are still consumed in order (each thread skips the
-    // stage indices of the other's tiles).
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // (A second issuing thread for alternate tiles was tried and removed: two consumers that are several phases
+    // apart on the same full/empty mbarriers alias under parity waits.)
     if (lane == 0) {
       const uint32_t row_bytes = p.block_k * 2;
       const int kk = p.block_k >> 4;
@@ -182,15 +180,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t b_res_addr = smem_u32(b_res);
       const uint32_t desc_hi = static_cast<uint32_t>(make_kmajor_desc(0, row_bytes) >> 32);
       const uint32_t a_step16 = p.a_stage_bytes >> 4, b_step16 = p.b_stage_bytes >> 4;
-      const int my_stage = warp - 1;
-      const int groups_per_tile = (p.num_k_iters + p.kpg - 1) / p.kpg;
       int kit = 0, lt = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
         const int as = lt & 1;
-        if (as != my_stage) {
-          kit += groups_per_tile;
-          continue;
-        }
+
         const uint32_t aph = (lt >> 1) & 1;
         mbar_wait(&acc_empty[as], aph ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
