@@ -280,15 +280,23 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const float tx = __uint_as_float(v[0]) + bias_s[base_col + 0], ty = __uint_as_float(v[1]) + bias_s[base_col + 1];
           const float tw = __uint_as_float(v[2]) + bias_s[base_col + 2], th = __uint_as_float(v[3]) + bias_s[base_col + 3];
           for (int c = 16; c < K; c += 16) {
+            // keep the 16-column read inside this accumulator stage (the last chunk of the last anchor would run
+            // past column block_n): slide it back and skip the columns already handled
+            int start = base_col + c, skip = 0;
+            if (start + 16 > p.block_n) {
+              skip = start + 16 - p.block_n;
+              start -= skip;
+            }
             uint32_t u[16];
-            tmem_ld_32x32b_x16(taddr + base_col + c, u);
+            tmem_ld_32x32b_x16(taddr + start, u);
             tmem_ld_wait();
             if (pass) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const int k = c + j - 5;
-                if (k < D.n_classes) {
-                  const float score = __fmul_rn(sigmoidf_ref(__uint_as_float(u[j]) + bias_s[base_col + c + j]), obj);
+                const int col = start + j;           // column inside the head
+                const int k = col - base_col - 5;    // class index
+                if (j >= skip && k < D.n_classes) {
+                  const float score = __fmul_rn(sigmoidf_ref(__uint_as_float(u[j]) + bias_s[col]), obj);
                   if (score > D.score_thresh) {
                     emit_candidate(D.keys, D.img_count, D.cap_per_image, n_img, anchor_flat, D.n_classes, k, score);
                     any = true;
