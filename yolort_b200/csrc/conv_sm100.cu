@@ -264,12 +264,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (!__any_sync(0xffffffffu, pass)) continue;
           const int anchor_flat = D.level_start + (a * p.dec_H + py) * p.dec_W + px;
           bool any = false;
+          // Cheap conservative pre-test on the raw class logit: sigmoid(x)*obj > thr  <=>  x > logit(thr/obj).
+          // Lanes that failed the objectness test get +inf; the exact fp32 expression is evaluated only for the
+          // few logits above the bound (minus a safety margin), so the decision itself is unchanged.
+          float lt = INFINITY;
           if (pass) {
+            const float r = D.score_thresh / obj;
+            lt = r < 1.0f ? __logf(r / (1.0f - r)) - 1e-2f : INFINITY;
+            if (!(D.score_thresh > 0.f)) lt = -INFINITY;
+          }
+          {
 #pragma unroll
             for (int j = 5; j < 16; ++j) {
               const int k = j - 5;
-              if (k < D.n_classes) {
-                const float score = __fmul_rn(sigmoidf_ref(__uint_as_float(v[j]) + bias_s[base_col + j]), obj);
+              const float x = __uint_as_float(v[j]) + bias_s[base_col + j];
+              if (k < D.n_classes && x > lt) {
+                const float score = __fmul_rn(sigmoidf_ref(x), obj);
                 if (score > D.score_thresh) {
                   emit_candidate(D.keys, D.img_count, D.cap_per_image, n_img, anchor_flat, D.n_classes, k, score);
                   any = true;
@@ -290,13 +300,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint32_t u[16];
             tmem_ld_32x32b_x16(taddr + start, u);
             tmem_ld_wait();
-            if (pass) {
+            {
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const int col = start + j;           // column inside the head
                 const int k = col - base_col - 5;    // class index
-                if (j >= skip && k < D.n_classes) {
-                  const float score = __fmul_rn(sigmoidf_ref(__uint_as_float(u[j]) + bias_s[col]), obj);
+                const float x = __uint_as_float(u[j]) + bias_s[col];
+                if (j >= skip && k < D.n_classes && x > lt) {
+                  const float score = __fmul_rn(sigmoidf_ref(x), obj);
                   if (score > D.score_thresh) {
                     emit_candidate(D.keys, D.img_count, D.cap_per_image, n_img, anchor_flat, D.n_classes, k, score);
                     any = true;
