@@ -254,73 +254,90 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int n_img = static_cast<int>(row / hw);
         const int rem = static_cast<int>(row - static_cast<long long>(n_img) * hw);
         const int py = rem / p.dec_W, px = rem - py * p.dec_W;
-        for (int a = 0; a < D.n_anchors; ++a) {
-          const int base_col = a * K;
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(taddr + base_col, v);
-          tmem_ld_wait();
-          const float obj = sigmoidf_ref(__uint_as_float(v[4]) + bias_s[base_col + 4]);
-          const bool pass = row_ok && obj > D.score_thresh;
-          if (!__any_sync(0xffffffffu, pass)) continue;
-          const int anchor_flat = D.level_start + (a * p.dec_H + py) * p.dec_W + px;
-          bool any = false;
-          // Cheap conservative pre-test on the raw class logit: sigmoid(x)*obj > thr  <=>  x > logit(thr/obj).
-          // Lanes that failed the objectness test get +inf; the exact fp32 expression is evaluated only for the
-          // few logits above the bound (minus a safety margin), so the decision itself is unchanged.
-          float lt = INFINITY;
-          if (pass) {
-            const float r = D.score_thresh / obj;
-            lt = r < 1.0f ? __logf(r / (1.0f - r)) - 1e-2f : INFINITY;
-            if (!(D.score_thresh > 0.f)) lt = -INFINITY;
-          }
-          {
+        // pass 1: objectness of every anchor (16-column ALIGNED TMEM reads: unaligned start columns are an order
+        // of magnitude slower)
+        constexpr int kMaxA = 4;
+        float obj[kMaxA], lt[kMaxA], bx[kMaxA][4];
+        bool pass[kMaxA], emitted[kMaxA];
+        uint32_t anchors_alive = 0;   // warp-uniform: bit a set iff some pixel of the warp passed anchor a
 #pragma unroll
-            for (int j = 5; j < 16; ++j) {
-              const int k = j - 5;
-              const float x = __uint_as_float(v[j]) + bias_s[base_col + j];
-              if (k < D.n_classes && x > lt) {
-                const float score = __fmul_rn(sigmoidf_ref(x), obj);
-                if (score > D.score_thresh) {
-                  emit_candidate(D.keys, D.img_count, D.cap_per_image, n_img, anchor_flat, D.n_classes, k, score);
-                  any = true;
-                }
-              }
-            }
-          }
-          const float tx = __uint_as_float(v[0]) + bias_s[base_col + 0], ty = __uint_as_float(v[1]) + bias_s[base_col + 1];
-          const float tw = __uint_as_float(v[2]) + bias_s[base_col + 2], th = __uint_as_float(v[3]) + bias_s[base_col + 3];
-          for (int c = 16; c < K; c += 16) {
-            // keep the 16-column read inside this accumulator stage (the last chunk of the last anchor would run
-            // past column block_n): slide it back and skip the columns already handled
-            int start = base_col + c, skip = 0;
-            if (start + 16 > p.block_n) {
-              skip = start + 16 - p.block_n;
-              start -= skip;
-            }
-            uint32_t u[16];
-            tmem_ld_32x32b_x16(taddr + start, u);
+        for (int a = 0; a < kMaxA; ++a) {
+          obj[a] = 0.f; lt[a] = INFINITY; pass[a] = false; emitted[a] = false;
+          bx[a][0] = bx[a][1] = bx[a][2] = bx[a][3] = 0.f;
+          if (a < D.n_anchors) {
+            const int oc = a * K + 4;
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(taddr + (oc & ~15), v);
             tmem_ld_wait();
-            {
+            float xo = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) xo = (j == (oc & 15)) ? __uint_as_float(v[j]) : xo;
+            obj[a] = sigmoidf_ref(xo + bias_s[oc]);
+            pass[a] = row_ok && obj[a] > D.score_thresh;
+            if (pass[a]) {
+              // cheap conservative pre-test on raw class logits: sigmoid(x)*obj > thr  <=>  x > logit(thr/obj)
+              const float r = D.score_thresh / obj[a];
+              lt[a] = r < 1.0f ? __logf(r / (1.0f - r)) - 1e-2f : INFINITY;
+              if (!(D.score_thresh > 0.f)) lt[a] = -INFINITY;
+            }
+            if (__any_sync(0xffffffffu, pass[a])) anchors_alive |= 1u << a;
+          }
+        }
+        // pass 2: aligned chunks that overlap an alive anchor
+        if (anchors_alive) {
+          int ca = 0, cr = 0;   // anchor / offset-in-anchor of the chunk's first column
+          for (int c = 0; c < D.n_anchors * K; c += 16) {
+            // anchors overlapping [c, c+16)
+            const int a_first = ca;
+            const int a_last = (cr + 15 >= K) ? ca + 1 : ca;
+            const bool need = ((anchors_alive >> a_first) & 1u) || (a_last < D.n_anchors && ((anchors_alive >> a_last) & 1u));
+            if (need) {
+              uint32_t u[16];
+              tmem_ld_32x32b_x16(taddr + c, u);
+              tmem_ld_wait();
+              int a = ca, r = cr;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
-                const int col = start + j;           // column inside the head
-                const int k = col - base_col - 5;    // class index
-                const float x = __uint_as_float(u[j]) + bias_s[col];
-                if (j >= skip && k < D.n_classes && x > lt) {
-                  const float score = __fmul_rn(sigmoidf_ref(x), obj);
-                  if (score > D.score_thresh) {
-                    emit_candidate(D.keys, D.img_count, D.cap_per_image, n_img, anchor_flat, D.n_classes, k, score);
-                    any = true;
+                if (a < D.n_anchors) {
+                  const float x = __uint_as_float(u[j]) + bias_s[c + j];
+#pragma unroll
+                  for (int aa = 0; aa < kMaxA; ++aa) {
+                    if (aa == a && pass[aa]) {
+                      if (r < 4) {
+                        bx[aa][r & 3] = x;
+                      } else if (r >= 5 && x > lt[aa]) {
+                        const float score = __fmul_rn(sigmoidf_ref(x), obj[aa]);
+                        if (score > D.score_thresh) {
+                          const int anchor_flat = D.level_start + (aa * p.dec_H + py) * p.dec_W + px;
+                          emit_candidate(D.keys, D.img_count, D.cap_per_image, n_img, anchor_flat, D.n_classes, r - 5, score);
+                          emitted[aa] = true;
+                        }
+                      }
+                    }
                   }
+                }
+                if (++r == K) {
+                  r = 0;
+                  ++a;
                 }
               }
             }
+            cr += 16;
+            if (cr >= K) {
+              cr -= K;
+              ++ca;
+            }
           }
-          if (any) {
-            const float4 b = decode_box(sigmoidf_ref(tx), sigmoidf_ref(ty), sigmoidf_ref(tw), sigmoidf_ref(th), px, py,
-                                        D.stride_px, D.anchors_px[2 * a], D.anchors_px[2 * a + 1]);
-            reinterpret_cast<float4*>(D.boxes)[static_cast<long long>(n_img) * D.anchors_per_image + anchor_flat] = b;
-            atomicMax(&D.img_maxc[n_img], float_to_ordered_int(fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
+#pragma unroll
+          for (int aa = 0; aa < kMaxA; ++aa) {
+            if (emitted[aa]) {
+              const int anchor_flat = D.level_start + (aa * p.dec_H + py) * p.dec_W + px;
+              const float4 b = decode_box(sigmoidf_ref(bx[aa][0]), sigmoidf_ref(bx[aa][1]), sigmoidf_ref(bx[aa][2]),
+                                          sigmoidf_ref(bx[aa][3]), px, py, D.stride_px, D.anchors_px[2 * aa],
+                                          D.anchors_px[2 * aa + 1]);
+              reinterpret_cast<float4*>(D.boxes)[static_cast<long long>(n_img) * D.anchors_per_image + anchor_flat] = b;
+              atomicMax(&D.img_maxc[n_img], float_to_ordered_int(fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
+            }
           }
         }
         tc_fence_before();
