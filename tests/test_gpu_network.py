@@ -29,10 +29,9 @@ def test_features_and_heads_vs_reference_fixture():
     z = util.load_npz("network_n.npz")
     m, sd = _model_n()
     x = torch.from_numpy(z["x"]).to(DEV)
-    dets = m.model(x)   # YOLO.forward on a pre-letterboxed NCHW batch (fused decode epilogue in the heads)
+    dets = m.model(x)   # YOLO.forward on a pre-letterboxed NCHW batch
     plan = m.model.get_plan(1, 96, 128)
-    assert plan.fused_post is not None
-    m.model.run_plan(plan)   # same plan with the heads storing their logits
+    m.model.run_plan(plan)   # (re)store the head logits
     torch.cuda.synchronize()
     for key, name in (("p3", "p3"), ("p4", "p4"), ("p5", "p5")):
         got = plan.features[name].float().permute(0, 3, 1, 2).cpu().numpy()
@@ -129,9 +128,10 @@ def test_fused_head_decode_equals_unfused(monkeypatch):
     m, sd = _model_n()
     z = util.load_npz("e2e_n.npz")
     ims = [torch.from_numpy(z["img0"]).to(DEV), torch.from_numpy(z["img1"]).to(DEV)]
-    fused = m(ims)
-    monkeypatch.setenv("YB_DISABLE_FUSED_DECODE", "1")
     plain = m(ims)
+    monkeypatch.setenv("YB_FUSED_DECODE", "1")
+    fused = m(ims)
+    assert m.model.get_plan(2, 128, 128).fused_post is not None
     for a, b in zip(fused, plain):
         assert abs(len(a["scores"]) - len(b["scores"])) <= 3
         frac = util.match_fraction(util.to_np(a), util.to_np(b), iou_thr=0.95)
