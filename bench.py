@@ -96,7 +96,7 @@ class ClockSampler:
                     q = cand
                     break
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
@@ -129,6 +129,16 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def conv_traffic():
+    """DRAM bytes of all convolution launches of one step, from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["dram_bytes_per_step"])
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -333,7 +343,7 @@ def main():
                     "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": (native_plan.n_ops + 1 + 2 + (0 if plan.fused_post is not None else 1)) * args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "conv_umma_kernel (all conv launches of one step)",
+                         "traffic": conv_traffic(), "peak_source": peak_src, "kernel": "conv_umma_kernel (all conv launches of one step)",
                          "plan_ms": plan_ms, "launches_per_step": native_plan.n_ops},
             "clocks": clocks,
         }
