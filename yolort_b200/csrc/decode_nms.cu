@@ -30,6 +30,7 @@ namespace {
 
 constexpr int kNmsThreads = 512;
 constexpr int kSweep = 512;       // candidates consumed per sweep round (== threads)
+constexpr int kMaxLabelMasks = 256; // per-class survivor bit-masks are used up to this many classes
 constexpr int kSmallSort = 4096;  // keys sorted in shared memory
 
 template <typename T>
@@ -314,7 +315,8 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
   int* sv_label = reinterpret_cast<int*>(sv_score + kSweep);                  // [kSweep]
   uint32_t* sv_cidx = reinterpret_cast<uint32_t*>(sv_label + kSweep);         // [kSweep]
   uint32_t* s_mask = sv_cidx + kSweep;                                        // [kSweep][kSweep/32]
-  float4* k_box = reinterpret_cast<float4*>(s_mask + kSweep * (kSweep / 32)); // [max_det]
+  uint32_t* s_labmask = s_mask + kSweep * (kSweep / 32);                      // [kMaxLabelMasks][kSweep/32]
+  float4* k_box = reinterpret_cast<float4*>(s_labmask + kMaxLabelMasks * (kSweep / 32)); // [max_det]
   float* k_area = reinterpret_cast<float*>(k_box + p.max_det);
   int* k_label = reinterpret_cast<int*>(k_area + p.max_det);
   __shared__ int s_kcount, s_warp_tot[kNmsThreads / 32], s_nsurv, s_newkept;
@@ -433,9 +435,16 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
       sv_cidx[pos] = cidx;
     }
     if (tid < kSweep / 32) s_keep[tid] = 0;
+    const bool use_labmask = !trick && !p.explicit_mode && p.n_classes <= kMaxLabelMasks;
+    if (use_labmask)
+      for (int i = tid; i < p.n_classes * (kSweep / 32); i += blockDim.x) s_labmask[i] = 0;
     __syncthreads();
     const int S = s_nsurv;
     const int nwords = (S + 31) >> 5;
+    if (use_labmask) {   // bit i of s_labmask[label] <=> survivor i carries that label
+      if (tid < S) atomicOr(&s_labmask[sv_label[tid] * (kSweep / 32) + (tid >> 5)], 1u << (tid & 31));
+      __syncthreads();
+    }
     if (base == 0) YB_NMS_TICK();  // slot 6: compaction
     // suppression bit-matrix: bit j of row i set iff survivor i (if kept) suppresses survivor j > i
     if (tid < S) {
@@ -451,6 +460,8 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
           const int jend = min(32, S - j0);
           if (trick) {
             cand = jend == 32 ? 0xffffffffu : ((1u << jend) - 1u);
+          } else if (use_labmask) {
+            cand = s_labmask[li * (kSweep / 32) + w];
           } else {
             cand = 0;
             for (int b = 0; b < jend; ++b) cand |= (sv_label[j0 + b] == li ? 1u : 0u) << b;
@@ -564,7 +575,7 @@ size_t carve(Workspace& ws, uint8_t* base, int n, long long cap, long long ancho
 
 size_t nms_smem_bytes(int max_det) {
   return 36 * 1024 + static_cast<size_t>(kSweep) * (16 + 16 + 4 + 4 + 4 + 4) + static_cast<size_t>(kSweep) * (kSweep / 32) * 4 +
-         static_cast<size_t>(max_det) * (16 + 4 + 4);
+         static_cast<size_t>(kMaxLabelMasks) * (kSweep / 32) * 4 + static_cast<size_t>(max_det) * (16 + 4 + 4);
 }
 
 int ensure_nms_smem(size_t bytes) {

@@ -70,6 +70,14 @@ __device__ __forceinline__ void sample_rgb(const ImgGeom& g, const float* lut, i
     rgb[0] = rgb[1] = rgb[2] = fill;
     return;
   }
+  if (g.new_h == g.src_h && g.new_w == g.src_w) {
+    // identity resize (ratios are exactly 1, all interpolation weights exactly 0/1): plain copy, same bits
+    const SrcT* base = static_cast<const SrcT*>(g.src);
+    const size_t plane = static_cast<size_t>(g.src_h) * g.src_w, o = static_cast<size_t>(yy) * g.src_w + xx;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rgb[c] = load_src<SrcT>(base + c * plane + o, lut);
+    return;
+  }
   int y0, y1, x0, x1;
   float ly, lx;
   src_coord(yy, g.ratio_h, g.src_h, y0, y1, ly);
