@@ -139,13 +139,14 @@ def test_fused_head_decode_equals_unfused(monkeypatch):
         assert frac >= 0.97      # logits rounded to fp16 in the unfused path move scores by <= 1e-3
 
 
-def test_pipelined_host_predict_equals_device_forward():
+def test_pipelined_host_predict_equals_device_forward(monkeypatch):
     """predict() on >= 16 host images copies the second half while the first is processed; results must equal the
     unsplit device-resident call (both halves are letterboxed to the whole batch's canvas)."""
     m, sd = _model_n()
     ims = [util.synth_image_u8(64 + 8 * (i % 5), 128 - 8 * (i % 3), 70 + i) for i in range(18)]
     ref = m([im.to(DEV) for im in ims])
     pinned = [im.pin_memory() for im in ims]
+    monkeypatch.setenv("YB_PIPELINE_H2D", "1")
     got = m.predict(pinned)
     assert len(got) == len(ref) == 18
     for a, b in zip(got, ref):

@@ -82,15 +82,17 @@ class YOLOv5(nn.Module):
         images = self.collate_images(x, image_loader)
         return self.forward(images)
 
-    # Host batches are processed in two halves: the PCIe copy of the second half (copy stream) overlaps the
-    # letterbox + backbone + NMS of the first (compute stream).  Both halves are letterboxed to the canvas of the
-    # WHOLE batch, so the detections are those of the unsplit call.
+    # Opt-in (YB_PIPELINE_H2D=1): host batches are processed in two halves, the PCIe copy of the second half (copy
+    # stream) overlapping the letterbox + backbone + NMS of the first (compute stream); both halves are letterboxed
+    # to the canvas of the WHOLE batch, so the detections are those of the unsplit call.  Measured on B200 at
+    # batch 32 it LOSES (8.3 k vs 9.7 k img/s): two half-size plans under-fill the 148 SMs by more than the
+    # ~0.4 ms of hidden copy time, so the default stays off.
     _PIPELINE_MIN_IMAGES = 16
 
     def _predict_pipelined(self, x: Any) -> Optional[List[Dict[str, Tensor]]]:
         import os
 
-        if os.environ.get("YB_PIPELINE_H2D", "1") != "1" or self.training:
+        if os.environ.get("YB_PIPELINE_H2D", "0") != "1" or self.training:
             return None
         if not (isinstance(x, (list, tuple)) and len(x) >= self._PIPELINE_MIN_IMAGES
                 and all(isinstance(t, Tensor) and not t.is_cuda and t.dim() == 3 for t in x)):
