@@ -17,8 +17,10 @@ GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))
 
 
 # ---- deterministic, construction-order-independent parameters ------------------------------------------
-def synth_state_dict(shapes: dict, knob_obj: float = 0.0, knob_cls: float = 0.0, seed: int = 0) -> dict:
-    """Weights as a pure function of (key name, shape, seed): conv ~ N(0, 2/fan_in) ; BN statistics
+def synth_state_dict(shapes: dict, knob_obj: float = 0.0, knob_cls: float = 0.0, seed: int = 0,
+                     gain: float = 2.0) -> dict:
+    """Weights as a pure function of (key name, shape, seed): conv ~ N(0, gain/fan_in) (the deeper
+    m/l/x residual chains need gain < 2 to keep activations inside fp16 range, as trained weights do); BN statistics
     randomised so that folding is exercised; head bias = the constructor's
     prior (box_head.py:40-46) plus a "load knob" that raises objectness / class logits."""
     sd = {}
@@ -29,7 +31,7 @@ def synth_state_dict(shapes: dict, knob_obj: float = 0.0, knob_cls: float = 0.0,
             t = torch.zeros(shp, dtype=torch.int64)
         elif k.endswith("conv.weight") or (k.startswith("model.head") and k.endswith(".weight")):
             fan_in = shp[1] * shp[2] * shp[3]
-            t = torch.randn(shp, generator=g) * (2.0 / fan_in) ** 0.5
+            t = torch.randn(shp, generator=g) * (gain / fan_in) ** 0.5
         elif k.endswith("bn.weight") or k.endswith("running_var"):
             t = torch.rand(shp, generator=g) + 0.5
         elif k.endswith("bn.bias") or k.endswith("running_mean"):

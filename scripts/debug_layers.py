@@ -10,7 +10,7 @@ from yolort_b200 import models
 name = sys.argv[1] if len(sys.argv) > 1 else "l"
 H, W = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (192, 192)
 dev = "cuda:0"
-sd = util.synth_state_dict(util.layouts()[name], knob_obj=7.0, knob_cls=4.5, seed=1)
+sd = util.synth_state_dict(util.layouts()[name], knob_obj=7.0, knob_cls=4.5, seed=1, gain={"m":1.7,"l":1.7,"x":1.5}.get(name,2.0))
 m = getattr(models, f"yolov5{name}")(size=(H, W), score_thresh=0.2).eval(); m.load_state_dict(sd); m = m.to(dev)
 g = torch.Generator().manual_seed(0)
 x = torch.rand(2, 3, H, W, generator=g)
