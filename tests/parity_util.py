@@ -11,8 +11,17 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def layouts():
-    with open(os.path.join(GOLDEN, "state_dict_layouts.json")) as f:
-        return json.load(f)
+    out = {}
+    for fn in ("state_dict_layouts.json", "state_dict_layouts_p6.json"):
+        with open(os.path.join(GOLDEN, fn)) as f:
+            out.update(json.load(f))
+    return out
+
+
+P6_STRIDES = [8, 16, 32, 64]
+P6_ANCHORS = [[19, 27, 44, 40, 38, 94], [96, 68, 86, 152, 180, 137], [140, 301, 303, 264, 238, 542],
+              [436, 615, 739, 380, 925, 792]]
+GAIN_N6 = 2.22   # oracle/make_golden_p6.py
 
 
 def load_npz(name):

@@ -194,9 +194,11 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
     L = _Lowering(dtype, device)
     bb = model.backbone
     body, pan = bb.body, bb.pan
-    if len(model.head.head) != 3 or getattr(pan, "intermediate_blocks", None) is not None:
-        raise NotImplementedError("only the 3-level r6.0 topology is lowered (P6 is 'next' in SURVEY.md 8f)")
-    c3, c4, c5 = bb.out_channels
+    ch = list(bb.out_channels)
+    nl = len(ch)                                   # detection levels: 3, or 4 with the P6 intermediate block
+    has_p6 = getattr(pan, "intermediate_blocks", None) is not None
+    if nl not in (3, 4) or len(model.head.head) != nl or has_p6 != (nl == 4):
+        raise NotImplementedError("lowering covers the r6.0 topologies: 3 levels, or 4 levels with the P6 block")
 
     x0 = L.buf("input.s2d", 2, 16)
     stem: Conv = body["0"]
@@ -211,15 +213,17 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
            _C.YB_ACT_SILU, ref_flops_per_pixel=spk * 2 * w.shape[0] * 3 * 36, pack=spk,
            force_im2col=os.environ.get("YB_STEM_IM2COL", "0") == "1")
 
-    # concat buffers of the neck (path_aggregation_network.py:215-237)
-    cat1 = L.buf("pan.cat1[up(lat1)|f6]", 16, 2 * c4)
-    cat2 = L.buf("pan.cat2[up(lat2)|f4]", 8, 2 * c3)
-    cat_p4 = L.buf("pan.cat_p4[down(p3)|lat2]", 16, 2 * c3)
-    cat_p5 = L.buf("pan.cat_p5[down(p4)|lat1]", 32, 2 * c4)
+    # Concat buffers of the neck (path_aggregation_network.py:215-237), level l at stride 8 << l:
+    #   cat_dn[l] = [up(lateral from level l+1) | body tap of level l]   (descending pass, l < nl-1)
+    #   cat_up[l] = [down(result of level l-1) | lateral of level l]     (ascending pass,  l > 0)
+    # lateral k (k = 1..nl-1) is the 1x1 conv output at level nl-k; producers write straight into these windows.
+    taps = (4, 6, 8)
+    cat_dn = {l: L.buf(f"pan.cat{nl - 1 - l}[up(lat{nl - 1 - l})|f{taps[l]}]", 8 << l, 2 * ch[l]) for l in range(nl - 1)}
+    cat_up = {l: L.buf(f"pan.cat_p{l + 3}[down(p{l + 2})|lat{nl - l}]", 8 << l, 2 * ch[l - 1]) for l in range(1, nl)}
 
     cur = _View(t0, 0, w.shape[0])
     div = 2
-    tap_dst = {4: _View(cat2, c3, c3), 6: _View(cat1, c4, c4)}
+    tap_dst = {taps[l]: _View(cat_dn[l], ch[l], ch[l]) for l in range(min(nl - 1, 3))}
     for i in range(1, 9):
         m = body[str(i)]
         if isinstance(m, Conv):
@@ -234,37 +238,46 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
             assert dst.C == co
             L.c3(f"body.{i}", m, cur, dst)
             cur = dst
-    f8 = cur
+    top = cur
+    if has_p6:   # IntermediateLevelP6 (path_aggregation_network.py:34-41): stride-64 level from the last tap
+        p6m = pan.intermediate_blocks.p6
+        t = _View(L.buf("pan.p6.conv", 64, ch[3]), 0, ch[3])
+        L.conv_module("pan.intermediate_blocks.p6.0", p6m[0], top, t)
+        top = _View(L.buf("pan.p6", 64, ch[3]), 0, ch[3])
+        L.c3("pan.intermediate_blocks.p6.1", p6m[1], t, top)
 
     inner, layer = pan.inner_blocks, pan.layer_blocks
-    s = _View(L.buf("pan.spp", 32, c5), 0, c5)
-    L.spp("pan.inner_blocks.0", inner[0], f8, s)
-    lat1 = _View(cat_p5, c4, c4)
-    L.conv_module("pan.inner_blocks.1", inner[1], s, lat1)
-    L.upsample("pan.inner_blocks.2", lat1, _View(cat1, 0, c4))
-    u1 = _View(L.buf("pan.u1", 16, c4), 0, c4)
-    L.c3("pan.inner_blocks.3", inner[3], _View(cat1, 0, 2 * c4), u1)
-    lat2 = _View(cat_p4, c3, c3)
-    L.conv_module("pan.inner_blocks.4", inner[4], u1, lat2)
-    L.upsample("pan.inner_blocks.5", lat2, _View(cat2, 0, c3))
-    p3 = _View(L.buf("pan.p3", 8, c3), 0, c3)
-    L.c3("pan.layer_blocks.0", layer[0], _View(cat2, 0, 2 * c3), p3)
-    L.conv_module("pan.layer_blocks.1", layer[1], p3, _View(cat_p4, 0, c3))
-    p4 = _View(L.buf("pan.p4", 16, c4), 0, c4)
-    L.c3("pan.layer_blocks.2", layer[2], _View(cat_p4, 0, 2 * c3), p4)
-    L.conv_module("pan.layer_blocks.3", layer[3], p4, _View(cat_p5, 0, c4))
-    p5 = _View(L.buf("pan.p5", 32, c5), 0, c5)
-    L.c3("pan.layer_blocks.4", layer[4], _View(cat_p5, 0, 2 * c4), p5)
+    # descending pass (`:215-222`): idx-th iteration works at level nl-1-idx
+    last = _View(L.buf("pan.spp", 8 << (nl - 1), ch[-1]), 0, ch[-1])
+    L.spp("pan.inner_blocks.0", inner[0], top, last)
+    for idx in range(nl - 1):
+        l = nl - 1 - idx
+        if idx > 0:
+            u = _View(L.buf(f"pan.u{idx}", 8 << l, ch[l]), 0, ch[l])
+            L.c3(f"pan.inner_blocks.{3 * idx}", inner[3 * idx], _View(cat_dn[l], 0, 2 * ch[l]), u)
+            last = u
+        lat = _View(cat_up[l], ch[l - 1], ch[l - 1])
+        L.conv_module(f"pan.inner_blocks.{3 * idx + 1}", inner[3 * idx + 1], last, lat)
+        L.upsample(f"pan.inner_blocks.{3 * idx + 2}", lat, _View(cat_dn[l - 1], 0, ch[l - 1]))
+    # ascending pass (`:226-237`)
+    results = [_View(L.buf("pan.p3", 8, ch[0]), 0, ch[0])]
+    L.c3("pan.layer_blocks.0", layer[0], _View(cat_dn[0], 0, 2 * ch[0]), results[0])
+    for idx in range(nl - 1):
+        l = idx + 1
+        L.conv_module(f"pan.layer_blocks.{2 * idx + 1}", layer[2 * idx + 1], results[idx], _View(cat_up[l], 0, ch[idx]))
+        r = _View(L.buf(f"pan.p{l + 3}", 8 << l, ch[l]), 0, ch[l])
+        L.c3(f"pan.layer_blocks.{2 * idx + 2}", layer[2 * idx + 2], _View(cat_up[l], 0, 2 * ch[idx]), r)
+        results.append(r)
 
     head_bufs = []
-    for i, (feat, conv) in enumerate(zip((p3, p4, p5), model.head.head)):
+    for i, (feat, conv) in enumerate(zip(results, model.head.head)):
         co = conv.out_channels
         co_buf = _round_up(co, 16)
         hb = L.buf(f"head.{i}", feat.buf.div, co_buf)
         L.conv(f"head.head.{i}", conv.weight.detach().double().cpu(), conv.bias.detach().double().cpu(), feat,
                _View(hb, 0, co_buf), 1, 1, 0, _C.YB_ACT_NONE)
         head_bufs.append(hb)
-    return L, x0, head_bufs, {"p3": p3, "p4": p4, "p5": p5}
+    return L, x0, head_bufs, {f"p{l + 3}": r for l, r in enumerate(results)}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -275,8 +288,9 @@ class PlanInstance:
 
     def __init__(self, L: _Lowering, x0: _Buf, head_bufs: List[_Buf], feats: Dict[str, _View], N: int, H: int, W: int,
                  post: Optional[dict] = None):
-        if H % 32 or W % 32:
-            raise ValueError(f"canvas {H}x{W} must be a multiple of 32")
+        grain = max(b.div for b in L.bufs)
+        if H % grain or W % grain:
+            raise ValueError(f"canvas {H}x{W} must be a multiple of {grain}")
         self.N, self.H, self.W = N, H, W
         self.dtype, self.device = L.dtype, L.device
         esz = 2

@@ -5,10 +5,10 @@ from typing import Any
 from .yolo import YOLO
 from .yolov5 import YOLOv5
 
-__all__ = ["YOLO", "YOLOv5", "yolov5n", "yolov5s", "yolov5m", "yolov5l", "yolov5x"]
+__all__ = ["YOLO", "YOLOv5", "yolov5n", "yolov5s", "yolov5m", "yolov5l", "yolov5x", "yolov5n6", "yolov5s6", "yolov5m6"]
 
 
-def _make(size: str):
+def _make(size: str, p6: bool = False):
     def ctor(upstream_version: str = "r6.0", export_friendly: bool = False, **kwargs: Any) -> YOLOv5:
         """Args:
             upstream_version (str): ultralytics release; only "r6.0" is built here.
@@ -17,9 +17,11 @@ def _make(size: str):
         """
         if upstream_version != "r6.0":
             raise NotImplementedError("Currently only supports r6.0 versions (r4.0/r3.1 are 'next' in SURVEY.md 8f)")
+        if p6:   # models/__init__.py:112-166: the P6 constructors letterbox to multiples of 64
+            return YOLOv5(arch=f"yolov5_darknet_pan_{size}6_r60", size_divisible=64, **kwargs)
         return YOLOv5(arch=f"yolov5_darknet_pan_{size}_r60", **kwargs)
 
-    ctor.__name__ = f"yolov5{size}"
+    ctor.__name__ = f"yolov5{size}" + ("6" if p6 else "")
     return ctor
 
 
@@ -28,3 +30,6 @@ yolov5s = _make("s")
 yolov5m = _make("m")
 yolov5l = _make("l")
 yolov5x = _make("x")
+yolov5n6 = _make("n", p6=True)
+yolov5s6 = _make("s", p6=True)
+yolov5m6 = _make("m", p6=True)

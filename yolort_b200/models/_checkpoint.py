@@ -99,12 +99,19 @@ def load_from_ultralytics(checkpoint_path: str, version: str = "r6.0") -> Dict[s
     # anchors in pixels = Detect.anchors (grid units) * stride  (_checkpoint.py:38-43)
     anchor_grids = (detect.anchors.float() * torch.as_tensor(detect.stride).float().view(-1, 1, 1)).reshape(
         len(strides), 2 * num_anchors).tolist()
-    if len(strides) != 3:
-        raise NotImplementedError("P6 checkpoints (4 detection levels) are 'next' in SURVEY.md section 8f")
-
-    inner_map = {"0": 9, "1": 10, "3": 13, "4": 14}          # _checkpoint.py:60
-    layer_map = {"0": 17, "1": 18, "2": 20, "3": 21, "4": 23}  # _checkpoint.py:61
-    head_ind = 24
+    use_p6 = len(strides) == 4                                # _checkpoint.py:49-51
+    if len(strides) not in (3, 4):
+        raise NotImplementedError(f"checkpoints with {len(strides)} detection levels are not supported")
+    if use_p6:                                                # _checkpoint.py:53-58
+        inner_map = {"0": 11, "1": 12, "3": 15, "4": 16, "6": 19, "7": 20}
+        layer_map = {"0": 23, "1": 24, "2": 26, "3": 27, "4": 29, "5": 30, "6": 32}
+        p6_map = {"0": 9, "1": 10}
+        head_ind = 33
+    else:
+        inner_map = {"0": 9, "1": 10, "3": 13, "4": 14}          # _checkpoint.py:60
+        layer_map = {"0": 17, "1": 18, "2": 20, "3": 21, "4": 23}  # _checkpoint.py:61
+        p6_map = {}
+        head_ind = 24
 
     sd: Dict[str, torch.Tensor] = {}
 
@@ -114,6 +121,8 @@ def load_from_ultralytics(checkpoint_path: str, version: str = "r6.0") -> Dict[s
 
     for i in range(9):
         take(f"backbone.body.{i}", seq[i])
+    for ours, theirs in p6_map.items():
+        take(f"backbone.pan.intermediate_blocks.p6.{ours}", seq[theirs])
     for ours, theirs in inner_map.items():
         take(f"backbone.pan.inner_blocks.{ours}", seq[theirs])
     for ours, theirs in layer_map.items():
@@ -128,7 +137,7 @@ def load_from_ultralytics(checkpoint_path: str, version: str = "r6.0") -> Dict[s
         "width_multiple": width_multiple,
         "strides": strides,
         "anchor_grids": anchor_grids,
-        "use_p6": False,
+        "use_p6": use_p6,
         "size": get_yolov5_size(depth_multiple, width_multiple),
         "state_dict": sd,
     }

@@ -1,8 +1,10 @@
 """PANet neck (r6.0) -- parameter container.
 
 Block order and indices follow the reference (yolort/models/path_aggregation_network.py:77-165):
-inner_blocks = [SPP, Conv1x1, Upsample, C3, Conv1x1, Upsample], layer_blocks = [C3, Conv3x3s2, C3,
-Conv3x3s2, C3].  Data flow (`:199-239`) is lowered by yolort_b200/engine.py.
+3 levels: inner_blocks = [SPP, Conv1x1, Upsample, C3, Conv1x1, Upsample], layer_blocks = [C3, Conv3x3s2, C3,
+Conv3x3s2, C3].  P6 (4 levels, `:10-41,119-126,148-154`): an intermediate [Conv3x3s2, C3] block builds the
+stride-64 map, inner_blocks gain [Conv1x1, Upsample, C3] after the SPP and layer_blocks gain [Conv3x3s2, C3].
+Data flow (`:199-239`) is lowered by yolort_b200/engine.py.
 """
 from typing import List
 
@@ -12,34 +14,52 @@ from ._utils import depth_gain
 from .common import C3, Conv, SPP, _PlanOnly
 
 
+class IntermediateLevelP6(_PlanOnly):
+    """Stride-64 level appended to the body taps (path_aggregation_network.py:10-41); the Sequential keeps the
+    reference's parameter names `intermediate_blocks.p6.{0,1}`."""
+
+    def __init__(self, depth_multiple: float, in_channel: int, out_channel: int):
+        super().__init__()
+        self.p6 = nn.Sequential(
+            Conv(in_channel, out_channel, k=3, s=2),
+            C3(out_channel, out_channel, n=depth_gain(3, depth_multiple)),
+        )
+
+
 class PathAggregationNetwork(_PlanOnly):
     def __init__(self, in_channels: List[int], depth_multiple: float, version: str = "r6.0", use_p6: bool = False):
         super().__init__()
         if version != "r6.0":
             raise NotImplementedError(f"only upstream version 'r6.0' is built here, got {version!r}")
-        if use_p6:
-            raise NotImplementedError("P6 variants are listed as 'next' in SURVEY.md section 8(f)")
-        if len(in_channels) != 3:
-            raise ValueError("Length of in channels should be 3.")
-        c3, c4, c5 = in_channels
         n = depth_gain(3, depth_multiple)
-        self.intermediate_blocks = None
-        self.inner_blocks = nn.ModuleList(
-            [
-                SPP(c5, c5, k=(5, 9, 13)),
-                Conv(c5, c4, 1, 1),
-                nn.Upsample(scale_factor=2),
-                C3(c5, c4, n=n, shortcut=False),
-                Conv(c4, c3, 1, 1),
-                nn.Upsample(scale_factor=2),
-            ]
-        )
-        self.layer_blocks = nn.ModuleList(
-            [
-                C3(c4, c3, n=n, shortcut=False),
-                Conv(c3, c3, 3, 2),
-                C3(c4, c4, n=n, shortcut=False),
-                Conv(c4, c4, 3, 2),
-                C3(c5, c5, n=n, shortcut=False),
-            ]
-        )
+        ch = list(in_channels)
+        if use_p6:
+            if len(ch) != 4:
+                raise ValueError("Length of in channels should be 4.")
+            self.intermediate_blocks = IntermediateLevelP6(depth_multiple, ch[2], ch[3])
+        else:
+            if len(ch) != 3:
+                raise ValueError("Length of in channels should be 3.")
+            self.intermediate_blocks = None
+        inner: List[nn.Module] = [SPP(ch[-1], ch[-1], k=(5, 9, 13))]
+        if use_p6:
+            inner += [Conv(ch[-1], ch[2], 1, 1), nn.Upsample(scale_factor=2),
+                      C3(ch[1] + ch[-1], ch[2], n=n, shortcut=False)]
+        inner += [
+            Conv(ch[2], ch[1], 1, 1),
+            nn.Upsample(scale_factor=2),
+            C3(ch[-1], ch[1], n=n, shortcut=False),
+            Conv(ch[1], ch[0], 1, 1),
+            nn.Upsample(scale_factor=2),
+        ]
+        self.inner_blocks = nn.ModuleList(inner)
+        layer: List[nn.Module] = [
+            C3(ch[1], ch[0], n=n, shortcut=False),
+            Conv(ch[0], ch[0], 3, 2),
+            C3(ch[1], ch[1], n=n, shortcut=False),
+            Conv(ch[1], ch[1], 3, 2),
+            C3(ch[-1], ch[2], n=n, shortcut=False),
+        ]
+        if use_p6:
+            layer += [Conv(ch[2], ch[2], 3, 2), C3(ch[1] + ch[-1], ch[-1], n=n, shortcut=False)]
+        self.layer_blocks = nn.ModuleList(layer)

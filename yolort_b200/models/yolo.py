@@ -23,6 +23,11 @@ __all__ = [
     "yolov5_darknet_pan_m_r60",
     "yolov5_darknet_pan_l_r60",
     "yolov5_darknet_pan_x_r60",
+    "yolov5_darknet_pan_n6_r60",
+    "yolov5_darknet_pan_s6_r60",
+    "yolov5_darknet_pan_m6_r60",
+    "yolov5_darknet_pan_l6_r60",
+    "yolov5_darknet_pan_x6_r60",
 ]
 
 DEFAULT_STRIDES = [8, 16, 32]
@@ -30,6 +35,14 @@ DEFAULT_ANCHOR_GRIDS = [
     [10, 13, 16, 30, 33, 23],
     [30, 61, 62, 45, 59, 119],
     [116, 90, 156, 198, 373, 326],
+]
+# P6 variants (yolort/models/yolo.py:641-647; the same table in every *6 factory)
+P6_STRIDES = [8, 16, 32, 64]
+P6_ANCHOR_GRIDS = [
+    [19, 27, 44, 40, 38, 94],
+    [96, 68, 86, 152, 180, 137],
+    [140, 301, 303, 264, 238, 542],
+    [436, 615, 739, 380, 925, 792],
 ]
 
 
@@ -179,13 +192,18 @@ def build_model(backbone_name: str, depth_multiple: float, width_multiple: float
     return model
 
 
-def _factory(size: str, depth: float, width: float):
-    def fn(pretrained: bool = False, progress: bool = True, num_classes: int = 80, **kwargs: Any) -> YOLO:
-        return build_model(f"darknet_{size}_r6_0", depth, width, "r6.0", f"yolov5_darknet_pan_{size}_r60_coco",
-                           pretrained, progress, num_classes, **kwargs)
+def _factory(size: str, depth: float, width: float, use_p6: bool = False):
+    six = "6" if use_p6 else ""
 
-    fn.__name__ = f"yolov5_darknet_pan_{size}_r60"
-    fn.__doc__ = f"yolov5 {size} release 6.0 (depth_multiple={depth}, width_multiple={width})."
+    def fn(pretrained: bool = False, progress: bool = True, num_classes: int = 80, **kwargs: Any) -> YOLO:
+        if use_p6:   # yolo.py:640-661: the *6 factories pin strides and anchor grids
+            kwargs = dict(kwargs, strides=P6_STRIDES, anchor_grids=P6_ANCHOR_GRIDS)
+        return build_model(f"darknet_{size}_r6_0", depth, width, "r6.0", f"yolov5_darknet_pan_{size}{six}_r60_coco",
+                           pretrained, progress, num_classes, use_p6=use_p6, **kwargs)
+
+    fn.__name__ = f"yolov5_darknet_pan_{size}{six}_r60"
+    fn.__doc__ = (f"yolov5 {size}{six} release 6.0 (depth_multiple={depth}, width_multiple={width}"
+                  + (", P6: 4 levels, strides 8..64)." if use_p6 else ")."))
     return fn
 
 
@@ -195,3 +213,9 @@ yolov5_darknet_pan_s_r60 = _factory("s", 0.33, 0.5)
 yolov5_darknet_pan_m_r60 = _factory("m", 0.67, 0.75)
 yolov5_darknet_pan_l_r60 = _factory("l", 1.0, 1.0)
 yolov5_darknet_pan_x_r60 = _factory("x", 1.33, 1.25)
+# P6 table: yolort/models/yolo.py:622-834
+yolov5_darknet_pan_n6_r60 = _factory("n", 0.33, 0.25, use_p6=True)
+yolov5_darknet_pan_s6_r60 = _factory("s", 0.33, 0.5, use_p6=True)
+yolov5_darknet_pan_m6_r60 = _factory("m", 0.67, 0.75, use_p6=True)
+yolov5_darknet_pan_l6_r60 = _factory("l", 1.0, 1.0, use_p6=True)
+yolov5_darknet_pan_x6_r60 = _factory("x", 1.33, 1.25, use_p6=True)
