@@ -66,6 +66,16 @@ int yb_letterbox(int n, const void* const* src_dev, int src_dtype, const yb_lett
                  int Hb, int Wb, float fill, const float* u8_lut_dev, void* dst_dev, int dst_dtype,
                  int dst_layout, void* stream);
 
+/* Same, with an explicit source memory order: YB_SRC_CHW (planar, what yb_letterbox assumes) or YB_SRC_HWC
+ * (interleaved RGBRGB..., what image decoders emit -- the output of the reference's default loader
+ * `read_image` (yolort/models/yolov5.py:218-228) before its permute), so decoded files go from a pinned
+ * host buffer to the canvas without a repacking pass. */
+#define YB_SRC_CHW 0
+#define YB_SRC_HWC 1
+int yb_letterbox_strided(int n, const void* const* src_dev, int src_dtype, int src_layout,
+                         const yb_letterbox_geom* geom, int Hb, int Wb, float fill, const float* u8_lut_dev,
+                         void* dst_dev, int dst_dtype, int dst_layout, void* stream);
+
 /* Host-only: scale_coords parameters of transform.py:354-367 for one image:
  * out[0]=gain, out[1]=pad_x, out[2]=pad_y (all fp32, fractional pads). */
 int yb_scale_coords_params(int Hb, int Wb, int src_h, int src_w, float* out3);
@@ -196,6 +206,13 @@ int yb_nms_begin(const yb_nms_params* p, const yb_head_level* levels, int64_t* s
 int yb_nms_finish(const yb_nms_params* p, const yb_head_level* levels, const float* rescale_dev, float* boxes_dev,
                   float* scores_dev, int64_t* labels_dev, int32_t* counts_dev, int64_t* status_dev,
                   void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* Dense decode, no threshold / NMS (replaces LogitsDecoder.forward: yolort/relay/logits_decoder.py:26-61, the
+ * output the reference hands to TensorRT's EfficientNMS plugin): boxes_dev [n_images, anchors_per_image, 4] fp32
+ * xyxy and scores_dev [n_images, anchors_per_image, n_classes] fp32 = sigmoid(cls) * sigmoid(obj), anchors in the
+ * reference's concatenation order (level, anchor, y, x). Only n_images/n_levels/n_anchors/n_classes of `p` are read. */
+int yb_decode_dense(const yb_nms_params* p, const yb_head_level* levels, float* boxes_dev, float* scores_dev,
+                    void* stream);
 
 /* torchvision.ops.batched_nms on explicit candidates (one image), first `max_keep` survivors in
  * score-descending order (ties: lower index first).  keep_dev [max_keep] int64, n_keep_dev [1]. */

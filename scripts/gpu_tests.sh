@@ -22,6 +22,9 @@ for t in test_conv1x1 test_conv1x1_ragged test_conv3x3 test_conv3x3_crosses test
 done
 run pool 300 python -m pytest tests/test_gpu_pool_upsample.py -q -m gpu -s
 run zoo 300 python -m pytest tests/test_gpu_zoo.py -q -m gpu -s
+run p6 300 python -m pytest tests/test_p6.py -q -m gpu -s
+run ingest 300 python -m pytest tests/test_gpu_ingest.py -q -m gpu -s
+run logits_decoder 300 python -m pytest tests/test_gpu_logits_decoder.py -q -m gpu -s
 run network 240 python -m pytest tests/test_gpu_network.py -q -m gpu -s
 run smoke 300 python __graft_entry__.py smoke
 if [ "$1" != "quick" ]; then

@@ -63,3 +63,29 @@ def test_rejects_bad_inputs():
         tr([torch.rand(1, 3, 8, 8, device=DEV)])
     with pytest.raises(_C.NativeLibraryError):
         tr([torch.rand(3, 8, 8)])   # CPU tensor: no fallback
+
+
+def test_interleaved_hwc_sources_equal_planar():
+    """Decoded image files are HWC in memory (a [3,H,W] view with strides (1, 3W, 3)); the kernel reads them in
+    place (yb_letterbox_strided) and must produce the bits of the planar path."""
+    g = torch.Generator().manual_seed(11)
+    for make in (lambda h, w: torch.randint(0, 256, (h, w, 3), generator=g, dtype=torch.uint8),
+                 lambda h, w: torch.rand(h, w, 3, generator=g)):
+        hwc = [make(70, 101).to(DEV), make(128, 128).to(DEV), make(55, 40).to(DEV), make(300, 211).to(DEV)]
+        views = [t.permute(2, 0, 1) for t in hwc]
+        assert all(_C._is_hwc_view(v) for v in views)
+        planar = [v.contiguous() for v in views]
+        tr = YOLOTransform(128, 128)
+        geoms, (Hb, Wb) = tr.geometry(views)
+        for layout, shape in ((_C.YB_LAYOUT_NCHW, (4, 3, Hb, Wb)), (_C.YB_LAYOUT_S2D16, (4, Hb // 2, Wb // 2, 16))):
+            a = torch.empty(shape, dtype=torch.float16, device=DEV)
+            b = torch.empty(shape, dtype=torch.float16, device=DEV)
+            tr.letterbox_into(views, geoms, Hb, Wb, a, layout)
+            tr.letterbox_into(planar, geoms, Hb, Wb, b, layout)
+            assert torch.equal(a, b)
+        # a mixed list (one planar image) falls back to the planar path for the whole batch
+        mixed = [views[0], planar[1], views[2], views[3]]
+        c = torch.empty((4, 3, Hb, Wb), dtype=torch.float16, device=DEV)
+        tr.letterbox_into(mixed, geoms, Hb, Wb, c, _C.YB_LAYOUT_NCHW)
+        tr.letterbox_into(planar, geoms, Hb, Wb, b := torch.empty_like(c), _C.YB_LAYOUT_NCHW)
+        assert torch.equal(c, b)

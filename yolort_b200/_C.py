@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = (
     "yb_abi_version",
     "yb_letterbox_geometry",
     "yb_letterbox",
+    "yb_letterbox_strided",
     "yb_scale_coords_params",
     "yb_plan_create",
     "yb_plan_run",
@@ -35,6 +36,7 @@ EXPORTED_SYMBOLS = (
     "yb_decode_nms_workspace_bytes",
     "yb_decode_nms_debug_offset",
     "yb_decode_nms",
+    "yb_decode_dense",
     "yb_nms_layout",
     "yb_nms_begin",
     "yb_nms_finish",
@@ -141,6 +143,10 @@ def lib() -> ctypes.CDLL:
         ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.POINTER(LetterboxGeom),
         ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
         ctypes.c_int, ctypes.c_void_p]
+    L.yb_letterbox_strided.argtypes = [
+        ctypes.c_int, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int, ctypes.POINTER(LetterboxGeom),
+        ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+        ctypes.c_int, ctypes.c_void_p]
     L.yb_scale_coords_params.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.POINTER(ctypes.c_float)]
     L.yb_plan_create.argtypes = [ctypes.POINTER(OpDesc), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
@@ -156,6 +162,8 @@ def lib() -> ctypes.CDLL:
         ctypes.POINTER(NmsParams), ctypes.POINTER(HeadLevel), ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_size_t, ctypes.c_void_p]
+    L.yb_decode_dense.argtypes = [ctypes.POINTER(NmsParams), ctypes.POINTER(HeadLevel), ctypes.c_void_p,
+                                  ctypes.c_void_p, ctypes.c_void_p]
     L.yb_nms_layout.argtypes = [ctypes.POINTER(NmsParams), ctypes.POINTER(HeadLevel), ctypes.c_void_p, ctypes.c_size_t,
                                 ctypes.POINTER(NmsLayout)]
     L.yb_nms_begin.argtypes = [ctypes.POINTER(NmsParams), ctypes.POINTER(HeadLevel), ctypes.c_void_p, ctypes.c_void_p,
@@ -232,6 +240,14 @@ def u8_lut(device: torch.device) -> torch.Tensor:
     return t
 
 
+YB_SRC_CHW, YB_SRC_HWC = 0, 1
+
+
+def _is_hwc_view(im: torch.Tensor) -> bool:
+    _, h, w = im.shape
+    return tuple(im.stride()) == (1, 3 * w, 3) and (h > 1 or w > 1)
+
+
 def letterbox(images: List[torch.Tensor], geoms, Hb: int, Wb: int, fill: float, out: torch.Tensor,
               layout: int) -> torch.Tensor:
     n = len(images)
@@ -240,19 +256,24 @@ def letterbox(images: List[torch.Tensor], geoms, Hb: int, Wb: int, fill: float, 
     src_dtype = images[0].dtype
     ptrs = (ctypes.c_void_p * n)()
     keep = []
-    for i, im in enumerate(images):
+    for im in images:
         require_cuda(im, "letterbox")
         if im.dtype != src_dtype:
             raise NativeLibraryError("letterbox: all images of a batch must share a dtype")
         if im.dim() != 3 or im.shape[0] != 3:
             raise ValueError(f"images is expected to be a list of 3d tensors of shape [C, H, W], but got '{im.shape}'.")
-        im = im.contiguous()
+    # [3,H,W] views of interleaved HWC memory (decoded image files) are read in place; anything else goes planar
+    hwc = all(_is_hwc_view(im) for im in images)
+    for i, im in enumerate(images):
+        if not hwc:
+            im = im.contiguous()
         keep.append(im)
         ptrs[i] = im.data_ptr()
     lut = u8_lut(dev) if src_dtype == torch.uint8 else None
-    check(lib().yb_letterbox(n, ptrs, dtype_code(src_dtype), geoms, int(Hb), int(Wb), float(fill),
-                             lut.data_ptr() if lut is not None else None, out.data_ptr(),
-                             dtype_code(out.dtype), int(layout), current_stream_ptr(dev)), "yb_letterbox")
+    check(lib().yb_letterbox_strided(n, ptrs, dtype_code(src_dtype), YB_SRC_HWC if hwc else YB_SRC_CHW, geoms,
+                                     int(Hb), int(Wb), float(fill), lut.data_ptr() if lut is not None else None,
+                                     out.data_ptr(), dtype_code(out.dtype), int(layout), current_stream_ptr(dev)),
+          "yb_letterbox")
     for im in keep:  # the kernel reads the sources asynchronously on this stream
         im.record_stream(torch.cuda.current_stream(dev))
     return out
@@ -359,6 +380,29 @@ def decode_nms_padded(head_outputs: List[torch.Tensor], layout: str, strides: Se
           "yb_decode_nms")
     arena.debug_offset = lib().yb_decode_nms_debug_offset(ctypes.byref(p), levels)
     return boxes, scores, labels, counts, status
+
+
+def decode_dense(head_outputs: List[torch.Tensor], layout: str, strides: Sequence[float],
+                 anchors_px: Sequence[Sequence[float]], num_classes: int):
+    """LogitsDecoder (yolort/relay/logits_decoder.py:26-61): (boxes [N,A,4] xyxy fp32, scores [N,A,nc] fp32) for
+    every anchor, no threshold and no NMS; one launch, no host synchronisation."""
+    t0 = head_outputs[0]
+    require_cuda(t0, "decode_dense")
+    dev = t0.device
+    n_images, n_levels = int(t0.shape[0]), len(head_outputs)
+    n_anchors = len(anchors_px[0]) // 2
+    if n_levels > YB_MAX_LEVELS or n_anchors > YB_MAX_ANCHORS:
+        raise NativeLibraryError("decode_dense: too many levels/anchors")
+    levels = (HeadLevel * n_levels)(*[
+        _level_struct(t, layout, n_anchors, num_classes + 5, strides[i], anchors_px[i])
+        for i, t in enumerate(head_outputs)])
+    total = sum(n_anchors * int(lv.H) * int(lv.W) for lv in levels)
+    boxes = torch.empty((n_images, total, 4), dtype=torch.float32, device=dev)
+    scores = torch.empty((n_images, total, int(num_classes)), dtype=torch.float32, device=dev)
+    p = NmsParams(n_images, n_levels, n_anchors, int(num_classes), 0.0, 0.0, 1, 0, 0)
+    check(lib().yb_decode_dense(ctypes.byref(p), levels, boxes.data_ptr(), scores.data_ptr(), current_stream_ptr(dev)),
+          "yb_decode_dense")
+    return boxes, scores
 
 
 def nms_phase_clocks(device) -> list:

@@ -156,6 +156,42 @@ __global__ void decode_candidates_kernel(const __grid_constant__ DecodeParams p,
   }
 }
 
+// Dense decode without threshold / NMS (yolort/relay/logits_decoder.py:10-61 = _concat_pred_logits +
+// _decode_pred_logits of box_head.py:328-360 for every anchor): one warp per anchor, lane k <-> output k, so the
+// (nc+5) logits are read and the nc scores written as contiguous runs. HBM-bound: 2(nc+5) B in, 4(nc+4) B out.
+template <typename T>
+__global__ void decode_dense_kernel(const __grid_constant__ DecodeParams p, float4* __restrict__ boxes,
+                                    float* __restrict__ scores) {
+  const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long total = static_cast<long long>(p.n_images) * p.anchors_per_image;
+  if (warp >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int img = static_cast<int>(warp / p.anchors_per_image);
+  const int anchor = static_cast<int>(warp - static_cast<long long>(img) * p.anchors_per_image);
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < YB_MAX_LEVELS; ++i)
+    if (i < p.n_levels && anchor >= p.lvl_start[i]) l = i;
+  const yb_head_level& L = p.lvl[l];
+  int r = anchor - p.lvl_start[l];
+  const int x = r % L.W;
+  r /= L.W;
+  const int y = r % L.H;
+  const int a = r / L.H;
+  const long long off = img * L.stride_n + a * L.stride_a + y * L.stride_y + x * L.stride_x;
+  const int K = p.n_classes + 5;
+  float s0 = 0.f;
+  if (lane < K) s0 = sigmoidf_ref(ld_logit<T>(L.logits, off + lane));
+  const float sx = __shfl_sync(0xffffffffu, s0, 0), sy = __shfl_sync(0xffffffffu, s0, 1);
+  const float sw = __shfl_sync(0xffffffffu, s0, 2), sh = __shfl_sync(0xffffffffu, s0, 3);
+  const float obj = __shfl_sync(0xffffffffu, s0, 4);
+  if (lane == 0) boxes[warp] = decode_box(sx, sy, sw, sh, x, y, L.stride_px, L.anchors_px[2 * a], L.anchors_px[2 * a + 1]);
+  float* out = scores + warp * p.n_classes;
+  if (lane >= 5 && lane < K) out[lane - 5] = __fmul_rn(s0, obj);          // box_head.py:357 scores = cls * obj
+  for (int k = 32 + lane; k < K; k += 32)
+    out[k - 5] = __fmul_rn(sigmoidf_ref(ld_logit<T>(L.logits, off + k)), obj);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Per-image sort + greedy sweep
 // ---------------------------------------------------------------------------------------------
@@ -703,6 +739,68 @@ extern "C" int yb_nms_finish(const yb_nms_params* p, const yb_head_level* levels
   rc = ensure_nms_smem(smem);
   if (rc != YB_OK) return rc;
   nms_image_kernel<<<p->n_images, kNmsThreads, smem, stream>>>(np, ws);
+  YB_CHECK_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+namespace yb {
+namespace {
+int fill_decode_params(const yb_nms_params* p, const yb_head_level* levels, DecodeParams& dp, int& dtype) {
+  YB_REQUIRE(p && levels, "decode: null argument");
+  YB_REQUIRE(p->n_images > 0 && p->n_levels > 0 && p->n_levels <= YB_MAX_LEVELS, "decode: n_images/n_levels");
+  YB_REQUIRE(p->n_anchors > 0 && p->n_anchors <= YB_MAX_ANCHORS && p->n_classes > 0, "decode: n_anchors/n_classes");
+  dtype = levels[0].dtype;
+  dp.lvl_start[0] = 0;
+  for (int l = 0; l < YB_MAX_LEVELS; ++l) {
+    if (l < p->n_levels) {
+      YB_REQUIRE(levels[l].dtype == dtype, "decode: all levels must share a dtype");
+      YB_REQUIRE(levels[l].logits != nullptr && levels[l].H > 0 && levels[l].W > 0, "decode: level %d empty", l);
+      dp.lvl[l] = levels[l];
+      dp.lvl_start[l + 1] = dp.lvl_start[l] + p->n_anchors * levels[l].H * levels[l].W;
+    } else {
+      dp.lvl[l] = levels[0];
+      dp.lvl_start[l + 1] = dp.lvl_start[l];
+    }
+  }
+  dp.n_images = p->n_images;
+  dp.n_levels = p->n_levels;
+  dp.n_anchors = p->n_anchors;
+  dp.n_classes = p->n_classes;
+  dp.anchors_per_image = dp.lvl_start[p->n_levels];
+  dp.score_thresh = p->score_thresh;
+  dp.cap_per_image = 0;
+  return YB_OK;
+}
+}  // namespace
+}  // namespace yb
+
+extern "C" int yb_decode_dense(const yb_nms_params* p, const yb_head_level* levels, float* boxes_dev, float* scores_dev,
+                               void* stream_) {
+  using namespace yb;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  YB_REQUIRE(boxes_dev && scores_dev, "decode_dense: null output");
+  DecodeParams dp;
+  int dtype = 0;
+  const int rc = fill_decode_params(p, levels, dp, dtype);
+  if (rc != YB_OK) return rc;
+  const long long total = static_cast<long long>(dp.n_images) * dp.anchors_per_image;
+  YB_REQUIRE(total * 32 / 256 + 1 < (1ll << 31), "decode_dense: too many anchors");
+  const unsigned blocks = static_cast<unsigned>((total * 32 + 255) / 256);
+  float4* b4 = reinterpret_cast<float4*>(boxes_dev);
+  switch (dtype) {
+    case YB_F32:
+      decode_dense_kernel<float><<<blocks, 256, 0, stream>>>(dp, b4, scores_dev);
+      break;
+    case YB_F16:
+      decode_dense_kernel<__half><<<blocks, 256, 0, stream>>>(dp, b4, scores_dev);
+      break;
+    case YB_BF16:
+      decode_dense_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(dp, b4, scores_dev);
+      break;
+    default:
+      set_error("decode_dense: unsupported logits dtype %d", dtype);
+      return YB_ERR_INVALID;
+  }
   YB_CHECK_CUDA(cudaGetLastError());
   return YB_OK;
 }

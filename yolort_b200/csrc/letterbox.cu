@@ -24,6 +24,8 @@ struct ImgGeom {
   const void* src;
   int src_h, src_w, new_h, new_w, top, left;
   float ratio_h, ratio_w;
+  // element strides of the source: planar CHW = (h*w, w, 1); interleaved HWC (what image decoders emit) = (1, 3w, 3)
+  int cs, rs, ps;
 };
 struct BatchGeom {
   ImgGeom img[kMaxImagesPerLaunch];
@@ -73,9 +75,9 @@ __device__ __forceinline__ void sample_rgb(const ImgGeom& g, const float* lut, i
   if (g.new_h == g.src_h && g.new_w == g.src_w) {
     // identity resize (ratios are exactly 1, all interpolation weights exactly 0/1): plain copy, same bits
     const SrcT* base = static_cast<const SrcT*>(g.src);
-    const size_t plane = static_cast<size_t>(g.src_h) * g.src_w, o = static_cast<size_t>(yy) * g.src_w + xx;
+    const size_t o = static_cast<size_t>(yy) * g.rs + static_cast<size_t>(xx) * g.ps;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) rgb[c] = load_src<SrcT>(base + c * plane + o, lut);
+    for (int c = 0; c < 3; ++c) rgb[c] = load_src<SrcT>(base + static_cast<size_t>(c) * g.cs + o, lut);
     return;
   }
   int y0, y1, x0, x1;
@@ -84,19 +86,20 @@ __device__ __forceinline__ void sample_rgb(const ImgGeom& g, const float* lut, i
   src_coord(xx, g.ratio_w, g.src_w, x0, x1, lx);
   const float wy0 = 1.f - ly, wx0 = 1.f - lx;
   const SrcT* base = static_cast<const SrcT*>(g.src);
-  const size_t plane = static_cast<size_t>(g.src_h) * g.src_w;
+  const size_t r0 = static_cast<size_t>(y0) * g.rs, r1 = static_cast<size_t>(y1) * g.rs;
+  const size_t c0 = static_cast<size_t>(x0) * g.ps, c1 = static_cast<size_t>(x1) * g.ps;
   // Taps with zero weight are not fetched (w*p + 0*q == w*p exactly for finite q): an identity resize
   // (the 640x640 headline case) touches one source texel per output pixel instead of four.
   const bool need_x1 = lx != 0.f, need_y1 = ly != 0.f;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const SrcT* p = base + c * plane;
-    const float p00 = load_src<SrcT>(p + static_cast<size_t>(y0) * g.src_w + x0, lut);
-    const float p01 = need_x1 ? load_src<SrcT>(p + static_cast<size_t>(y0) * g.src_w + x1, lut) : p00;
+    const SrcT* p = base + static_cast<size_t>(c) * g.cs;
+    const float p00 = load_src<SrcT>(p + r0 + c0, lut);
+    const float p01 = need_x1 ? load_src<SrcT>(p + r0 + c1, lut) : p00;
     float bot = 0.f;
     if (need_y1) {
-      const float p10 = load_src<SrcT>(p + static_cast<size_t>(y1) * g.src_w + x0, lut);
-      const float p11 = need_x1 ? load_src<SrcT>(p + static_cast<size_t>(y1) * g.src_w + x1, lut) : p10;
+      const float p10 = load_src<SrcT>(p + r1 + c0, lut);
+      const float p11 = need_x1 ? load_src<SrcT>(p + r1 + c1, lut) : p10;
       bot = __fadd_rn(__fmul_rn(wx0, p10), __fmul_rn(lx, p11));
     }
     const float top = __fadd_rn(__fmul_rn(wx0, p00), __fmul_rn(lx, p01));
@@ -282,7 +285,16 @@ extern "C" int yb_scale_coords_params(int Hb, int Wb, int src_h, int src_w, floa
 extern "C" int yb_letterbox(int n, const void* const* src_dev, int src_dtype, const yb_letterbox_geom* geom,
                             int Hb, int Wb, float fill, const float* u8_lut_dev, void* dst_dev,
                             int dst_dtype, int dst_layout, void* stream_) {
+  return yb_letterbox_strided(n, src_dev, src_dtype, YB_SRC_CHW, geom, Hb, Wb, fill, u8_lut_dev, dst_dev, dst_dtype,
+                              dst_layout, stream_);
+}
+
+extern "C" int yb_letterbox_strided(int n, const void* const* src_dev, int src_dtype, int src_layout,
+                                    const yb_letterbox_geom* geom, int Hb, int Wb, float fill,
+                                    const float* u8_lut_dev, void* dst_dev, int dst_dtype, int dst_layout,
+                                    void* stream_) {
   using namespace yb;
+  YB_REQUIRE(src_layout == YB_SRC_CHW || src_layout == YB_SRC_HWC, "letterbox: bad source layout %d", src_layout);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   YB_REQUIRE(n > 0 && src_dev && geom && dst_dev, "letterbox: null/empty arguments");
   YB_REQUIRE(dst_layout == YB_LAYOUT_NCHW || dst_layout == YB_LAYOUT_S2D16, "letterbox: bad layout");
@@ -296,7 +308,10 @@ extern "C" int yb_letterbox(int n, const void* const* src_dev, int src_dtype, co
       const yb_letterbox_geom& g = geom[i0 + j];
       YB_REQUIRE(g.top >= 0 && g.left >= 0 && g.top + g.new_h <= Hb && g.left + g.new_w <= Wb,
                  "letterbox: image %d does not fit the canvas", i0 + j);
-      bg.img[j] = ImgGeom{src_dev[i0 + j], g.src_h, g.src_w, g.new_h, g.new_w, g.top, g.left, g.ratio_h, g.ratio_w};
+      YB_REQUIRE(static_cast<long long>(g.src_h) * g.src_w * 3 < (1ll << 31), "letterbox: image %d too large", i0 + j);
+      const bool hwc = src_layout == YB_SRC_HWC;
+      bg.img[j] = ImgGeom{src_dev[i0 + j], g.src_h, g.src_w, g.new_h, g.new_w, g.top, g.left, g.ratio_h, g.ratio_w,
+                          hwc ? 1 : g.src_h * g.src_w, hwc ? 3 * g.src_w : g.src_w, hwc ? 3 : 1};
     }
     int rc;
     switch (src_dtype) {

@@ -107,6 +107,8 @@ class YOLO(nn.Module):
         """Post-processing parameters baked into a plan's fused head epilogues / NMS arena."""
         pp = self.post_process
         ag = self.anchor_generator
+        if not hasattr(pp, "score_thresh"):
+            raise NotImplementedError(f"{type(pp).__name__} has no thresholded detections; call the model's forward")
         return {"strides": list(pp.strides), "anchors_px": ag.anchors_px(), "n_anchors": ag.num_anchors,
                 "num_classes": self.num_classes, "score_thresh": float(pp.score_thresh),
                 "nms_thresh": float(pp.nms_thresh), "detections_per_img": int(pp.detections_per_img),
@@ -136,7 +138,13 @@ class YOLO(nn.Module):
                                     pc["score_thresh"], pc["nms_thresh"], pc["detections_per_img"], pc["semantics"],
                                     rescale)
 
-    def detect(self, plan, rescale: Optional[Tensor] = None) -> List[Dict[str, Tensor]]:
+    def detect(self, plan, rescale: Optional[Tensor] = None):
+        from ..relay.logits_decoder import LogitsDecoder
+
+        if isinstance(self.post_process, LogitsDecoder):
+            # relay/trt_inference.py:43: post_process=LogitsDecoder(strides) -> dense (boxes, scores), canvas coordinates
+            heads = self.run_plan(plan)
+            return self.post_process.decode_plan_heads(heads, self.anchor_generator.anchors_px(), self.num_classes)
         pc = self.post_config()
         if plan.fused_post is not None:
             boxes, scores, labels, counts, status = self.detect_padded(plan, rescale)

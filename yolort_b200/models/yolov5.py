@@ -159,10 +159,54 @@ class YOLOv5(nn.Module):
         if isinstance(samples, str):
             samples = [samples]
         if isinstance(samples, (list, tuple)) and all(isinstance(s, str) for s in samples):
+            if image_loader == self.default_loader and p.device.type == "cuda":
+                return self._ingest_files(samples, p.device)
             return [place(image_loader(s)) for s in samples]
         raise NotImplementedError(
             f"The type of the sample is {type(samples)}, we currently don't support it now, the "
             "samples should be either a tensor, list of tensors, a image path or list of image paths.")
+
+    # -- file ingest -------------------------------------------------------------
+    _DECODE_THREADS = 8
+
+    def _ingest_files(self, paths: List[str], device: torch.device) -> List[Tensor]:
+        """`predict(paths)` fast path: CPU decode (nvJPEG is third-party; torchvision's decoder releases the GIL, so
+        files decode on a small thread pool), the decoder's interleaved HWC bytes are packed into ONE pinned staging
+        buffer and cross PCIe as a single asynchronous copy; the letterbox kernel reads HWC uint8 in place
+        (`yb_letterbox_strided`), so there is no repacking pass on either side and `/255` stays in the kernel."""
+        if len(paths) > 1:
+            from concurrent.futures import ThreadPoolExecutor
+
+            with ThreadPoolExecutor(max_workers=min(self._DECODE_THREADS, len(paths))) as pool:
+                decoded = list(pool.map(self.default_loader, paths))
+        else:
+            decoded = [self.default_loader(paths[0])]
+        total = sum(t.numel() for t in decoded)
+        slots = self.__dict__.setdefault("_ingest_slots", [None, None])   # double-buffered pinned staging
+        k = self.__dict__.get("_ingest_next", 0)
+        self.__dict__["_ingest_next"] = k ^ 1
+        slot = slots[k]
+        if slot is not None:
+            slot[1].synchronize()            # the previous copy out of this buffer has finished
+        if slot is None or slot[0].numel() < total:
+            slot = [torch.empty((max(total, 1 << 20),), dtype=torch.uint8, pin_memory=True), None]
+        host = slot[0]
+        off = 0
+        for t in decoded:
+            hwc = t.permute(1, 2, 0)          # read_image returns a CHW view of HWC memory: this is contiguous
+            host[off: off + t.numel()].view(hwc.shape).copy_(hwc)
+            off += t.numel()
+        dev = host[:total].to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        slot[1] = ev
+        slots[k] = slot
+        out, off = [], 0
+        for t in decoded:
+            _, h, w = t.shape
+            out.append(dev[off: off + t.numel()].view(h, w, 3).permute(2, 0, 1))
+            off += t.numel()
+        return out
 
     @staticmethod
     def _place_packed(samples, p):
