@@ -91,6 +91,8 @@ int yb_scale_coords_params(int Hb, int Wb, int src_h, int src_w, float* out3);
 
 #define YB_ACT_NONE 0
 #define YB_ACT_SILU 1
+#define YB_ACT_HARDSWISH 2 /* r3.1 Conv (yolort/v5/models/common.py:64)              */
+#define YB_ACT_LEAKY01 3   /* r3.1 BottleneckCSP: LeakyReLU(0.1) after the concat BN (:141-142) */
 
 /* Optional fused post-processing of a detection-head convolution (yolort/models/box_head.py:68-82 followed by
  * :328-360,418): instead of storing the logits, the epilogue applies sigmoid / anchor decode / multi-label

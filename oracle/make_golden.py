@@ -29,7 +29,8 @@ def synth_state_dict(shapes: dict, knob_obj: float = 0.0, knob_cls: float = 0.0,
         g = torch.Generator().manual_seed((zlib.crc32(k.encode()) + 7919 * seed) & 0x7FFFFFFF)
         if k.endswith("num_batches_tracked"):
             t = torch.zeros(shp, dtype=torch.int64)
-        elif k.endswith("conv.weight") or (k.startswith("model.head") and k.endswith(".weight")):
+        elif k.endswith("conv.weight") or (k.startswith("model.head") and k.endswith(".weight")) or \
+                (len(shp) == 4 and k.endswith(".weight")):      # bare cv2 / cv3 of the r3.1 BottleneckCSP
             fan_in = shp[1] * shp[2] * shp[3]
             t = torch.randn(shp, generator=g) * (gain / fan_in) ** 0.5
         elif k.endswith("bn.weight") or k.endswith("running_var"):

@@ -17,12 +17,13 @@ for m in 0 2; do
   run conv_patch_mode$m 240 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "test_patch_conv_view_modes and ${m}]"
 done
 run conv_patch_misc 240 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "test_patch_conv_ragged or test_patch_conv_matches"
-for t in test_conv1x1 test_conv1x1_ragged test_conv3x3 test_conv3x3_crosses test_bottleneck test_head_conv test_wide_output test_bf16 test_large_m test_rejects; do
+for t in test_conv1x1 test_conv1x1_ragged test_conv3x3 test_conv3x3_crosses test_bottleneck test_head_conv test_wide_output test_bf16 test_large_m test_rejects test_r31_activations; do
   run conv_$t 240 python -m pytest tests/test_gpu_conv.py -q -m gpu -s -k "$t"
 done
 run pool 300 python -m pytest tests/test_gpu_pool_upsample.py -q -m gpu -s
 run zoo 300 python -m pytest tests/test_gpu_zoo.py -q -m gpu -s
 run p6 300 python -m pytest tests/test_p6.py -q -m gpu -s
+run v4 300 python -m pytest tests/test_v4.py -q -m gpu -s
 run ingest 300 python -m pytest tests/test_gpu_ingest.py -q -m gpu -s
 run logits_decoder 300 python -m pytest tests/test_gpu_logits_decoder.py -q -m gpu -s
 run network 240 python -m pytest tests/test_gpu_network.py -q -m gpu -s

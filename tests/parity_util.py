@@ -12,7 +12,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def layouts():
     out = {}
-    for fn in ("state_dict_layouts.json", "state_dict_layouts_p6.json"):
+    for fn in ("state_dict_layouts.json", "state_dict_layouts_p6.json", "state_dict_layouts_v4.json"):
         with open(os.path.join(GOLDEN, fn)) as f:
             out.update(json.load(f))
     return out
@@ -22,6 +22,7 @@ P6_STRIDES = [8, 16, 32, 64]
 P6_ANCHORS = [[19, 27, 44, 40, 38, 94], [96, 68, 86, 152, 180, 137], [140, 301, 303, 264, 238, 542],
               [436, 615, 739, 380, 925, 792]]
 GAIN_N6 = 2.22   # oracle/make_golden_p6.py
+GAINS_V4 = {"s_r40": 2.1, "s_r31": 2.05}   # oracle/make_golden_v4.py
 
 
 def load_npz(name):

@@ -30,7 +30,9 @@ def run_conv(N, H, W, Cin, Cout, k, s, p, dtype=torch.float16, act=True, residua
     d.in_ = x_full.data_ptr() + in_off * 2
     d.Ho, d.Wo, d.Cout, d.out_cstride = Ho, Wo, Cout, out_cs
     d.out = out_full.data_ptr() + out_off * 2
-    d.ksize, d.stride, d.pad, d.act = k, s, p, (_C.YB_ACT_SILU if act else _C.YB_ACT_NONE)
+    act_code = {True: _C.YB_ACT_SILU, False: _C.YB_ACT_NONE, "hardswish": _C.YB_ACT_HARDSWISH,
+                "leaky": _C.YB_ACT_LEAKY01}[act]
+    d.ksize, d.stride, d.pad, d.act = k, s, p, act_code
     d.weight, d.Cin_pad, d.Cout_pad, d.bias = wp.data_ptr(), ci_pad, co_pad, bp.data_ptr()
     if residual:
         d.residual, d.res_cstride = res.data_ptr(), Cout
@@ -39,7 +41,11 @@ def run_conv(N, H, W, Cin, Cout, k, s, p, dtype=torch.float16, act=True, residua
     torch.cuda.synchronize()
     x = x_full[..., in_off:in_off + Cin].float().permute(0, 3, 1, 2)
     ref = F.conv2d(x, w.float().to(DEV), b.to(DEV), s, p)
-    if act:
+    if act == "hardswish":
+        ref = F.hardswish(ref)
+    elif act == "leaky":
+        ref = F.leaky_relu(ref, 0.1)
+    elif act:
         ref = F.silu(ref)
     if residual:
         ref = ref + res.float().permute(0, 3, 1, 2)
@@ -133,3 +139,11 @@ def test_patch_conv_matches_im2col_kernel(monkeypatch):
     run_conv(2, 32, 32, 64, 64, 3, 1, 1, seed=11)
     monkeypatch.delenv("YB_DISABLE_PATCH_CONV")
     run_conv(2, 32, 32, 64, 64, 3, 1, 1, seed=11)
+
+
+@pytest.mark.parametrize("act", ["hardswish", "leaky"])
+def test_r31_activations(act):
+    """Hardswish (r3.1 Conv) and LeakyReLU(0.1) (BottleneckCSP) epilogues, on both kernels (1x1 generic, 3x3 patch)."""
+    run_conv(2, 24, 40, 64, 64, 1, 1, 0, act=act, bias_scale=2.0)
+    run_conv(2, 32, 32, 32, 64, 3, 1, 1, act=act, residual=(act == "hardswish"), bias_scale=2.0)
+    run_conv(1, 20, 28, 48, 96, 3, 2, 1, act=act, dtype=torch.bfloat16)

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libyolort_b200.so")
 YB_U8, YB_F16, YB_BF16, YB_F32 = 0, 1, 2, 3
 YB_LAYOUT_NCHW, YB_LAYOUT_S2D16 = 0, 1
 YB_OP_CONV, YB_OP_SPP_POOL, YB_OP_UPSAMPLE2X = 0, 1, 2
-YB_ACT_NONE, YB_ACT_SILU = 0, 1
+YB_ACT_NONE, YB_ACT_SILU, YB_ACT_HARDSWISH, YB_ACT_LEAKY01 = 0, 1, 2, 3
 YB_MAX_LEVELS, YB_MAX_ANCHORS = 4, 4
 NMS_TV_AUTO, NMS_EXACT_PER_CLASS, NMS_OFFSET_TRICK = 0, 1, 2
 

@@ -25,6 +25,11 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // SiLU(v) = v / (1 + 2^(-v*log2 e)); both transcendental steps on the MUFU pipe.
 __device__ __forceinline__ float silu(float v) { return v * rcp_approx(1.0f + ex2_approx(v * -1.4426950408889634f)); }
 
+// r3.1 graphs (yolort/v5/models/common.py:64 nn.Hardswish, :142 nn.LeakyReLU(0.1)), ATen's formulas:
+// hardswish(x) = x * min(max(x + 3, 0), 6) / 6 ; leaky_relu(x) = x > 0 ? x : x * 0.1
+__device__ __forceinline__ float hardswish(float v) { return __fdiv_rn(__fmul_rn(v, fminf(fmaxf(v + 3.0f, 0.f), 6.0f)), 6.0f); }
+__device__ __forceinline__ float leaky01(float v) { return v > 0.f ? v : __fmul_rn(v, 0.1f); }
+
 template <bool kBf16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
   if constexpr (kBf16) {
@@ -54,6 +59,8 @@ __device__ __forceinline__ void finish16(const EpilogueParams& p, const uint32_t
   for (int j = 0; j < 16; ++j) {
     v[j] = __uint_as_float(acc[j]) + s_bias[j];
     if (p.act == YB_ACT_SILU) v[j] = silu(v[j]);
+    else if (p.act == YB_ACT_HARDSWISH) v[j] = hardswish(v[j]);
+    else if (p.act == YB_ACT_LEAKY01) v[j] = leaky01(v[j]);
   }
   if (p.residual != nullptr && row_ok && col < p.Cout) {
     const uint4* r = reinterpret_cast<const uint4*>(
@@ -140,6 +147,12 @@ __device__ __forceinline__ void epilogue_box(const EpilogueParams& p, uint32_t t
         v[j] = fmaf(h0, t.x, h0);
         v[j + 1] = fmaf(h1, t.y, h1);
       }
+    } else if (p.act == YB_ACT_HARDSWISH) {
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) v[j] = v[j] * fminf(fmaxf(v[j] + 3.0f, 0.f), 6.0f) * (1.0f / 6.0f);
+    } else if (p.act == YB_ACT_LEAKY01) {
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * 0.1f;
     }
     if (has_res) {
 #pragma unroll

@@ -23,7 +23,7 @@ import torch
 from torch import nn
 
 from . import _C
-from .models.common import C3, Bottleneck, Conv, SPP
+from .models.common import C3, Bottleneck, BottleneckCSP, Conv, Focus, SPP
 
 
 def _round_up(v: int, m: int) -> int:
@@ -74,6 +74,29 @@ def fold_conv_bn(m: Conv) -> Tuple[torch.Tensor, torch.Tensor]:
     scale = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
     shift = bn.bias.detach().double().cpu() - bn.running_mean.detach().double().cpu() * scale
     return w * scale.view(-1, 1, 1, 1), shift
+
+
+def act_code(act: nn.Module) -> int:
+    if isinstance(act, nn.SiLU):
+        return _C.YB_ACT_SILU
+    if isinstance(act, nn.Hardswish):
+        return _C.YB_ACT_HARDSWISH
+    if isinstance(act, nn.Identity):
+        return _C.YB_ACT_NONE
+    raise NotImplementedError(f"no epilogue for activation {type(act).__name__}")
+
+
+def focus_to_s2d(w: torch.Tensor) -> torch.Tensor:
+    """Focus conv weight [Co,12,3,3] -> [Co,16,3,3] over the plan's space-to-depth input.  focus_transform
+    (common.py:237-240) orders the four parities as (row,col) = (0,0), (1,0), (0,1), (1,1); the plan's input channel
+    is (dy*2+dx)*4 + c with c == 3 a zero channel, so this is a pure channel permutation (stride 1, pad 1 kept)."""
+    co, ci, kh, kw = w.shape
+    assert ci == 12 and (kh, kw) == (3, 3)
+    out = torch.zeros((co, 16, 3, 3), dtype=w.dtype)
+    for g, (dy, dx) in enumerate(((0, 0), (1, 0), (0, 1), (1, 1))):
+        q = (dy * 2 + dx) * 4
+        out[:, q:q + 3] = w[:, 3 * g:3 * g + 3]
+    return out
 
 
 def stem_to_s2d(w: torch.Tensor) -> torch.Tensor:
@@ -154,7 +177,40 @@ class _Lowering:
     def conv_module(self, name, m: Conv, src: _View, dst: _View, residual=None):
         w, b = fold_conv_bn(m)
         k, s, p = m.conv.kernel_size[0], m.conv.stride[0], m.conv.padding[0]
-        self.conv(name, w, b, src, dst, k, s, p, _C.YB_ACT_SILU, residual)
+        self.conv(name, w, b, src, dst, k, s, p, act_code(m.act), residual)
+
+    def block(self, name, m, src: _View, dst: _View):
+        """C3 (r4.0 / r6.0 graphs) or BottleneckCSP (r3.1)."""
+        if isinstance(m, C3):
+            self.c3(name, m, src, dst)
+        elif isinstance(m, BottleneckCSP):
+            self.csp(name, m, src, dst)
+        else:
+            raise NotImplementedError(f"{name}: no lowering for {type(m).__name__}")
+
+    def csp(self, name, m: BottleneckCSP, src: _View, dst: _View):
+        """common.py:144-146: cv4(LeakyReLU(BN(cat(cv3(m(cv1(x))), cv2(x))))).  The BatchNorm over the concat is
+        per channel, so its two halves fold into the bare convolutions cv3 and cv2 (fp64), each followed by the
+        LeakyReLU in its own epilogue; the concat is the channel window the two GEMMs write."""
+        div = src.buf.div
+        c_ = m.cv1.conv.out_channels
+        cat = self.buf(f"{name}.cat", div, 2 * c_)
+        bn = m.bn
+        scale = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
+        shift = bn.bias.detach().double().cpu() - bn.running_mean.detach().double().cpu() * scale
+        y = _View(self.buf(f"{name}.y", div, c_), 0, c_)
+        self.conv_module(f"{name}.cv1", m.cv1, src, y)
+        w2 = m.cv2.weight.detach().double().cpu() * scale[c_:].view(-1, 1, 1, 1)
+        self.conv(f"{name}.cv2+bn", w2, shift[c_:], src, _View(cat, c_, c_), 1, 1, 0, _C.YB_ACT_LEAKY01)
+        for i, blk in enumerate(m.m):
+            t = _View(self.buf(f"{name}.m{i}.t", div, c_), 0, c_)
+            self.conv_module(f"{name}.m.{i}.cv1", blk.cv1, y, t)
+            out = _View(self.buf(f"{name}.m{i}.y", div, c_), 0, c_)
+            self.conv_module(f"{name}.m.{i}.cv2", blk.cv2, t, out, residual=y if blk.add else None)
+            y = out
+        w3 = m.cv3.weight.detach().double().cpu() * scale[:c_].view(-1, 1, 1, 1)
+        self.conv(f"{name}.cv3+bn", w3, shift[:c_], y, _View(cat, 0, c_), 1, 1, 0, _C.YB_ACT_LEAKY01)
+        self.conv_module(f"{name}.cv4", m.cv4, _View(cat, 0, 2 * c_), dst)
 
     def c3(self, name, m: C3, src: _View, dst: _View):
         div = src.buf.div
@@ -201,16 +257,24 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
         raise NotImplementedError("lowering covers the r6.0 topologies: 3 levels, or 4 levels with the P6 block")
 
     x0 = L.buf("input.s2d", 2, 16)
-    stem: Conv = body["0"]
-    if stem.conv.kernel_size != (6, 6) or stem.conv.stride != (2, 2) or stem.conv.padding != (2, 2):
-        raise NotImplementedError("stem must be the r6.0 6x6/s2/p2 convolution")
-    w, b = fold_conv_bn(stem)
+    stem = body["0"]
+    if isinstance(stem, Focus):       # r3.1 / r4.0: Focus = 2x2 space-to-depth + 3x3/s1/p1 conv (darknetv4.py:82)
+        stem = stem.conv
+        if stem.conv.kernel_size != (3, 3) or stem.conv.stride != (1, 1) or stem.conv.padding != (1, 1):
+            raise NotImplementedError("Focus stem must be the 3x3/s1/p1 convolution")
+        w, b = fold_conv_bn(stem)
+        w_s2d = focus_to_s2d(w)
+    else:                             # r6.0: 6x6/s2/p2 conv == 3x3/s1/p1 over the same space-to-depth input
+        if stem.conv.kernel_size != (6, 6) or stem.conv.stride != (2, 2) or stem.conv.padding != (2, 2):
+            raise NotImplementedError("stem must be the r6.0 6x6/s2/p2 convolution")
+        w, b = fold_conv_bn(stem)
+        w_s2d = stem_to_s2d(w)
     t0 = L.buf("body.0", 2, w.shape[0])
     import os
     spk = int(os.environ.get("YB_STEM_PACK", "4"))
-    w_sp, b_sp = stem_superpixel(stem_to_s2d(w), b, spk)
+    w_sp, b_sp = stem_superpixel(w_s2d, b, spk)
     L.conv("body.0(stem: 3x3 over s2d super-pixels)", w_sp, b_sp, _View(x0, 0, 16), _View(t0, 0, w.shape[0]), 3, 1, 1,
-           _C.YB_ACT_SILU, ref_flops_per_pixel=spk * 2 * w.shape[0] * 3 * 36, pack=spk,
+           act_code(stem.act), ref_flops_per_pixel=spk * 2 * w.shape[0] * 3 * 36, pack=spk,
            force_im2col=os.environ.get("YB_STEM_IM2COL", "0") == "1")
 
     # Concat buffers of the neck (path_aggregation_network.py:215-237), level l at stride 8 << l:
@@ -232,11 +296,16 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
             t = L.buf(f"body.{i}", div, co)
             L.conv_module(f"body.{i}", m, cur, _View(t, 0, co))
             cur = _View(t, 0, co)
+        elif isinstance(m, SPP):      # r3.1 / r4.0 keep the SPP as the last body module (darknetv4.py:97)
+            co = m.cv2.conv.out_channels
+            dst = _View(L.buf(f"body.{i}", div, co), 0, co)
+            L.spp(f"body.{i}", m, cur, dst)
+            cur = dst
         else:
-            co = m.cv3.conv.out_channels
+            co = (m.cv3 if isinstance(m, C3) else m.cv4).conv.out_channels
             dst = tap_dst.get(i) or _View(L.buf(f"body.{i}", div, co), 0, co)
             assert dst.C == co
-            L.c3(f"body.{i}", m, cur, dst)
+            L.block(f"body.{i}", m, cur, dst)
             cur = dst
     top = cur
     if has_p6:   # IntermediateLevelP6 (path_aggregation_network.py:34-41): stride-64 level from the last tap
@@ -244,29 +313,32 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
         t = _View(L.buf("pan.p6.conv", 64, ch[3]), 0, ch[3])
         L.conv_module("pan.intermediate_blocks.p6.0", p6m[0], top, t)
         top = _View(L.buf("pan.p6", 64, ch[3]), 0, ch[3])
-        L.c3("pan.intermediate_blocks.p6.1", p6m[1], t, top)
+        L.block("pan.intermediate_blocks.p6.1", p6m[1], t, top)
 
     inner, layer = pan.inner_blocks, pan.layer_blocks
     # descending pass (`:215-222`): idx-th iteration works at level nl-1-idx
     last = _View(L.buf("pan.spp", 8 << (nl - 1), ch[-1]), 0, ch[-1])
-    L.spp("pan.inner_blocks.0", inner[0], top, last)
+    if isinstance(inner[0], SPP):
+        L.spp("pan.inner_blocks.0", inner[0], top, last)
+    else:                             # r3.1 / r4.0: a block without shortcut (path_aggregation_network.py:108-109)
+        L.block("pan.inner_blocks.0", inner[0], top, last)
     for idx in range(nl - 1):
         l = nl - 1 - idx
         if idx > 0:
             u = _View(L.buf(f"pan.u{idx}", 8 << l, ch[l]), 0, ch[l])
-            L.c3(f"pan.inner_blocks.{3 * idx}", inner[3 * idx], _View(cat_dn[l], 0, 2 * ch[l]), u)
+            L.block(f"pan.inner_blocks.{3 * idx}", inner[3 * idx], _View(cat_dn[l], 0, 2 * ch[l]), u)
             last = u
         lat = _View(cat_up[l], ch[l - 1], ch[l - 1])
         L.conv_module(f"pan.inner_blocks.{3 * idx + 1}", inner[3 * idx + 1], last, lat)
         L.upsample(f"pan.inner_blocks.{3 * idx + 2}", lat, _View(cat_dn[l - 1], 0, ch[l - 1]))
     # ascending pass (`:226-237`)
     results = [_View(L.buf("pan.p3", 8, ch[0]), 0, ch[0])]
-    L.c3("pan.layer_blocks.0", layer[0], _View(cat_dn[0], 0, 2 * ch[0]), results[0])
+    L.block("pan.layer_blocks.0", layer[0], _View(cat_dn[0], 0, 2 * ch[0]), results[0])
     for idx in range(nl - 1):
         l = idx + 1
         L.conv_module(f"pan.layer_blocks.{2 * idx + 1}", layer[2 * idx + 1], results[idx], _View(cat_up[l], 0, ch[idx]))
         r = _View(L.buf(f"pan.p{l + 3}", 8 << l, ch[l]), 0, ch[l])
-        L.c3(f"pan.layer_blocks.{2 * idx + 2}", layer[2 * idx + 2], _View(cat_up[l], 0, 2 * ch[idx]), r)
+        L.block(f"pan.layer_blocks.{2 * idx + 2}", layer[2 * idx + 2], _View(cat_up[l], 0, 2 * ch[idx]), r)
         results.append(r)
 
     head_bufs = []

@@ -11,12 +11,16 @@ __all__ = ["YOLO", "YOLOv5", "yolov5n", "yolov5s", "yolov5m", "yolov5l", "yolov5
 def _make(size: str, p6: bool = False):
     def ctor(upstream_version: str = "r6.0", export_friendly: bool = False, **kwargs: Any) -> YOLOv5:
         """Args:
-            upstream_version (str): ultralytics release; only "r6.0" is built here.
+            upstream_version (str): ultralytics release: "r6.0" (default), and "r4.0" / "r3.1" for s, m, l.
             export_friendly (bool): accepted for signature compatibility; there is no export path here
                 (SiLU is evaluated inside the conv epilogue either way).
         """
+        # models/__init__.py:24-110: s/m/l exist for r3.1, r4.0 and r6.0; n, x and the P6 variants only for r6.0
+        allowed = ("r3.1", "r4.0", "r6.0") if (size in "sml" and not p6) else ("r6.0",)
+        if upstream_version not in allowed:
+            raise NotImplementedError(f"yolov5{size}{'6' if p6 else ''} supports upstream versions {allowed}")
         if upstream_version != "r6.0":
-            raise NotImplementedError("Currently only supports r6.0 versions (r4.0/r3.1 are 'next' in SURVEY.md 8f)")
+            return YOLOv5(arch=f"yolov5_darknet_pan_{size}_{upstream_version.replace('.', '')}", **kwargs)
         if p6:   # models/__init__.py:112-166: the P6 constructors letterbox to multiples of 64
             return YOLOv5(arch=f"yolov5_darknet_pan_{size}6_r60", size_divisible=64, **kwargs)
         return YOLOv5(arch=f"yolov5_darknet_pan_{size}_r60", **kwargs)

@@ -87,8 +87,8 @@ def _sequential(model: nn.Module) -> nn.Module:
 
 
 def load_from_ultralytics(checkpoint_path: str, version: str = "r6.0") -> Dict[str, Any]:
-    if version != "r6.0":
-        raise NotImplementedError(f"Currently does not support version: {version} (r4.0/r3.1 are 'next', SURVEY.md 8f)")
+    if version not in ("r3.1", "r4.0", "r6.0"):     # _checkpoint.py:26-30; the module index maps are shared (`:60-64`)
+        raise NotImplementedError(f"Currently does not support version: {version}.")
     up = load_upstream_model(checkpoint_path)
     seq = _sequential(up)
     detect = seq[-1]

@@ -7,6 +7,7 @@ from typing import List, Optional
 from torch import nn
 
 from .common import _PlanOnly
+from .darknetv4 import darknet_v4_features
 from .darknetv6 import darknet_v6_features
 from .path_aggregation_network import PathAggregationNetwork
 
@@ -31,12 +32,15 @@ def darknet_pan_backbone(
     version: str = "r6.0",
     use_p6: bool = False,
 ) -> BackboneWithPAN:
-    if version != "r6.0":
-        raise NotImplementedError("Currently only upstream version 'r6.0' is built (SURVEY.md section 8f lists r4.0/r3.1 as next).")
+    if version not in ("r3.1", "r4.0", "r6.0"):
+        raise NotImplementedError("Currently only supports version 'r3.1', 'r4.0' and 'r6.0'.")
     if pretrained:
         raise ValueError("no backbone checkpoints exist offline")
     last_channel = 768 if use_p6 else 1024
-    body = darknet_v6_features(depth_multiple, width_multiple, last_channel=last_channel)
+    if version == "r6.0":
+        body = darknet_v6_features(depth_multiple, width_multiple, last_channel=last_channel)
+    else:
+        body = darknet_v4_features(depth_multiple, width_multiple, version=version, last_channel=last_channel)
     if returned_layers is None:
         returned_layers = [4, 6, 8]
     grow_widths = [256, 512, 768, 1024] if use_p6 else [256, 512, 1024]

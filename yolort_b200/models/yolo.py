@@ -18,6 +18,12 @@ from .box_head import PostProcess, YOLOHead
 
 __all__ = [
     "YOLO",
+    "yolov5_darknet_pan_s_r31",
+    "yolov5_darknet_pan_m_r31",
+    "yolov5_darknet_pan_l_r31",
+    "yolov5_darknet_pan_s_r40",
+    "yolov5_darknet_pan_m_r40",
+    "yolov5_darknet_pan_l_r40",
     "yolov5_darknet_pan_n_r60",
     "yolov5_darknet_pan_s_r60",
     "yolov5_darknet_pan_m_r60",
@@ -200,21 +206,29 @@ def build_model(backbone_name: str, depth_multiple: float, width_multiple: float
     return model
 
 
-def _factory(size: str, depth: float, width: float, use_p6: bool = False):
+def _factory(size: str, depth: float, width: float, use_p6: bool = False, version: str = "r6.0"):
     six = "6" if use_p6 else ""
+    vtag, vname = version.replace(".", ""), version.replace(".", "_")
 
     def fn(pretrained: bool = False, progress: bool = True, num_classes: int = 80, **kwargs: Any) -> YOLO:
         if use_p6:   # yolo.py:640-661: the *6 factories pin strides and anchor grids
             kwargs = dict(kwargs, strides=P6_STRIDES, anchor_grids=P6_ANCHOR_GRIDS)
-        return build_model(f"darknet_{size}_r6_0", depth, width, "r6.0", f"yolov5_darknet_pan_{size}{six}_r60_coco",
+        return build_model(f"darknet_{size}_{vname}", depth, width, version, f"yolov5_darknet_pan_{size}{six}_{vtag}_coco",
                            pretrained, progress, num_classes, use_p6=use_p6, **kwargs)
 
-    fn.__name__ = f"yolov5_darknet_pan_{size}{six}_r60"
-    fn.__doc__ = (f"yolov5 {size}{six} release 6.0 (depth_multiple={depth}, width_multiple={width}"
+    fn.__name__ = f"yolov5_darknet_pan_{size}{six}_{vtag}"
+    fn.__doc__ = (f"yolov5 {size}{six} release {version[1:]} (depth_multiple={depth}, width_multiple={width}"
                   + (", P6: 4 levels, strides 8..64)." if use_p6 else ")."))
     return fn
 
 
+# r3.1 / r4.0 (Focus stem; BottleneckCSP+Hardswish / C3+SiLU): yolort/models/yolo.py:292-469
+yolov5_darknet_pan_s_r31 = _factory("s", 0.33, 0.5, version="r3.1")
+yolov5_darknet_pan_m_r31 = _factory("m", 0.67, 0.75, version="r3.1")
+yolov5_darknet_pan_l_r31 = _factory("l", 1.0, 1.0, version="r3.1")
+yolov5_darknet_pan_s_r40 = _factory("s", 0.33, 0.5, version="r4.0")
+yolov5_darknet_pan_m_r40 = _factory("m", 0.67, 0.75, version="r4.0")
+yolov5_darknet_pan_l_r40 = _factory("l", 1.0, 1.0, version="r4.0")
 # (depth, width) table: yolort/models/yolo.py:468-619
 yolov5_darknet_pan_n_r60 = _factory("n", 0.33, 0.25)
 yolov5_darknet_pan_s_r60 = _factory("s", 0.33, 0.5)
