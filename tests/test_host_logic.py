@@ -112,7 +112,7 @@ def test_constructor_surface_and_errors():
     assert (m.transform.min_size, m.transform.max_size, m.transform.size_divisible, m.transform.fill_color) == (320, 416, 64, 0.0)
     assert yolov5s().model.post_process.score_thresh == 0.005  # yolo.py:77-79 defaults
     with pytest.raises(NotImplementedError):
-        yolov5s(upstream_version="r4.0")
+        yolov5s(upstream_version="r5.0")
     with pytest.raises(ValueError):
         YOLOv5(arch="nope")
     with pytest.raises(NotImplementedError):
