@@ -25,10 +25,8 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // SiLU(v) = v / (1 + 2^(-v*log2 e)); both transcendental steps on the MUFU pipe.
 __device__ __forceinline__ float silu(float v) { return v * rcp_approx(1.0f + ex2_approx(v * -1.4426950408889634f)); }
 
-// r3.1 graphs (yolort/v5/models/common.py:64 nn.Hardswish, :142 nn.LeakyReLU(0.1)), ATen's formulas:
-// hardswish(x) = x * min(max(x + 3, 0), 6) / 6 ; leaky_relu(x) = x > 0 ? x : x * 0.1
-__device__ __forceinline__ float hardswish(float v) { return __fdiv_rn(__fmul_rn(v, fminf(fmaxf(v + 3.0f, 0.f), 6.0f)), 6.0f); }
-__device__ __forceinline__ float leaky01(float v) { return v > 0.f ? v : __fmul_rn(v, 0.1f); }
+// r3.1 graphs (yolort/v5/models/common.py:64 nn.Hardswish, :142 nn.LeakyReLU(0.1)), ATen's formulas
+// hardswish(x) = x * min(max(x + 3, 0), 6) / 6 ; leaky_relu(x) = x > 0 ? x : x * 0.1 -- see epilogue_box<.., kRareAct>.
 
 template <bool kBf16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -49,42 +47,6 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
   }
 }
 
-// 16 accumulator columns -> bias, activation, residual, convert; result as two 16-byte chunks.
-template <bool kBf16>
-__device__ __forceinline__ void finish16(const EpilogueParams& p, const uint32_t (&acc)[16],
-                                         const float* __restrict__ s_bias, long long row, bool row_ok,
-                                         int col, uint4& o0, uint4& o1) {
-  float v[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    v[j] = __uint_as_float(acc[j]) + s_bias[j];
-    if (p.act == YB_ACT_SILU) v[j] = silu(v[j]);
-    else if (p.act == YB_ACT_HARDSWISH) v[j] = hardswish(v[j]);
-    else if (p.act == YB_ACT_LEAKY01) v[j] = leaky01(v[j]);
-  }
-  if (p.residual != nullptr && row_ok && col < p.Cout) {
-    const uint4* r = reinterpret_cast<const uint4*>(
-        reinterpret_cast<const uint16_t*>(p.residual) + row * p.res_cstride + col);
-    const uint4 r0 = __ldg(r);
-    const uint4 r1 = (col + 8 < p.Cout) ? __ldg(r + 1) : make_uint4(0, 0, 0, 0);
-    const uint32_t ru[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float2 f = unpack2<kBf16>(ru[j]);
-      v[2 * j] += f.x;
-      v[2 * j + 1] += f.y;
-    }
-  }
-  o0.x = pack2<kBf16>(v[0], v[1]);
-  o0.y = pack2<kBf16>(v[2], v[3]);
-  o0.z = pack2<kBf16>(v[4], v[5]);
-  o0.w = pack2<kBf16>(v[6], v[7]);
-  o1.x = pack2<kBf16>(v[8], v[9]);
-  o1.y = pack2<kBf16>(v[10], v[11]);
-  o1.z = pack2<kBf16>(v[12], v[13]);
-  o1.w = pack2<kBf16>(v[14], v[15]);
-}
-
 // Physical 16-byte chunk index of logical chunk `j` in row `r` of a tile whose rows are `row_bytes`
 // long, under the TMA/UMMA swizzle of the same width (address bits [4,7) ^= bits [7,10), truncated).
 __device__ __forceinline__ int swizzle_chunk(int r, int j, int row_bytes) {
@@ -97,7 +59,9 @@ __device__ __forceinline__ int swizzle_chunk(int r, int j, int row_bytes) {
 // One TMA-store box (kCols = 16/32/64 accumulator columns of this thread's output pixel), handled in batches
 // of up to 32 columns: the TMEM loads and residual loads of a batch are issued up front (one exposed latency
 // per 32 columns instead of one per 16), then bias + SiLU (+ residual) + pack and the swizzled smem writes.
-template <bool kBf16, int kCols>
+// kRareAct instantiates the r3.1 activations (Hardswish / LeakyReLU) in a separate copy: with them as extra
+// branches of the common copy the r6.0 plan measured 5% slower (ptxas schedules the SiLU batch differently).
+template <bool kBf16, int kCols, bool kRareAct = false>
 __device__ __forceinline__ void epilogue_box(const EpilogueParams& p, uint32_t taddr, const float* __restrict__ s_bias,
                                              long long row, bool row_ok, int col0, uint8_t* my_row, int row_in_tile) {
   constexpr int kBatch = kCols < 32 ? kCols : 32;
@@ -132,7 +96,15 @@ __device__ __forceinline__ void epilogue_box(const EpilogueParams& p, uint32_t t
       v[j + 2] = __uint_as_float(acc[j >> 4][(j & 15) + 2]) + b4.z;
       v[j + 3] = __uint_as_float(acc[j >> 4][(j & 15) + 3]) + b4.w;
     }
-    if (p.act == YB_ACT_SILU) {
+    if constexpr (kRareAct) {
+      if (p.act == YB_ACT_HARDSWISH) {
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) v[j] = v[j] * fminf(fmaxf(v[j] + 3.0f, 0.f), 6.0f) * (1.0f / 6.0f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * 0.1f;
+      }
+    } else if (p.act == YB_ACT_SILU) {
       // SiLU(v) = h + h*tanh(h), h = v/2.  tanh.approx.f16x2 evaluates two elements per MUFU op (0.5 op per
       // element instead of the 2 of exp+rcp, which made 1x1 layers MUFU-bound: 16 ops/clk/SM).  Its ~2^-11
       // absolute error is below the fp16 rounding of the stored activation for |v| < ~4 (measured network
@@ -147,12 +119,6 @@ __device__ __forceinline__ void epilogue_box(const EpilogueParams& p, uint32_t t
         v[j] = fmaf(h0, t.x, h0);
         v[j + 1] = fmaf(h1, t.y, h1);
       }
-    } else if (p.act == YB_ACT_HARDSWISH) {
-#pragma unroll
-      for (int j = 0; j < kBatch; ++j) v[j] = v[j] * fminf(fmaxf(v[j] + 3.0f, 0.f), 6.0f) * (1.0f / 6.0f);
-    } else if (p.act == YB_ACT_LEAKY01) {
-#pragma unroll
-      for (int j = 0; j < kBatch; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * 0.1f;
     }
     if (has_res) {
 #pragma unroll
@@ -190,6 +156,15 @@ template <bool kBf16>
 __device__ __forceinline__ void epilogue_box_dispatch(const EpilogueParams& p, int store_cols, uint32_t taddr,
                                                       const float* s_bias, long long row, bool row_ok, int col0,
                                                       uint8_t* my_row, int row_in_tile) {
+  if (p.act >= YB_ACT_HARDSWISH) {
+    if (store_cols == 64)
+      epilogue_box<kBf16, 64, true>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
+    else if (store_cols == 32)
+      epilogue_box<kBf16, 32, true>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
+    else
+      epilogue_box<kBf16, 16, true>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
+    return;
+  }
   if (store_cols == 64)
     epilogue_box<kBf16, 64>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
   else if (store_cols == 32)

@@ -24,8 +24,15 @@ struct ImgGeom {
   const void* src;
   int src_h, src_w, new_h, new_w, top, left;
   float ratio_h, ratio_w;
-  // element strides of the source: planar CHW = (h*w, w, 1); interleaved HWC (what image decoders emit) = (1, 3w, 3)
-  int cs, rs, ps;
+};
+// Element strides (channel, row, pixel) of the source: planar CHW = (h*w, w, 1); interleaved HWC (what image
+// decoders emit) = (1, 3w, 3).  A template parameter, so the planar path keeps its constant-stride addressing.
+template <bool kHwc>
+struct SrcStrides {
+  size_t cs, rs, ps;
+  __device__ __forceinline__ explicit SrcStrides(const ImgGeom& g)
+      : cs(kHwc ? 1 : static_cast<size_t>(g.src_h) * g.src_w), rs(kHwc ? 3 * static_cast<size_t>(g.src_w) : g.src_w),
+        ps(kHwc ? 3 : 1) {}
 };
 struct BatchGeom {
   ImgGeom img[kMaxImagesPerLaunch];
@@ -64,7 +71,7 @@ __device__ __forceinline__ void src_coord(int dst, float ratio, int size, int& i
   l1 = lam;
 }
 
-template <typename SrcT>
+template <typename SrcT, bool kHwc>
 __device__ __forceinline__ void sample_rgb(const ImgGeom& g, const float* lut, int y, int x, float fill,
                                            float (&rgb)[3]) {
   const int yy = y - g.top, xx = x - g.left;
@@ -72,12 +79,13 @@ __device__ __forceinline__ void sample_rgb(const ImgGeom& g, const float* lut, i
     rgb[0] = rgb[1] = rgb[2] = fill;
     return;
   }
+  const SrcStrides<kHwc> st(g);
   if (g.new_h == g.src_h && g.new_w == g.src_w) {
     // identity resize (ratios are exactly 1, all interpolation weights exactly 0/1): plain copy, same bits
     const SrcT* base = static_cast<const SrcT*>(g.src);
-    const size_t o = static_cast<size_t>(yy) * g.rs + static_cast<size_t>(xx) * g.ps;
+    const size_t o = static_cast<size_t>(yy) * st.rs + static_cast<size_t>(xx) * st.ps;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) rgb[c] = load_src<SrcT>(base + static_cast<size_t>(c) * g.cs + o, lut);
+    for (int c = 0; c < 3; ++c) rgb[c] = load_src<SrcT>(base + static_cast<size_t>(c) * st.cs + o, lut);
     return;
   }
   int y0, y1, x0, x1;
@@ -86,14 +94,14 @@ __device__ __forceinline__ void sample_rgb(const ImgGeom& g, const float* lut, i
   src_coord(xx, g.ratio_w, g.src_w, x0, x1, lx);
   const float wy0 = 1.f - ly, wx0 = 1.f - lx;
   const SrcT* base = static_cast<const SrcT*>(g.src);
-  const size_t r0 = static_cast<size_t>(y0) * g.rs, r1 = static_cast<size_t>(y1) * g.rs;
-  const size_t c0 = static_cast<size_t>(x0) * g.ps, c1 = static_cast<size_t>(x1) * g.ps;
+  const size_t r0 = static_cast<size_t>(y0) * st.rs, r1 = static_cast<size_t>(y1) * st.rs;
+  const size_t c0 = static_cast<size_t>(x0) * st.ps, c1 = static_cast<size_t>(x1) * st.ps;
   // Taps with zero weight are not fetched (w*p + 0*q == w*p exactly for finite q): an identity resize
   // (the 640x640 headline case) touches one source texel per output pixel instead of four.
   const bool need_x1 = lx != 0.f, need_y1 = ly != 0.f;
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
-    const SrcT* p = base + static_cast<size_t>(c) * g.cs;
+    const SrcT* p = base + static_cast<size_t>(c) * st.cs;
     const float p00 = load_src<SrcT>(p + r0 + c0, lut);
     const float p01 = need_x1 ? load_src<SrcT>(p + r0 + c1, lut) : p00;
     float bot = 0.f;
@@ -123,7 +131,7 @@ __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) {
 }
 
 // NCHW destination (reference layout): thread per (y, x), three planes.
-template <typename SrcT, typename DstT>
+template <typename SrcT, typename DstT, bool kHwc>
 __global__ void letterbox_nchw_kernel(const __grid_constant__ BatchGeom bg, int img0, int Hb, int Wb,
                                       float fill, const float* lut, DstT* __restrict__ dst) {
   __shared__ float s_lut[256];
@@ -137,7 +145,7 @@ __global__ void letterbox_nchw_kernel(const __grid_constant__ BatchGeom bg, int 
   const int li = blockIdx.z;
   if (x >= Wb) return;
   float rgb[3];
-  sample_rgb<SrcT>(bg.img[li], lut, y, x, fill, rgb);
+  sample_rgb<SrcT, kHwc>(bg.img[li], lut, y, x, fill, rgb);
   const size_t plane = static_cast<size_t>(Hb) * Wb;
   DstT* o = dst + static_cast<size_t>(img0 + li) * 3 * plane + static_cast<size_t>(y) * Wb + x;
 #pragma unroll
@@ -145,7 +153,7 @@ __global__ void letterbox_nchw_kernel(const __grid_constant__ BatchGeom bg, int 
 }
 
 // Space-to-depth NHWC destination [N, Hb/2, Wb/2, 16]: thread per 2x2 pixel block, one 32-byte store.
-template <typename SrcT, typename DstT>
+template <typename SrcT, typename DstT, bool kHwc>
 __global__ void letterbox_s2d_kernel(const __grid_constant__ BatchGeom bg, int img0, int Hb, int Wb,
                                      float fill, const float* lut, DstT* __restrict__ dst) {
   __shared__ float s_lut[256];
@@ -165,7 +173,7 @@ __global__ void letterbox_s2d_kernel(const __grid_constant__ BatchGeom bg, int i
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
         float rgb[3];
-        sample_rgb<SrcT>(bg.img[li], lut, 2 * Y + dy, 2 * X + dx, fill, rgb);
+        sample_rgb<SrcT, kHwc>(bg.img[li], lut, 2 * Y + dy, 2 * X + dx, fill, rgb);
         const int q = (dy * 2 + dx) * 4;
         v[q + 0] = cvt_out<DstT>(rgb[0]);
         v[q + 1] = cvt_out<DstT>(rgb[1]);
@@ -179,34 +187,34 @@ __global__ void letterbox_s2d_kernel(const __grid_constant__ BatchGeom bg, int i
   }
 }
 
-template <typename SrcT, typename DstT>
+template <typename SrcT, typename DstT, bool kHwc>
 int launch_typed(const BatchGeom& bg, int img0, int count, int Hb, int Wb, float fill, const float* lut,
                  void* dst, int layout, cudaStream_t stream) {
   const int threads = 128;
   if (layout == YB_LAYOUT_NCHW) {
     dim3 grid((Wb + threads - 1) / threads, Hb, count);
-    letterbox_nchw_kernel<SrcT, DstT><<<grid, threads, 0, stream>>>(bg, img0, Hb, Wb, fill, lut,
+    letterbox_nchw_kernel<SrcT, DstT, kHwc><<<grid, threads, 0, stream>>>(bg, img0, Hb, Wb, fill, lut,
                                                                     static_cast<DstT*>(dst));
   } else {
     dim3 grid((Wb / 2 + threads - 1) / threads, (Hb / 2 + kRowsPerBlock - 1) / kRowsPerBlock, count);
-    letterbox_s2d_kernel<SrcT, DstT><<<grid, threads, 0, stream>>>(bg, img0, Hb, Wb, fill, lut,
+    letterbox_s2d_kernel<SrcT, DstT, kHwc><<<grid, threads, 0, stream>>>(bg, img0, Hb, Wb, fill, lut,
                                                                    static_cast<DstT*>(dst));
   }
   YB_CHECK_CUDA(cudaGetLastError());
   return YB_OK;
 }
 
-template <typename SrcT>
+template <typename SrcT, bool kHwc>
 int launch_src(const BatchGeom& bg, int img0, int count, int Hb, int Wb, float fill, const float* lut,
                void* dst, int dst_dtype, int layout, cudaStream_t stream) {
   switch (dst_dtype) {
     case YB_F32:
       if (layout == YB_LAYOUT_S2D16) break;
-      return launch_typed<SrcT, float>(bg, img0, count, Hb, Wb, fill, lut, dst, layout, stream);
+      return launch_typed<SrcT, float, kHwc>(bg, img0, count, Hb, Wb, fill, lut, dst, layout, stream);
     case YB_F16:
-      return launch_typed<SrcT, __half>(bg, img0, count, Hb, Wb, fill, lut, dst, layout, stream);
+      return launch_typed<SrcT, __half, kHwc>(bg, img0, count, Hb, Wb, fill, lut, dst, layout, stream);
     case YB_BF16:
-      return launch_typed<SrcT, __nv_bfloat16>(bg, img0, count, Hb, Wb, fill, lut, dst, layout, stream);
+      return launch_typed<SrcT, __nv_bfloat16, kHwc>(bg, img0, count, Hb, Wb, fill, lut, dst, layout, stream);
     default:
       break;
   }
@@ -309,23 +317,26 @@ extern "C" int yb_letterbox_strided(int n, const void* const* src_dev, int src_d
       YB_REQUIRE(g.top >= 0 && g.left >= 0 && g.top + g.new_h <= Hb && g.left + g.new_w <= Wb,
                  "letterbox: image %d does not fit the canvas", i0 + j);
       YB_REQUIRE(static_cast<long long>(g.src_h) * g.src_w * 3 < (1ll << 31), "letterbox: image %d too large", i0 + j);
-      const bool hwc = src_layout == YB_SRC_HWC;
-      bg.img[j] = ImgGeom{src_dev[i0 + j], g.src_h, g.src_w, g.new_h, g.new_w, g.top, g.left, g.ratio_h, g.ratio_w,
-                          hwc ? 1 : g.src_h * g.src_w, hwc ? 3 * g.src_w : g.src_w, hwc ? 3 : 1};
+      bg.img[j] = ImgGeom{src_dev[i0 + j], g.src_h, g.src_w, g.new_h, g.new_w, g.top, g.left, g.ratio_h, g.ratio_w};
     }
     int rc;
+    const bool hwc = src_layout == YB_SRC_HWC;
     switch (src_dtype) {
       case YB_U8:
-        rc = launch_src<uint8_t>(bg, i0, count, Hb, Wb, fill, u8_lut_dev, dst_dev, dst_dtype, dst_layout, stream);
+        rc = hwc ? launch_src<uint8_t, true>(bg, i0, count, Hb, Wb, fill, u8_lut_dev, dst_dev, dst_dtype, dst_layout, stream)
+                 : launch_src<uint8_t, false>(bg, i0, count, Hb, Wb, fill, u8_lut_dev, dst_dev, dst_dtype, dst_layout, stream);
         break;
       case YB_F32:
-        rc = launch_src<float>(bg, i0, count, Hb, Wb, fill, u8_lut_dev, dst_dev, dst_dtype, dst_layout, stream);
+        rc = hwc ? launch_src<float, true>(bg, i0, count, Hb, Wb, fill, u8_lut_dev, dst_dev, dst_dtype, dst_layout, stream)
+                 : launch_src<float, false>(bg, i0, count, Hb, Wb, fill, u8_lut_dev, dst_dev, dst_dtype, dst_layout, stream);
         break;
       case YB_F16:
-        rc = launch_src<__half>(bg, i0, count, Hb, Wb, fill, u8_lut_dev, dst_dev, dst_dtype, dst_layout, stream);
+        rc = hwc ? launch_src<__half, true>(bg, i0, count, Hb, Wb, fill, u8_lut_dev, dst_dev, dst_dtype, dst_layout, stream)
+                 : launch_src<__half, false>(bg, i0, count, Hb, Wb, fill, u8_lut_dev, dst_dev, dst_dtype, dst_layout, stream);
         break;
       case YB_BF16:
-        rc = launch_src<__nv_bfloat16>(bg, i0, count, Hb, Wb, fill, u8_lut_dev, dst_dev, dst_dtype, dst_layout, stream);
+        rc = hwc ? launch_src<__nv_bfloat16, true>(bg, i0, count, Hb, Wb, fill, u8_lut_dev, dst_dev, dst_dtype, dst_layout, stream)
+                 : launch_src<__nv_bfloat16, false>(bg, i0, count, Hb, Wb, fill, u8_lut_dev, dst_dev, dst_dtype, dst_layout, stream);
         break;
       default:
         set_error("letterbox: unsupported source dtype %d", src_dtype);
