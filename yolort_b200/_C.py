@@ -11,7 +11,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libyolort_b200.so")
+# YB_LIB_PATH: A/B timing of alternative builds of the same ABI (scripts/ab_step.sh); never set in product use
+LIB_PATH = os.environ.get("YB_LIB_PATH") or os.path.join(_HERE, "libyolort_b200.so")
 
 YB_U8, YB_F16, YB_BF16, YB_F32 = 0, 1, 2, 3
 YB_LAYOUT_NCHW, YB_LAYOUT_S2D16 = 0, 1
