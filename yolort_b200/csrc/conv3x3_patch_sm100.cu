@@ -82,6 +82,7 @@ __device__ __forceinline__ uint64_t make_view_desc(uint32_t addr, uint32_t row_b
   return d;
 }
 
+template <bool kBf16, int kStoreCols, bool kRareAct>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_out, const PatchParams p) {
@@ -330,7 +331,8 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const int row_in_tile = q * 32 + lane;     // j = r*8 + x  (r: output row in tile, x: column in tile)
     const bool issuer = (gtid == 0);
     const uint32_t bar_id = 1 + g;
-    const int row_bytes = p.store_cols * 2;
+    const int store_cols = kStoreCols != 0 ? kStoreCols : p.store_cols;
+    const int row_bytes = store_cols * 2;
     uint8_t* my_staging = staging + static_cast<size_t>(g) * p.store_bufs * kStageBufBytes;
     float* bias_s = s_bias[g];
     int lt = 0, store_idx = 0;
@@ -358,18 +360,15 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       mbar_wait(&acc_full[g], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * p.block_n;
-      for (int c0 = 0; c0 < p.block_n; c0 += p.store_cols, ++store_idx) {
+      for (int c0 = 0; c0 < p.block_n; c0 += store_cols, ++store_idx) {
         // Two staging buffers, one barrier per box: before the barrier below the issuer waits until the PREVIOUS
         // store has finished reading its buffer, which is the one the next box will overwrite.
         uint8_t* buf = my_staging + (store_idx & 1) * kStageBufBytes;
         uint8_t* my_row = buf + row_in_tile * row_bytes;
         if (!(p.dbg & 1)) {
-          if (p.ep.is_bf16)
-            epilogue_box_dispatch<true>(p.ep, p.store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
-          else
-            epilogue_box_dispatch<false>(p.ep, p.store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
+          epilogue_box_select<kBf16, kStoreCols, kRareAct>(p.ep, store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
         }
-        if (c0 + p.store_cols >= p.block_n) {
+        if (c0 + store_cols >= p.block_n) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[g]);
@@ -396,9 +395,25 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
 }  // namespace
 
+using PatchKernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const PatchParams);
+
+template <bool kBf16>
+PatchKernelFn select_patch_kernel_t(const PatchParams& kp) {
+  if (kp.ep.act >= YB_ACT_HARDSWISH) return conv3x3_patch_kernel<kBf16, 0, true>;
+  switch (kp.store_cols) {
+    case 64: return conv3x3_patch_kernel<kBf16, 64, false>;
+    case 32: return conv3x3_patch_kernel<kBf16, 32, false>;
+    default: return conv3x3_patch_kernel<kBf16, 16, false>;
+  }
+}
+PatchKernelFn select_patch_kernel(const PatchParams& kp) {
+  return kp.ep.is_bf16 ? select_patch_kernel_t<true>(kp) : select_patch_kernel_t<false>(kp);
+}
+
 struct PatchConvOp {
   CUtensorMap tmap_a, tmap_b, tmap_out;
   PatchParams kp;
+  PatchKernelFn fn = nullptr;
   dim3 grid;
   size_t smem_bytes;
 };
@@ -548,16 +563,12 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
       return YB_ERR_CUDA;
     }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(kSmemBudget));
-    if (e != cudaSuccess) {
-      set_error("patch conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-      delete op;
-      return YB_ERR_CUDA;
-    }
-    attr_set = true;
+  op->fn = select_patch_kernel(kp);
+  cudaError_t e = cudaFuncSetAttribute(op->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget));
+  if (e != cudaSuccess) {
+    set_error("patch conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    delete op;
+    return YB_ERR_CUDA;
   }
   *out = op;
   return YB_OK;
@@ -574,7 +585,7 @@ int patch_conv_launch(const PatchConvOp* op, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv3x3_patch_kernel, op->tmap_a, op->tmap_b, op->tmap_out, op->kp));
+  YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, op->fn, op->tmap_a, op->tmap_b, op->tmap_out, op->kp));
   return YB_OK;
 }
 

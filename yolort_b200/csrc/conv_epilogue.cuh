@@ -152,25 +152,30 @@ __device__ __forceinline__ void epilogue_box(const EpilogueParams& p, uint32_t t
   }
 }
 
-template <bool kBf16>
+template <bool kBf16, bool kRareAct>
 __device__ __forceinline__ void epilogue_box_dispatch(const EpilogueParams& p, int store_cols, uint32_t taddr,
                                                       const float* s_bias, long long row, bool row_ok, int col0,
                                                       uint8_t* my_row, int row_in_tile) {
-  if (p.act >= YB_ACT_HARDSWISH) {
-    if (store_cols == 64)
-      epilogue_box<kBf16, 64, true>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
-    else if (store_cols == 32)
-      epilogue_box<kBf16, 32, true>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
-    else
-      epilogue_box<kBf16, 16, true>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
-    return;
-  }
   if (store_cols == 64)
-    epilogue_box<kBf16, 64>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
+    epilogue_box<kBf16, 64, kRareAct>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
   else if (store_cols == 32)
-    epilogue_box<kBf16, 32>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
+    epilogue_box<kBf16, 32, kRareAct>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
   else
-    epilogue_box<kBf16, 16>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
+    epilogue_box<kBf16, 16, kRareAct>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
+}
+
+// Kernel-level specialisation (dtype, TMA-store box width, activation family, fused decode).  Every variant the hot
+// path uses is its own kernel with exactly ONE epilogue copy inlined: with all copies inlined in one kernel and
+// selected at run time, adding the r3.1 activations cost the r6.0 plan 5-13% (measured A/B on the same box,
+// 1.85 -> 1.95 / 2.10 ms); kStoreCols == 0 keeps the run-time selection for the rarely used variants.
+template <bool kBf16, int kStoreCols, bool kRareAct>
+__device__ __forceinline__ void epilogue_box_select(const EpilogueParams& p, int store_cols, uint32_t taddr,
+                                                    const float* s_bias, long long row, bool row_ok, int col0,
+                                                    uint8_t* my_row, int row_in_tile) {
+  if constexpr (kStoreCols != 0)
+    epilogue_box<kBf16, kStoreCols, kRareAct>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
+  else
+    epilogue_box_dispatch<kBf16, kRareAct>(p, store_cols, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
 }
 
 }  // namespace yb

@@ -62,6 +62,7 @@ struct ConvKernelParams {
   yb_head_decode dec;   // copied from the op descriptor
 };
 
+template <bool kBf16, int kStoreCols, bool kRareAct, bool kDecode>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const ConvKernelParams p) {
@@ -217,7 +218,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int row_in_tile = q * 32 + lane;
     const bool issuer = (gtid == 0);
     const uint32_t bar_id = 1 + g;
-    const int row_bytes = p.store_cols * 2;
+    const int store_cols = kStoreCols != 0 ? kStoreCols : p.store_cols;
+    const int row_bytes = store_cols * 2;
     uint8_t* my_staging = staging + static_cast<size_t>(g) * 2 * kStageBufBytes;
     float* bias_s = s_bias[g];
     int lt = 0, store_idx = 0;
@@ -242,7 +244,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_wait(&acc_full[g], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * p.block_n;
-      if (p.decode_on) {
+      if constexpr (kDecode) {
         // ---- fused post-processing front end (yolort/models/box_head.py:328-360,418) ----
         // This thread owns one output pixel: all A*(nc+5) logits of its anchors sit in its TMEM lane.  Per anchor:
         // objectness first (score = cls*obj <= obj, so most anchors stop there), then the classes in 16-column
@@ -345,18 +347,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) mbar_arrive(&acc_empty[g]);
         continue;
       }
-      for (int c0 = 0; c0 < p.block_n; c0 += p.store_cols, ++store_idx) {
+      for (int c0 = 0; c0 < p.block_n; c0 += store_cols, ++store_idx) {
         // Two staging buffers, one barrier per box: before the barrier below the issuer waits until the PREVIOUS
         // store has finished reading its buffer, which is the one the next box will overwrite.
         uint8_t* buf = my_staging + (store_idx & 1) * kStageBufBytes;
         uint8_t* my_row = buf + row_in_tile * row_bytes;
         if (!(p.dbg & 1)) {
-          if (p.ep.is_bf16)
-            epilogue_box_dispatch<true>(p.ep, p.store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
-          else
-            epilogue_box_dispatch<false>(p.ep, p.store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
+          epilogue_box_select<kBf16, kStoreCols, kRareAct>(p.ep, store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
         }
-        if (c0 + p.store_cols >= p.block_n) {
+        if (c0 + store_cols >= p.block_n) {
           // all TMEM reads of this tile are done: hand the accumulator stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -421,10 +420,29 @@ uint32_t pow2_cols(int n) {
 
 }  // namespace
 
+using ConvKernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKernelParams);
+
+// One kernel per (dtype, store-box width) for the SiLU / linear epilogue; the r3.1 activations and the fused decode
+// epilogue are separate kernels that pick the store width at run time (see conv_epilogue.cuh).
+template <bool kBf16>
+ConvKernelFn select_conv_kernel_t(const ConvKernelParams& kp) {
+  if (kp.decode_on) return conv_umma_kernel<kBf16, 0, false, true>;
+  if (kp.ep.act >= YB_ACT_HARDSWISH) return conv_umma_kernel<kBf16, 0, true, false>;
+  switch (kp.store_cols) {
+    case 64: return conv_umma_kernel<kBf16, 64, false, false>;
+    case 32: return conv_umma_kernel<kBf16, 32, false, false>;
+    default: return conv_umma_kernel<kBf16, 16, false, false>;
+  }
+}
+ConvKernelFn select_conv_kernel(const ConvKernelParams& kp) {
+  return kp.ep.is_bf16 ? select_conv_kernel_t<true>(kp) : select_conv_kernel_t<false>(kp);
+}
+
 struct ConvOp {
   PatchConvOp* patch = nullptr;  // non-null: this conv runs on the halo-patch kernel
   CUtensorMap tmap_a, tmap_b, tmap_out;
   ConvKernelParams kp;
+  ConvKernelFn fn = nullptr;
   dim3 grid;
   size_t smem_bytes;
 };
@@ -626,16 +644,12 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
       return YB_ERR_CUDA;
     }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(kSmemBudget));
-    if (e != cudaSuccess) {
-      set_error("conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-      delete op;
-      return YB_ERR_CUDA;
-    }
-    attr_set = true;
+  op->fn = select_conv_kernel(kp);
+  cudaError_t e = cudaFuncSetAttribute(op->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget));
+  if (e != cudaSuccess) {
+    set_error("conv: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    delete op;
+    return YB_ERR_CUDA;
   }
   *out = op;
   return YB_OK;
@@ -653,7 +667,7 @@ int conv_op_launch(const ConvOp* op, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel, op->tmap_a, op->tmap_b, op->tmap_out, op->kp));
+  YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, op->fn, op->tmap_a, op->tmap_b, op->tmap_out, op->kp));
   return YB_OK;
 }
 
