@@ -29,8 +29,11 @@ constexpr int kPatchH = 18, kPatchW = 10;        // TMA box (pixels): the tile p
 constexpr int kMaxA = 4, kMaxB = 12;
 constexpr int kEpiGroups = 2;
 constexpr int kFirstLoadWarp = 3, kLoadWarps = 4;   // cooperative cp.async patch loaders
-constexpr int kFirstEpiWarp = kFirstLoadWarp + kLoadWarps;
-constexpr int kThreads = 32 * kFirstEpiWarp + kEpiGroups * 128;
+// The cp.async loader warps exist only in the kCpAsync kernel variants (YB_PATCH_LOADER=1, measured equal to TMA);
+// the default variants start the epilogue warps right after the three producer / MMA warps: 352 threads instead
+// of 480, which also lifts the per-thread register cap of __launch_bounds__ from 128 to 186.
+constexpr int first_epi_warp(bool cp_async) { return cp_async ? kFirstLoadWarp + kLoadWarps : kFirstLoadWarp; }
+constexpr int block_threads(bool cp_async) { return 32 * first_epi_warp(cp_async) + kEpiGroups * 128; }
 constexpr int kStageBufBytes = 128 * 128;
 constexpr int kMaxBlockN = 256;
 constexpr size_t kSmemBudget = 222 * 1024;
@@ -82,10 +85,11 @@ __device__ __forceinline__ uint64_t make_view_desc(uint32_t addr, uint32_t row_b
   return d;
 }
 
-template <bool kBf16, int kStoreCols, bool kRareAct>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool kBf16, int kStoreCols, bool kRareAct, bool kCpAsync>
+__global__ void __launch_bounds__(block_threads(kCpAsync), 1)
 conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_out, const PatchParams p) {
+  constexpr int kFirstEpiWarp = first_epi_warp(kCpAsync);
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kMaxA], a_empty[kMaxA];
   __shared__ __align__(8) uint64_t b_full[kMaxB], b_empty[kMaxB];
@@ -246,13 +250,13 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         umma_commit(&acc_full[as]);
       }
     }
-  } else if (warp >= kFirstLoadWarp && warp < kFirstEpiWarp) {
+  } else if (kCpAsync && warp >= kFirstLoadWarp && warp < kFirstEpiWarp) {
     // ===================== patch (A) producer, cooperative cp.async variant =====================
     // The TMA unit handles a box row by row (measured ~19 clk per 128-byte row for these 4-D boxes, ~15 clk
     // even for 32-byte rows); 128 threads issuing 16-byte cp.async copies move the same patch several times
     // faster.  Each thread writes its chunks to the swizzled position the UMMA descriptor expects and
     // zero-fills the halo (src-size 0).  Completion: wait_group -> proxy fence -> mbarrier arrive.
-    if (p.a_loader == 1) {
+    if constexpr (kCpAsync) {
       const int ltid = threadIdx.x - 32 * kFirstLoadWarp;
       const int row_bytes = p.block_k * 2;
       const int cpr = row_bytes >> 4;                    // 16-byte chunks per pixel-row
@@ -399,11 +403,12 @@ using PatchKernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUten
 
 template <bool kBf16>
 PatchKernelFn select_patch_kernel_t(const PatchParams& kp) {
-  if (kp.ep.act >= YB_ACT_HARDSWISH) return conv3x3_patch_kernel<kBf16, 0, true>;
+  if (kp.a_loader == 1) return conv3x3_patch_kernel<kBf16, 0, false, true>;   // experiment knob: one generic variant
+  if (kp.ep.act >= YB_ACT_HARDSWISH) return conv3x3_patch_kernel<kBf16, 0, true, false>;
   switch (kp.store_cols) {
-    case 64: return conv3x3_patch_kernel<kBf16, 64, false>;
-    case 32: return conv3x3_patch_kernel<kBf16, 32, false>;
-    default: return conv3x3_patch_kernel<kBf16, 16, false>;
+    case 64: return conv3x3_patch_kernel<kBf16, 64, false, false>;
+    case 32: return conv3x3_patch_kernel<kBf16, 32, false, false>;
+    default: return conv3x3_patch_kernel<kBf16, 16, false, false>;
   }
 }
 PatchKernelFn select_patch_kernel(const PatchParams& kp) {
@@ -503,6 +508,7 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
     const char* e = getenv("YB_PATCH_LOADER");
     kp.a_loader = e ? atoi(e) : 0;
     if (kp.view_mode == 2) kp.a_loader = 0;   // the dx-split layout exists only for the TMA variant
+    if (d.act >= YB_ACT_HARDSWISH) kp.a_loader = 0;   // ... and so do the r3.1 activation variants
   }
   const uint32_t fmt = kp.ep.is_bf16 ? 1u : 0u;
   kp.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(block_n >> 3) << 17) | (8u << 24);
@@ -577,7 +583,7 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
 int patch_conv_launch(const PatchConvOp* op, cudaStream_t stream) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = op->grid;
-  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.blockDim = dim3(block_threads(op->kp.a_loader == 1), 1, 1);
   cfg.dynamicSmemBytes = op->smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
