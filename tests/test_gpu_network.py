@@ -152,3 +152,29 @@ def test_pipelined_host_predict_equals_device_forward(monkeypatch):
     for a, b in zip(got, ref):
         assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["scores"], b["scores"])
         assert torch.equal(a["boxes"], b["boxes"])
+
+
+def test_predict_stream_equals_predict():
+    """The throughput API (copy of batch i+1 overlapping batch i, async result block) returns exactly predict()'s
+    detections, batch after batch, for mixed sizes, changing batch sizes and more batches than ring slots."""
+    m, sd = _model_n()
+    batches = []
+    for b in range(7):
+        n = 1 + (b * 3) % 5
+        ims = [util.synth_image_u8(64 + 8 * ((b + j) % 5), 96 + 16 * ((b * j) % 3), 500 + 10 * b + j) for j in range(n)]
+        pinned = torch.cat([im.reshape(-1) for im in ims]).pin_memory()
+        off, views = 0, []
+        for im in ims:
+            views.append(pinned[off: off + im.numel()].view(im.shape))
+            off += im.numel()
+        batches.append(views)
+    want = [m.predict(b) for b in batches]
+    got = list(m.predict_stream(iter(batches)))
+    assert len(got) == len(want) == 7
+    for gb, wb in zip(got, want):
+        assert len(gb) == len(wb)
+        for g, w in zip(gb, wb):
+            assert not g["boxes"].is_cuda and g["labels"].dtype == torch.int64
+            assert torch.equal(g["labels"], w["labels"].cpu())
+            assert torch.equal(g["scores"], w["scores"].cpu()) and torch.equal(g["boxes"], w["boxes"].cpu())
+    assert list(m.predict_stream(iter([]))) == []
