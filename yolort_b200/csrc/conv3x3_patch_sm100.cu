@@ -4,17 +4,21 @@
 // ingests 9x the tile's input (plus the weights) through the TMA path, and that path saturates at
 // ~18 B/clk/SM (profiles/: 3x3 layers sat at Cin FLOP/B x ~5 TB/s).  Here an output tile is a 16 x 8 pixel
 // block of one image; its (16+2) x (8+2) input halo is fetched by ONE tiled 4-D TMA load per 64-channel
-// chunk (box 18 x 16 pixels, halo zero-filled by the TMA unit), and the nine filter taps are nine
-// *views* of that patch: tap (dy,dx) starts (dy*16 + dx) pixel-rows into the patch, rows of one 8-pixel
-// group are contiguous (one swizzle atom) and consecutive groups are exactly 16 pixel-rows apart, which is
-// precisely what a K-major UMMA shared-memory descriptor expresses (SBO = 16 * row_bytes).
-// Input traffic per tile drops from 9 x 128 to 288 pixel-rows (4x less).
+// chunk (box 18 x 10 pixels, halo zero-filled by the TMA unit), and the nine filter taps are nine
+// *views* of that patch: tap (dy,dx) starts (dy*10 + dx) pixel-rows into the patch, rows of one 8-pixel
+// group are contiguous and consecutive groups are exactly one patch row (10 pixel-rows) apart, which is
+// what a K-major UMMA shared-memory descriptor expresses (SBO = 10 * row_bytes; the swizzle phase follows the
+// absolute shared-memory address, so a view may start inside a swizzle atom as long as base_offset stays 0).
+// Input traffic per tile drops from 9 x 128 to 180 pixel-rows (6.4x less).
 //
 // Same arithmetic as conv_sm100.cu (yolort/v5/models/common.py:42-73,94-116): BN folded, bias + SiLU
 // (+ residual) epilogue, fp32 accumulation in TMEM.
 //
 // Roles (one persistent CTA per SM): warp 0 = patch (A) producer, warp 1 = MMA issuer + TMEM owner,
-// warp 2 = weight (B) producer (unless the weights are resident in shared memory), warps 3-10 = two epilogue groups.
+// warp 2 = weight (B) producer (unless the weights are resident in shared memory), warps 3-10 = two epilogue groups
+// (352 threads).  The kCpAsync variants insert four cooperative cp.async patch-loader warps before the epilogue
+// groups (YB_PATCH_LOADER=1, an experiment measured equal to the TMA loads).  Like conv_sm100.cu the kernel is
+// specialised per (dtype, store-box width, activation family).
 #include <cstdlib>
 
 #include "common.cuh"

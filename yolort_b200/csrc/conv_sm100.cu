@@ -15,12 +15,15 @@
 //                current tile is still being multiplied / drained.
 //   warp 1     : allocates TMEM (two accumulator stages) and issues tcgen05.mma (M=128, N=block_n,
 //                K=16) from one thread; tcgen05.commit releases smem stages and publishes accumulators.
-//   warps 2-9  : two epilogue groups of 4 warps; group g drains accumulator stage g (tiles alternate),
+//   warp 2     : idle (a second MMA-issuer thread was tried here and removed: DESIGN.md section 3)
+//   warps 3-10 : two epilogue groups of 4 warps; group g drains accumulator stage g (tiles alternate),
 //                so one tile's epilogue overlaps the next tile's MMAs and the other group's epilogue.
-//                tcgen05.ld (one output pixel per thread) -> +bias -> SiLU -> (+residual) -> fp16/bf16
+//                tcgen05.ld (one output pixel per thread) -> +bias -> activation -> (+residual) -> fp16/bf16
 //                -> swizzled shared-memory staging -> TMA store into the NHWC destination view (a
 //                channel window of a concat buffer is just a strided tensor map; ragged M is clipped
 //                by the TMA unit).
+// The kernel is a template over (dtype, store-box width, activation family, fused decode): every variant the hot
+// path launches carries exactly one inlined epilogue (conv_epilogue.cuh, select_conv_kernel below).
 #include <cstdlib>
 
 #include "common.cuh"
@@ -35,7 +38,7 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kMaxStages = 12;
 constexpr int kEpiGroups = 2;
-constexpr int kFirstEpiWarp = 3;                     // warp 0: TMA producer, warps 1-2: MMA issuers (one per accumulator stage)
+constexpr int kFirstEpiWarp = 3;                     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warp 2: idle
 constexpr int kThreads = 32 * kFirstEpiWarp + kEpiGroups * 128;
 constexpr int kStageBufBytes = 128 * 128;  // 128 rows x (up to) 64 columns x 2 B
 constexpr int kMaxBlockN = 256;
