@@ -395,17 +395,18 @@ def main():
     # Every step's H2D (39.3 MB from pinned host memory) and D2H (padded detections) is inside the timed region; the
     # API overlaps the copy of batch i+1 with the compute of batch i (two batches in flight).
     e2e_value, e2e_api, d2h, stream_err = e2e_sync_value, "YOLOv5.predict(list of host tensors)", d2h_sync, None
-    try:
+    sync_all()
+    try:   # no collective inside the try: a rank that fails must not leave the others waiting in a barrier
         for _ in model.predict_stream(host_lists[i % NBUF] for i in range(3)):
             pass
-        sync_all()
+        torch.cuda.synchronize(dev)
         n_out = 0
         t0 = time.perf_counter()
         e0.record()
         for dets in model.predict_stream(host_lists[i % NBUF] for i in range(args.steps)):
             n_out += len(dets)
         e1.record()
-        sync_all()
+        torch.cuda.synchronize(dev)
         assert n_out == BATCH * args.steps
         stream_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
     except Exception as exc:   # keep the line: fall back to the synchronous call's number
