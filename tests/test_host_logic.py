@@ -143,3 +143,53 @@ def test_lowering_carries_the_reference_work(name, ctor, gflop, n_convs):
     assert total / 1e9 == pytest.approx(gflop, rel=2e-3)
     assert sum(1 for op in L.ops if op.kind == _C.YB_OP_UPSAMPLE2X) == 2
     assert sum(1 for op in L.ops if op.kind == _C.YB_OP_SPP_POOL) == 1
+
+
+def test_stem_band_weights_reproduce_the_stem_conv():
+    """engine.stem_band (opt-in kBand kernel variant): emulate the kernel's addressing on the CPU -- per output
+    super-pixel and filter row, the 6 pixels x 16 channels that are contiguous in the patch (96 B into the left
+    neighbour) times the banded weights -- and compare with the plain 3x3/s1/p1 conv over the space-to-depth input."""
+    import torch.nn.functional as F
+
+    from yolort_b200.engine import stem_band, stem_superpixel
+
+    g = torch.Generator().manual_seed(0)
+    co, H, W = 8, 6, 16
+    x = torch.randn(2, 16, H, W, generator=g, dtype=torch.float64)
+    w = torch.randn(co, 16, 3, 3, generator=g, dtype=torch.float64)
+    b = torch.randn(co, generator=g, dtype=torch.float64)
+    want = F.conv2d(x, w, b, padding=1)                                   # [2, co, H, W]
+    wb, bb = stem_band(w, b)
+    assert tuple(wb.shape) == (4 * co, 3, 128) and torch.all(wb[:, :, 96:] == 0)
+    # patch memory order: NHWC rows of super-pixels (4 pixels x 16 channels = 64 values), zero halo all around
+    xs = x.permute(0, 2, 3, 1).reshape(2, H, W // 4, 64)
+    padded = torch.zeros(2, H + 2, W // 4 + 2, 64, dtype=torch.float64)
+    padded[:, 1:-1, 1:-1] = xs
+    flat = padded.reshape(2, H + 2, -1)                                    # one patch row = consecutive super-pixels
+    got = torch.zeros(2, H, W // 4, 4 * co, dtype=torch.float64)
+    for h in range(H):
+        for X in range(W // 4):
+            acc = bb.clone()
+            for ky in range(3):
+                start = X * 64 + 48                                        # 96 bytes (48 fp16) into the LEFT neighbour
+                span = flat[:, h + ky, start:start + 96]                   # 6 pixels x 16 channels, contiguous
+                acc = acc + span @ wb[:, ky, :96].T
+            got[:, h, X] = acc
+    got = got.reshape(2, H, W // 4, 4, co).reshape(2, H, W, co).permute(0, 3, 1, 2)
+    torch.testing.assert_close(got, want, rtol=1e-12, atol=1e-12)
+    # and it is the same linear map as the dense super-pixel matrix the default path uses
+    w_sp, b_sp = stem_superpixel(w, b, 4)
+    dense = F.conv2d(xs.permute(0, 3, 1, 2), w_sp, b_sp, padding=1)        # [2, 4co, H, W/4]
+    torch.testing.assert_close(dense.permute(0, 2, 3, 1).reshape(2, H, W // 4, 4, co).reshape(2, H, W, co).permute(0, 3, 1, 2),
+                               want, rtol=1e-12, atol=1e-12)
+
+
+def test_stem_band_is_opt_in(monkeypatch):
+    from yolort_b200.engine import lower_yolo
+
+    m = yolov5s().eval()
+    L, *_ = lower_yolo(m.model, torch.float16, torch.device("cpu"))
+    assert not L.ops[0].band and tuple(L.ops[0].weight.shape) == (128, 9, 64)
+    monkeypatch.setenv("YB_STEM_BAND", "1")
+    L, *_ = lower_yolo(m.model, torch.float16, torch.device("cpu"))
+    assert L.ops[0].band and tuple(L.ops[0].weight.shape) == (128, 3, 128) and L.ops[0].pack == 4

@@ -47,6 +47,7 @@ struct PatchParams {
   int tiles_x, tiles_y, m_tiles, n_tiles, num_tiles;
   int block_n, block_k, chunks;
   int a_stages, b_stages, b_resident;
+  int band;               // 1: banded super-pixel weights (stem), see the kBand MMA loop
   int store_cols, store_bufs, bias_len;
   int dbg;                // ablation knobs (YB_CONV_DBG), see conv_sm100.cu
   int a_loader;           // 0: TMA box loads, 1: cooperative cp.async loads (4 warps)
@@ -89,7 +90,7 @@ __device__ __forceinline__ uint64_t make_view_desc(uint32_t addr, uint32_t row_b
   return d;
 }
 
-template <bool kBf16, int kStoreCols, bool kRareAct, bool kCpAsync>
+template <bool kBf16, int kStoreCols, bool kRareAct, bool kCpAsync, bool kBand = false>
 __global__ void __launch_bounds__(block_threads(kCpAsync), 1)
 conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_out, const PatchParams p) {
@@ -174,7 +175,12 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     // ===================== weight (B) producer =====================
     if (lane == 0) {
       const uint32_t b_bytes = p.block_n * p.block_k * 2;
-      if (p.b_resident) {
+      if constexpr (kBand) {
+        // banded stem weights: 3 filter rows x 2 blocks of 64 K-columns, consecutive in the weight matrix
+        mbar_expect_tx(&b_full[0], 6 * b_bytes);
+        for (int i = 0; i < 6; ++i)
+          tma_load_2d(&tmap_b, &b_full[0], b_buf + static_cast<size_t>(i) * p.b_sub_bytes, i * p.block_k, 0);
+      } else if (p.b_resident) {
         mbar_expect_tx(&b_full[0], taps_total * b_bytes);
         for (int i = 0; i < taps_total; ++i)   // i = chunk*9 + tap ; weight column block = tap*chunks + chunk
           tma_load_2d(&tmap_b, &b_full[0], b_buf + static_cast<size_t>(i) * p.b_sub_bytes,
@@ -230,6 +236,31 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           tc_fence_after();
           const uint32_t patch = smem_u32(a_buf + static_cast<size_t>(sa) * p.a_stride);
           const uint32_t a_lo0 = (patch & 0x3FFFFu) >> 4;
+          if constexpr (kBand) {
+            // Super-pixel stem (engine.stem_superpixel, pack 4, 16 channels per pixel, one 64-channel chunk): the
+            // expanded weight matrix is block-banded -- a group of 4 output pixels reads, per filter row, exactly
+            // the 6 input pixels x 16 channels that sit in 192 CONTIGUOUS bytes of the patch, starting 96 bytes into
+            // the left neighbour super-pixel.  Six K=16 steps per filter row walk that span (every start is a
+            // (dx, k-step) address the plain 9-tap loop also uses: (0,3), (1,0..3), (2,0)); the weights hold only
+            // those K-slices: [ky][2 blocks of 64], the last 32 columns of the second block are zero padding that
+            // is never multiplied.  18 MMAs per tile instead of 36, 96 KB of resident weights instead of a
+            // 147 KB ring that is re-streamed from L2 for every tile.
+            if (!(p.dbg & 2)) {
+              const uint32_t row16 = (static_cast<uint32_t>(pitch) * row_bytes) >> 4;
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                  const uint32_t a_lo = a_lo0 + ky * row16 + 6 + 2 * j;
+                  const uint32_t b_lo = b_res_lo0 + static_cast<uint32_t>(ky * 2 + (j >> 2)) * b_step16 + 2 * (j & 3);
+                  if (ky == 0 && j == 0)
+                    umma_f16_lohi<false>(tmem_d, a_lo, a_hi, b_lo, b_hi, p.idesc);
+                  else
+                    umma_f16_lohi<true>(tmem_d, a_lo, a_hi, b_lo, b_hi, p.idesc);
+                }
+              }
+            }
+          } else {
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             uint32_t b_lo;
@@ -248,6 +279,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
               umma_commit(&b_empty[sb]);
               ++kb;
             }
+          }
           }
           umma_commit(&a_empty[sa]);
         }
@@ -407,6 +439,7 @@ using PatchKernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUten
 
 template <bool kBf16>
 PatchKernelFn select_patch_kernel_t(const PatchParams& kp) {
+  if (kp.band) return conv3x3_patch_kernel<kBf16, 64, false, false, true>;    // banded stem (opt-in, YB_STEM_BAND=1)
   if (kp.a_loader == 1) return conv3x3_patch_kernel<kBf16, 0, false, true>;   // experiment knob: one generic variant
   if (kp.ep.act >= YB_ACT_HARDSWISH) return conv3x3_patch_kernel<kBf16, 0, true, false>;
   switch (kp.store_cols) {
@@ -473,9 +506,22 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
     kp.dbg = e ? atoi(e) : 0;
   }
   const size_t staging = static_cast<size_t>(kEpiGroups) * kp.store_bufs * kStageBufBytes;
-  const size_t b_total = static_cast<size_t>(9) * kp.chunks * kp.b_sub_bytes;
+  // reserved bit 1: the weights are the banded super-pixel stem matrix [Cout_pad][3 rows][2 x 64] (engine.stem_band)
+  kp.band = (d.reserved & 2) ? 1 : 0;
+  if (kp.band && !(d.Cin_pad == 64 && n_tiles == 1 && kp.store_cols == 64 && kp.view_mode == 0 && d.act < YB_ACT_HARDSWISH &&
+                   d.residual == nullptr)) {
+    set_error("patch conv: banded stem weights need Cin_pad 64, one N tile with 64-column store boxes, SiLU/linear epilogue");
+    delete op;
+    return YB_ERR_INVALID;
+  }
+  const size_t b_total = static_cast<size_t>(kp.band ? 6 : 9 * kp.chunks) * kp.b_sub_bytes;
   const size_t avail = kSmemBudget - staging - 1024;
   kp.b_resident = (n_tiles == 1 && b_total + 2 * kp.a_stride <= avail) ? 1 : 0;
+  if (kp.band && !kp.b_resident) {
+    set_error("patch conv: banded stem weights do not fit in shared memory (block_n=%d)", block_n);
+    delete op;
+    return YB_ERR_INVALID;
+  }
   kp.b_res_bytes = kp.b_resident ? static_cast<uint32_t>(b_total) : 0u;
   if (kp.b_resident) {
     int a_st = static_cast<int>((avail - b_total) / kp.a_stride);
@@ -511,7 +557,7 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
   {
     const char* e = getenv("YB_PATCH_LOADER");
     kp.a_loader = e ? atoi(e) : 0;
-    if (kp.view_mode == 2) kp.a_loader = 0;   // the dx-split layout exists only for the TMA variant
+    if (kp.view_mode == 2 || kp.band) kp.a_loader = 0;   // the dx-split layout / banded weights exist only for the TMA variant
     if (d.act >= YB_ACT_HARDSWISH) kp.a_loader = 0;   // ... and so do the r3.1 activation variants
   }
   const uint32_t fmt = kp.ep.is_bf16 ? 1u : 0u;
@@ -543,7 +589,7 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
     }
   }
   {
-    const int ktot = 9 * d.Cin_pad;
+    const int ktot = kp.band ? 6 * 64 : 9 * d.Cin_pad;
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(ktot), static_cast<cuuint64_t>(d.Cout_pad)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(ktot) * 2};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(kp.block_k), static_cast<cuuint32_t>(block_n)};

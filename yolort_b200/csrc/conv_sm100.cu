@@ -476,6 +476,9 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
   const long long M_ll = static_cast<long long>(d.N) * Ho * Wo;
   YB_REQUIRE(M_ll > 0 && M_ll < (1ll << 31), "conv: M out of range");
 
+  YB_REQUIRE(!(d.reserved & 2) || patch_conv_eligible(d),
+             "conv: banded stem weights (reserved bit 1) need the halo-patch kernel, which this %dx%d map does not qualify for",
+             d.H, d.W);
   ConvOp* op = new ConvOp();
   if (patch_conv_eligible(d)) {
     rc = patch_conv_create(d, g_encode_tiled, &op->patch);

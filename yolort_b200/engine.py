@@ -61,6 +61,7 @@ class _Op:
     flops_per_pixel: int = 0               # 2*MACs per output pixel of the REFERENCE conv (algorithmic work)
     pack: int = 1                          # horizontally adjacent pixels treated as ONE pixel with pack x channels
     force_im2col: bool = False             # keep this 3x3/s1 conv on the generic im2col kernel
+    band: bool = False                     # weight is the banded super-pixel stem matrix (stem_band), Cin_pad 64
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -134,6 +135,25 @@ def stem_superpixel(w: torch.Tensor, b: torch.Tensor, pack: int = 4) -> Tuple[to
     return out, b.repeat(pack)
 
 
+def stem_band(w: torch.Tensor, b: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Banded form of `stem_superpixel(w, b, pack=4)` for a 16-channel 3x3/s1/p1 conv (the space-to-depth stem).
+
+    A group of 4 output pixels (one super-pixel X) reads, per filter row, the 6 input pixels 4X-1 .. 4X+4; in the
+    patch kernel's shared-memory patch those 6 x 16 channels are 192 contiguous bytes.  Row `po*Co + co` of the result
+    holds, per filter row ky, the 96 weights over (r, c) with r = po + kx the position inside that span; everything
+    else of the 4Co x (3*3*64) super-pixel matrix is structurally zero and is not stored.  Layout
+    [4*Co, 3, 128]: 96 real K-columns per filter row padded to two 64-column blocks (the kernel multiplies 6 K=16
+    steps per row and never touches the padding).  Opt-in (YB_STEM_BAND=1) until measured on B200."""
+    co, ci, kh, kw = w.shape
+    assert (ci, kh, kw) == (16, 3, 3)
+    out = torch.zeros((4 * co, 3, 128), dtype=w.dtype)
+    for po in range(4):
+        for kx in range(3):
+            r = po + kx
+            out[po * co:(po + 1) * co, :, r * 16:(r + 1) * 16] = w[:, :, :, kx].permute(0, 2, 1)   # [co, ky, c]
+    return out, b.repeat(4)
+
+
 def pack_weight(w: torch.Tensor, dtype: torch.dtype, device: torch.device) -> Tuple[torch.Tensor, int, int]:
     """[Co,Ci,k,k] -> K-major [Co_pad, k*k, Ci_pad] (zero padded, both multiples of 16)."""
     co, ci, kh, kw = w.shape
@@ -173,6 +193,16 @@ class _Lowering:
         if ref_flops_per_pixel is None:
             ref_flops_per_pixel = 2 * w.shape[0] * w.shape[1] * k * k
         self.ops.append(_Op(_C.YB_OP_CONV, src, dst, k, s, p, act, wp, bp, residual, name, ref_flops_per_pixel, pack, force_im2col))
+
+    def conv_band(self, name, w_band, b, src: _View, dst: _View, act, ref_flops_per_pixel):
+        """Stem on the banded super-pixel weights (stem_band): pack 4, 3x3/s1/p1, handled by the patch kernel's
+        kBand variant."""
+        co4 = w_band.shape[0]
+        assert src.C == 16 and src.ch0 == 0 and src.C == src.buf.C and dst.ch0 == 0 and dst.C == dst.buf.C and 4 * dst.C == co4
+        assert co4 % 64 == 0 and co4 <= 256, "banded stem needs 64 | 4*Cout <= 256"
+        wp = w_band.to(self.dtype).to(self.device).contiguous()
+        bp = pack_bias(b, co4, self.device)
+        self.ops.append(_Op(_C.YB_OP_CONV, src, dst, 3, 1, 1, act, wp, bp, None, name, ref_flops_per_pixel, 4, False, True))
 
     def conv_module(self, name, m: Conv, src: _View, dst: _View, residual=None):
         w, b = fold_conv_bn(m)
@@ -272,10 +302,17 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
     t0 = L.buf("body.0", 2, w.shape[0])
     import os
     spk = int(os.environ.get("YB_STEM_PACK", "4"))
-    w_sp, b_sp = stem_superpixel(w_s2d, b, spk)
-    L.conv("body.0(stem: 3x3 over s2d super-pixels)", w_sp, b_sp, _View(x0, 0, 16), _View(t0, 0, w.shape[0]), 3, 1, 1,
-           act_code(stem.act), ref_flops_per_pixel=spk * 2 * w.shape[0] * 3 * 36, pack=spk,
-           force_im2col=os.environ.get("YB_STEM_IM2COL", "0") == "1")
+    co4 = 4 * w.shape[0]
+    if (os.environ.get("YB_STEM_BAND", "0") == "1" and spk == 4 and co4 % 64 == 0 and co4 <= 256
+            and act_code(stem.act) in (_C.YB_ACT_SILU, _C.YB_ACT_NONE)):
+        w_b, b_b = stem_band(w_s2d, b)
+        L.conv_band("body.0(stem: banded 3x3 over s2d super-pixels)", w_b, b_b, _View(x0, 0, 16), _View(t0, 0, w.shape[0]),
+                    act_code(stem.act), ref_flops_per_pixel=spk * 2 * w.shape[0] * 3 * 36)
+    else:
+        w_sp, b_sp = stem_superpixel(w_s2d, b, spk)
+        L.conv("body.0(stem: 3x3 over s2d super-pixels)", w_sp, b_sp, _View(x0, 0, 16), _View(t0, 0, w.shape[0]), 3, 1, 1,
+               act_code(stem.act), ref_flops_per_pixel=spk * 2 * w.shape[0] * 3 * 36, pack=spk,
+               force_im2col=os.environ.get("YB_STEM_IM2COL", "0") == "1")
 
     # Concat buffers of the neck (path_aggregation_network.py:215-237), level l at stride 8 << l:
     #   cat_dn[l] = [up(lateral from level l+1) | body tap of level l]   (descending pass, l < nl-1)
@@ -399,8 +436,10 @@ class PlanInstance:
             if op.kind == _C.YB_OP_CONV:
                 d.weight, d.bias = op.weight.data_ptr(), op.bias.data_ptr()
                 d.Cout_pad, _, d.Cin_pad = op.weight.shape
+                if op.band:
+                    d.Cin_pad = 64     # [Cout_pad, 3, 2 x 64] banded stem matrix: one 64-channel chunk of super-pixels
                 flops = N * ho * wo * op.flops_per_pixel
-            d.reserved = 1 if op.force_im2col else 0
+            d.reserved = (1 if op.force_im2col else 0) | (2 if op.band else 0)
             if op.residual is not None:
                 d.residual, d.res_cstride = ptr(op.residual), op.residual.buf.C
             descs.append(d)
