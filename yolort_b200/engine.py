@@ -16,14 +16,14 @@ path_aggregation_network.py:199-239, box_head.py:68-82).  Here the module tree i
 
 Host code only prepares descriptors; all arithmetic happens in csrc/*.cu.
 """
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
 import torch
 from torch import nn
 
 from . import _C
-from .models.common import C3, Bottleneck, BottleneckCSP, Conv, Focus, SPP
+from .models.common import C3, BottleneckCSP, Conv, Focus, SPP
 
 
 def _round_up(v: int, m: int) -> int:
