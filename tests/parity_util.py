@@ -72,3 +72,70 @@ def match_fraction(got, ref, iou_thr=0.9):
     iou = _iou_matrix(np.asarray(ref["boxes"], dtype=np.float64), np.asarray(got["boxes"], dtype=np.float64))
     same = np.asarray(ref["labels"])[:, None] == np.asarray(got["labels"])[None, :]
     return float(((iou > iou_thr) & same).any(axis=1).mean())
+
+
+# ---------------------------------------------------------------------------------------------------
+# north_star tolerance (BASELINE.json): class indices bit-exact, boxes within 1e-3 relative (x canvas side) of the
+# reference, on the detections both sides agree exist (greedy match by label and IoU > 0.9)
+# ---------------------------------------------------------------------------------------------------
+BOX_REL_TOL = 1e-3
+
+
+def pair_stats(got, ref, side: float, iou_thr: float = 0.9):
+    """One-to-one greedy matching of reference detections (score-descending) to same-label detections of `got` with
+    IoU > iou_thr.  Returns matched fraction of the reference, and over the matched pairs: the largest coordinate
+    difference relative to the canvas side, the fraction within BOX_REL_TOL, and the largest score difference."""
+    nr, ng = len(ref["scores"]), len(got["scores"])
+    st = {"n_ref": nr, "n_got": ng, "matched": 1.0 if nr == 0 and ng == 0 else 0.0, "within": 1.0, "max_box_rel": 0.0,
+          "max_score_err": 0.0, "labels_equal": True}
+    if nr == 0 or ng == 0:
+        return st
+    rb, gb = np.asarray(ref["boxes"], dtype=np.float64), np.asarray(got["boxes"], dtype=np.float64)
+    rl, gl = np.asarray(ref["labels"]), np.asarray(got["labels"])
+    rs, gs = np.asarray(ref["scores"], dtype=np.float64), np.asarray(got["scores"], dtype=np.float64)
+    iou = _iou_matrix(rb, gb)
+    ok = (iou > iou_thr) & (rl[:, None] == gl[None, :])
+    taken = np.zeros(ng, dtype=bool)
+    errs, serrs = [], []
+    for i in np.argsort(-rs, kind="stable"):
+        cand = np.nonzero(ok[i] & ~taken)[0]
+        if cand.size == 0:
+            continue
+        j = cand[np.argmax(iou[i, cand])]
+        taken[j] = True
+        errs.append(np.abs(rb[i] - gb[j]).max() / side)
+        serrs.append(abs(rs[i] - gs[j]))
+    st["matched"] = len(errs) / nr
+    if errs:
+        e = np.asarray(errs)
+        st["within"] = float((e <= BOX_REL_TOL).mean())
+        st["max_box_rel"] = float(e.max())
+        st["max_score_err"] = float(max(serrs))
+    return st
+
+
+def assert_e2e_parity(name, got_list, ref_list, side, min_matched, min_within, max_box_rel, max_score_err, iou_thr=0.9):
+    """Every image: labels of matched pairs are equal by construction of the matching (bit-exact class indices);
+    matched fraction >= min_matched; >= min_within of the matched boxes within 1e-3 x side, none beyond max_box_rel."""
+    tot = {"n_ref": 0, "n_pairs": 0.0, "within_w": 0.0}
+    worst = {"matched": 1.0, "within": 1.0, "max_box_rel": 0.0, "max_score_err": 0.0}
+    for k, (got, ref) in enumerate(zip(got_list, ref_list)):
+        st = pair_stats(to_np(got), ref, side, iou_thr)
+        tot["n_ref"] += st["n_ref"]
+        tot["n_pairs"] += st["matched"] * st["n_ref"]
+        tot["within_w"] += st["within"] * st["matched"] * st["n_ref"]
+        worst["matched"] = min(worst["matched"], st["matched"])
+        worst["within"] = min(worst["within"], st["within"])
+        worst["max_box_rel"] = max(worst["max_box_rel"], st["max_box_rel"])
+        worst["max_score_err"] = max(worst["max_score_err"], st["max_score_err"])
+    matched = tot["n_pairs"] / max(tot["n_ref"], 1)
+    within = tot["within_w"] / max(tot["n_pairs"], 1)
+    print(f"PARITY {name}: ref dets {tot['n_ref']} matched {matched:.4f} (worst image {worst['matched']:.4f}) "
+          f"within 1e-3*side {within:.4f} (worst {worst['within']:.4f}) max |dbox|/side {worst['max_box_rel']:.2e} "
+          f"max |dscore| {worst['max_score_err']:.2e}")
+    assert tot["n_ref"] > 0, "the oracle produced no detections: the test would be vacuous"
+    assert matched >= min_matched, (matched, min_matched)
+    assert within >= min_within, (within, min_within)
+    assert worst["max_box_rel"] <= max_box_rel, worst
+    assert worst["max_score_err"] <= max_score_err, worst
+    return {"matched": matched, "within_1e-3": within, **worst}

@@ -55,8 +55,10 @@ def test_per_layer_stagewise_parity_yolov5n():
     m, sd = _model_n()
     g = torch.Generator().manual_seed(3)
     x = torch.rand(2, 3, 64, 96, generator=g)
-    m.model(x.to(DEV))
-    plan = m.model.get_plan(2, 64, 96)
+    plan = m.model.get_plan(2, 64, 96, keep_intermediates=True)   # default arenas reuse the bytes of dead activations
+    m.model._write_samples(plan, x.to(DEV))
+    plan.run()
+    torch.cuda.synchronize()
     net = R.Net(sd)
     with torch.no_grad():
         xr = x.half().float()

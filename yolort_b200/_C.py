@@ -198,6 +198,27 @@ def current_stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def device_guard(device: torch.device):
+    """Context manager that makes `device` the current CUDA device for the native launches inside it (the kernels are
+    launched on `device`'s current stream, which must belong to the current device: the reference works on any
+    device, and so does this path).  Free when `device` already is current."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if torch.cuda.current_device() == idx:
+        return _NO_GUARD
+    return torch.cuda.device(idx)
+
+
 def require_cuda(t: torch.Tensor, what: str) -> None:
     if not t.is_cuda:
         raise NativeLibraryError(
@@ -271,10 +292,11 @@ def letterbox(images: List[torch.Tensor], geoms, Hb: int, Wb: int, fill: float, 
         keep.append(im)
         ptrs[i] = im.data_ptr()
     lut = u8_lut(dev) if src_dtype == torch.uint8 else None
-    check(lib().yb_letterbox_strided(n, ptrs, dtype_code(src_dtype), YB_SRC_HWC if hwc else YB_SRC_CHW, geoms,
-                                     int(Hb), int(Wb), float(fill), lut.data_ptr() if lut is not None else None,
-                                     out.data_ptr(), dtype_code(out.dtype), int(layout), current_stream_ptr(dev)),
-          "yb_letterbox")
+    with device_guard(dev):
+        check(lib().yb_letterbox_strided(n, ptrs, dtype_code(src_dtype), YB_SRC_HWC if hwc else YB_SRC_CHW, geoms,
+                                         int(Hb), int(Wb), float(fill), lut.data_ptr() if lut is not None else None,
+                                         out.data_ptr(), dtype_code(out.dtype), int(layout), current_stream_ptr(dev)),
+              "yb_letterbox")
     for im in keep:  # the kernel reads the sources asynchronously on this stream
         im.record_stream(torch.cuda.current_stream(dev))
     return out
@@ -298,7 +320,8 @@ class Plan:
     def run(self, first: int = 0, count: Optional[int] = None) -> None:
         if count is None:
             count = self.n_ops - first
-        check(lib().yb_plan_run_range(self._h, first, count, current_stream_ptr(self.device)), "yb_plan_run")
+        with device_guard(self.device):
+            check(lib().yb_plan_run_range(self._h, first, count, current_stream_ptr(self.device)), "yb_plan_run")
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -375,10 +398,11 @@ def decode_nms_padded(head_outputs: List[torch.Tensor], layout: str, strides: Se
     need = lib().yb_decode_nms_workspace_bytes(ctypes.byref(p), levels)
     if arena.ws is None or arena.ws.numel() < need or arena.ws.device != dev:
         arena.ws = torch.empty((need,), dtype=torch.uint8, device=dev)
-    check(lib().yb_decode_nms(ctypes.byref(p), levels, rescale.data_ptr() if rescale is not None else None,
-                              boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), counts.data_ptr(),
-                              status.data_ptr(), arena.ws.data_ptr(), arena.ws.numel(), current_stream_ptr(dev)),
-          "yb_decode_nms")
+    with device_guard(dev):
+        check(lib().yb_decode_nms(ctypes.byref(p), levels, rescale.data_ptr() if rescale is not None else None,
+                                  boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), counts.data_ptr(),
+                                  status.data_ptr(), arena.ws.data_ptr(), arena.ws.numel(), current_stream_ptr(dev)),
+              "yb_decode_nms")
     arena.debug_offset = lib().yb_decode_nms_debug_offset(ctypes.byref(p), levels)
     return boxes, scores, labels, counts, status
 
@@ -401,8 +425,9 @@ def decode_dense(head_outputs: List[torch.Tensor], layout: str, strides: Sequenc
     boxes = torch.empty((n_images, total, 4), dtype=torch.float32, device=dev)
     scores = torch.empty((n_images, total, int(num_classes)), dtype=torch.float32, device=dev)
     p = NmsParams(n_images, n_levels, n_anchors, int(num_classes), 0.0, 0.0, 1, 0, 0)
-    check(lib().yb_decode_dense(ctypes.byref(p), levels, boxes.data_ptr(), scores.data_ptr(), current_stream_ptr(dev)),
-          "yb_decode_dense")
+    with device_guard(dev):
+        check(lib().yb_decode_dense(ctypes.byref(p), levels, boxes.data_ptr(), scores.data_ptr(), current_stream_ptr(dev)),
+              "yb_decode_dense")
     return boxes, scores
 
 
@@ -483,8 +508,9 @@ class FusedPost:
         self.status = torch.empty((4,), dtype=torch.int64, device=device)
 
     def begin(self) -> None:
-        check(lib().yb_nms_begin(ctypes.byref(self.params), self.levels, self.status.data_ptr(), self.ws.data_ptr(),
-                                 self.ws.numel(), current_stream_ptr(self.device)), "yb_nms_begin")
+        with device_guard(self.device):
+            check(lib().yb_nms_begin(ctypes.byref(self.params), self.levels, self.status.data_ptr(), self.ws.data_ptr(),
+                                     self.ws.numel(), current_stream_ptr(self.device)), "yb_nms_begin")
 
     def finish(self, rescale: Optional[torch.Tensor]):
         n, D, dev = self.n_images, self.D, self.device
@@ -492,10 +518,11 @@ class FusedPost:
         scores = torch.empty((n, D), dtype=torch.float32, device=dev)
         labels = torch.empty((n, D), dtype=torch.int64, device=dev)
         counts = torch.empty((n,), dtype=torch.int32, device=dev)
-        check(lib().yb_nms_finish(ctypes.byref(self.params), self.levels,
-                                  rescale.data_ptr() if rescale is not None else None, boxes.data_ptr(),
-                                  scores.data_ptr(), labels.data_ptr(), counts.data_ptr(), self.status.data_ptr(),
-                                  self.ws.data_ptr(), self.ws.numel(), current_stream_ptr(dev)), "yb_nms_finish")
+        with device_guard(dev):
+            check(lib().yb_nms_finish(ctypes.byref(self.params), self.levels,
+                                      rescale.data_ptr() if rescale is not None else None, boxes.data_ptr(),
+                                      scores.data_ptr(), labels.data_ptr(), counts.data_ptr(), self.status.data_ptr(),
+                                      self.ws.data_ptr(), self.ws.numel(), current_stream_ptr(dev)), "yb_nms_finish")
         return boxes, scores, labels, counts, self.status
 
 
@@ -512,7 +539,8 @@ def batched_nms(boxes: torch.Tensor, scores: torch.Tensor, labels: torch.Tensor,
     n_keep = torch.zeros((1,), dtype=torch.int32, device=dev)
     need = lib().yb_batched_nms_workspace_bytes(n)
     ws = torch.empty((need,), dtype=torch.uint8, device=dev)
-    check(lib().yb_batched_nms(boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), n, float(iou_threshold),
-                               int(semantics), int(max_keep), keep.data_ptr(), n_keep.data_ptr(), ws.data_ptr(),
-                               ws.numel(), current_stream_ptr(dev)), "yb_batched_nms")
+    with device_guard(dev):
+        check(lib().yb_batched_nms(boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), n, float(iou_threshold),
+                                   int(semantics), int(max_keep), keep.data_ptr(), n_keep.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), current_stream_ptr(dev)), "yb_batched_nms")
     return keep[: int(n_keep.item())]

@@ -33,13 +33,17 @@ void set_error(const char* fmt, ...);
     }                                                                                            \
   } while (0)
 
+// SM count of the CURRENT device (plans are created under the owning device; cached per device index).
 static inline int num_sms() {
-  static int n = 0;
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int n = cache[dev];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cache[dev] = n;
   }
   return n;
 }

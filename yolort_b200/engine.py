@@ -67,14 +67,19 @@ class _Op:
 # ---------------------------------------------------------------------------------------------------
 # parameter preparation
 # ---------------------------------------------------------------------------------------------------
+def bn_scale_shift(bn: nn.BatchNorm2d) -> Tuple[torch.Tensor, torch.Tensor]:
+    """gamma/sqrt(var+eps) and beta - mean*gamma/sqrt(var+eps) in fp64 (on the parameters' device: IEEE fp64
+    mul/div/sqrt give the same bits on the host and on the GPU)."""
+    scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+    shift = bn.bias.detach().double() - bn.running_mean.detach().double() * scale
+    return scale, shift
+
+
 def fold_conv_bn(m: Conv) -> Tuple[torch.Tensor, torch.Tensor]:
     """w' = w * gamma/sqrt(var+eps), b' = beta - mean*gamma/sqrt(var+eps), in fp64.
     (Equivalent to conv -> BatchNorm2d.eval(), yolort/v5/models/common.py:60-70.)"""
-    w = m.conv.weight.detach().double().cpu()
-    bn = m.bn
-    scale = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
-    shift = bn.bias.detach().double().cpu() - bn.running_mean.detach().double().cpu() * scale
-    return w * scale.view(-1, 1, 1, 1), shift
+    scale, shift = bn_scale_shift(m.bn)
+    return m.conv.weight.detach().double() * scale.view(-1, 1, 1, 1), shift
 
 
 def act_code(act: nn.Module) -> int:
@@ -93,7 +98,7 @@ def focus_to_s2d(w: torch.Tensor) -> torch.Tensor:
     is (dy*2+dx)*4 + c with c == 3 a zero channel, so this is a pure channel permutation (stride 1, pad 1 kept)."""
     co, ci, kh, kw = w.shape
     assert ci == 12 and (kh, kw) == (3, 3)
-    out = torch.zeros((co, 16, 3, 3), dtype=w.dtype)
+    out = torch.zeros((co, 16, 3, 3), dtype=w.dtype, device=w.device)
     for g, (dy, dx) in enumerate(((0, 0), (1, 0), (0, 1), (1, 1))):
         q = (dy * 2 + dx) * 4
         out[:, q:q + 3] = w[:, 3 * g:3 * g + 3]
@@ -104,7 +109,7 @@ def stem_to_s2d(w: torch.Tensor) -> torch.Tensor:
     """[Co,3,6,6] stride-2 pad-2 kernel -> [Co,16,3,3] stride-1 pad-1 kernel over the space-to-depth
     input whose channel is (dy*2+dx)*4 + c (c == 3 is a zero channel)."""
     co = w.shape[0]
-    out = torch.zeros((co, 16, 3, 3), dtype=w.dtype)
+    out = torch.zeros((co, 16, 3, 3), dtype=w.dtype, device=w.device)
     for a in range(3):
         for b in range(3):
             for dy in range(2):
@@ -125,7 +130,7 @@ def stem_superpixel(w: torch.Tensor, b: torch.Tensor, pack: int = 4) -> Tuple[to
     the loads alone); as 128-byte super-pixels the stem runs like an ordinary 64->128 3x3 layer."""
     co, ci, kh, kw = w.shape
     assert (kh, kw) == (3, 3)
-    out = torch.zeros((pack * co, pack * ci, 3, 3), dtype=w.dtype)
+    out = torch.zeros((pack * co, pack * ci, 3, 3), dtype=w.dtype, device=w.device)
     for po in range(pack):
         for pi in range(pack):
             for S in range(3):
@@ -143,10 +148,10 @@ def stem_band(w: torch.Tensor, b: torch.Tensor) -> Tuple[torch.Tensor, torch.Ten
     holds, per filter row ky, the 96 weights over (r, c) with r = po + kx the position inside that span; everything
     else of the 4Co x (3*3*64) super-pixel matrix is structurally zero and is not stored.  Layout
     [4*Co, 3, 128]: 96 real K-columns per filter row padded to two 64-column blocks (the kernel multiplies 6 K=16
-    steps per row and never touches the padding).  Opt-in (YB_STEM_BAND=1) until measured on B200."""
+    steps per row and never touches the padding).  Measured on B200 (yolov5s batch 32): 164 -> 88 us."""
     co, ci, kh, kw = w.shape
     assert (ci, kh, kw) == (16, 3, 3)
-    out = torch.zeros((4 * co, 3, 128), dtype=w.dtype)
+    out = torch.zeros((4 * co, 3, 128), dtype=w.dtype, device=w.device)
     for po in range(4):
         for kx in range(3):
             r = po + kx
@@ -158,13 +163,13 @@ def pack_weight(w: torch.Tensor, dtype: torch.dtype, device: torch.device) -> Tu
     """[Co,Ci,k,k] -> K-major [Co_pad, k*k, Ci_pad] (zero padded, both multiples of 16)."""
     co, ci, kh, kw = w.shape
     ci_pad, co_pad = _round_up(ci, 16), _round_up(co, 16)
-    p = torch.zeros((co_pad, kh * kw, ci_pad), dtype=torch.float64)
+    p = torch.zeros((co_pad, kh * kw, ci_pad), dtype=torch.float64, device=w.device)
     p[:co, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci)
     return p.to(dtype).to(device).contiguous(), ci_pad, co_pad
 
 
 def pack_bias(b: torch.Tensor, co_pad: int, device: torch.device) -> torch.Tensor:
-    out = torch.zeros((co_pad,), dtype=torch.float64)
+    out = torch.zeros((co_pad,), dtype=torch.float64, device=b.device)
     out[: b.numel()] = b
     return out.to(torch.float32).to(device).contiguous()
 
@@ -225,12 +230,10 @@ class _Lowering:
         div = src.buf.div
         c_ = m.cv1.conv.out_channels
         cat = self.buf(f"{name}.cat", div, 2 * c_)
-        bn = m.bn
-        scale = bn.weight.detach().double().cpu() / torch.sqrt(bn.running_var.detach().double().cpu() + bn.eps)
-        shift = bn.bias.detach().double().cpu() - bn.running_mean.detach().double().cpu() * scale
+        scale, shift = bn_scale_shift(m.bn)
         y = _View(self.buf(f"{name}.y", div, c_), 0, c_)
         self.conv_module(f"{name}.cv1", m.cv1, src, y)
-        w2 = m.cv2.weight.detach().double().cpu() * scale[c_:].view(-1, 1, 1, 1)
+        w2 = m.cv2.weight.detach().double() * scale[c_:].view(-1, 1, 1, 1)
         self.conv(f"{name}.cv2+bn", w2, shift[c_:], src, _View(cat, c_, c_), 1, 1, 0, _C.YB_ACT_LEAKY01)
         for i, blk in enumerate(m.m):
             t = _View(self.buf(f"{name}.m{i}.t", div, c_), 0, c_)
@@ -238,7 +241,7 @@ class _Lowering:
             out = _View(self.buf(f"{name}.m{i}.y", div, c_), 0, c_)
             self.conv_module(f"{name}.m.{i}.cv2", blk.cv2, t, out, residual=y if blk.add else None)
             y = out
-        w3 = m.cv3.weight.detach().double().cpu() * scale[:c_].view(-1, 1, 1, 1)
+        w3 = m.cv3.weight.detach().double() * scale[:c_].view(-1, 1, 1, 1)
         self.conv(f"{name}.cv3+bn", w3, shift[:c_], y, _View(cat, 0, c_), 1, 1, 0, _C.YB_ACT_LEAKY01)
         self.conv_module(f"{name}.cv4", m.cv4, _View(cat, 0, 2 * c_), dst)
 
@@ -275,8 +278,9 @@ class _Lowering:
         self.ops.append(_Op(_C.YB_OP_UPSAMPLE2X, src, dst, name=name))
 
 
-def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
-    """Walk YOLO.backbone / YOLO.head and emit (lowering, input_buf, head_bufs)."""
+def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device, stem_variant: str = "auto"):
+    """Walk YOLO.backbone / YOLO.head and emit (lowering, input_buf, head_bufs, features).
+    `stem_variant`: "auto" | "band" | "superpixel" | "im2col" (the last two are kept for parity tests and A/B timing)."""
     L = _Lowering(dtype, device)
     bb = model.backbone
     body, pan = bb.body, bb.pan
@@ -300,11 +304,13 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
         w, b = fold_conv_bn(stem)
         w_s2d = stem_to_s2d(w)
     t0 = L.buf("body.0", 2, w.shape[0])
-    import os
-    spk = int(os.environ.get("YB_STEM_PACK", "4"))
-    co4 = 4 * w.shape[0]
-    if (os.environ.get("YB_STEM_BAND", "0") == "1" and spk == 4 and co4 % 64 == 0 and co4 <= 256
-            and act_code(stem.act) in (_C.YB_ACT_SILU, _C.YB_ACT_NONE)):
+    # The stem runs over "super-pixels" of 4 horizontally adjacent s2d pixels (128-byte TMA rows instead of 32).  Its
+    # expanded weight matrix is block-banded, and when 4*Cout fits one N tile the banded kernel variant multiplies only
+    # the band (measured on B200, yolov5s batch 32: 164 -> 88 us); wider stems (yolov5x) use the dense super-pixel form.
+    spk = 4
+    co4 = spk * w.shape[0]
+    if stem_variant == "band" or (stem_variant == "auto" and co4 % 64 == 0 and co4 <= 256
+                                  and act_code(stem.act) in (_C.YB_ACT_SILU, _C.YB_ACT_NONE)):
         w_b, b_b = stem_band(w_s2d, b)
         L.conv_band("body.0(stem: banded 3x3 over s2d super-pixels)", w_b, b_b, _View(x0, 0, 16), _View(t0, 0, w.shape[0]),
                     act_code(stem.act), ref_flops_per_pixel=spk * 2 * w.shape[0] * 3 * 36)
@@ -312,7 +318,7 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
         w_sp, b_sp = stem_superpixel(w_s2d, b, spk)
         L.conv("body.0(stem: 3x3 over s2d super-pixels)", w_sp, b_sp, _View(x0, 0, 16), _View(t0, 0, w.shape[0]), 3, 1, 1,
                act_code(stem.act), ref_flops_per_pixel=spk * 2 * w.shape[0] * 3 * 36, pack=spk,
-               force_im2col=os.environ.get("YB_STEM_IM2COL", "0") == "1")
+               force_im2col=(stem_variant == "im2col"))
 
     # Concat buffers of the neck (path_aggregation_network.py:215-237), level l at stride 8 << l:
     #   cat_dn[l] = [up(lateral from level l+1) | body tap of level l]   (descending pass, l < nl-1)
@@ -383,7 +389,7 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
         co = conv.out_channels
         co_buf = _round_up(co, 16)
         hb = L.buf(f"head.{i}", feat.buf.div, co_buf)
-        L.conv(f"head.head.{i}", conv.weight.detach().double().cpu(), conv.bias.detach().double().cpu(), feat,
+        L.conv(f"head.head.{i}", conv.weight.detach().double(), conv.bias.detach().double(), feat,
                _View(hb, 0, co_buf), 1, 1, 0, _C.YB_ACT_NONE)
         head_bufs.append(hb)
     return L, x0, head_bufs, {f"p{l + 3}": r for l, r in enumerate(results)}
@@ -392,28 +398,116 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device):
 # ---------------------------------------------------------------------------------------------------
 # plan instances
 # ---------------------------------------------------------------------------------------------------
-class PlanInstance:
-    """Arena + native plan for one (N, H, W)."""
+class Lowered:
+    """Shape-independent part of a model's plans: the op list with BN-folded, packed weights on the device.  Built
+    once per Engine and shared by every PlanInstance (a plan adds only an activation arena and TMA descriptors)."""
 
-    def __init__(self, L: _Lowering, x0: _Buf, head_bufs: List[_Buf], feats: Dict[str, _View], N: int, H: int, W: int,
-                 post: Optional[dict] = None):
+    def __init__(self, model: nn.Module, dtype: torch.dtype, device: torch.device, stem_variant: str = "auto"):
+        self.L, self.x0, self.head_bufs, self.feats = lower_yolo(model, dtype, device, stem_variant)
+        self.n_heads = len(self.head_bufs)
+        self.weight_bytes = sum(op.weight.numel() * op.weight.element_size() + op.bias.numel() * 4
+                                for op in self.L.ops if op.weight is not None)
+
+
+def assign_offsets(L: _Lowering, x0: _Buf, keep: List[_Buf], N: int, H: int, W: int, reuse: bool, esz: int = 2):
+    """Arena layout for one (N, H, W): byte offset per buffer and the arena size.
+
+    With `reuse`, a buffer occupies its bytes only from its first writer to its last reader (launch order is the op
+    order and every launch waits for the previous one, programmatic dependent launch included), so the arena is the
+    peak of the live set instead of the sum of all activations (yolov5x batch 64 1280x1280: 56 GB -> a few GB).
+    Buffers in `keep` (head logits, the PAN results) stay live to the end."""
+    n_ops = len(L.ops)
+    size = {id(b): _round_up(N * (H // b.div) * (W // b.div) * b.C * esz, 1024) for b in L.bufs}
+    first = {id(b): n_ops for b in L.bufs}
+    last = {id(b): -1 for b in L.bufs}
+    first[id(x0)] = -1
+    for i, op in enumerate(L.ops):
+        first[id(op.dst.buf)] = min(first[id(op.dst.buf)], i)
+        last[id(op.dst.buf)] = max(last[id(op.dst.buf)], i)
+        for v in (op.src, op.residual):
+            if v is not None:
+                last[id(v.buf)] = max(last[id(v.buf)], i)
+                first[id(v.buf)] = min(first[id(v.buf)], i)
+    for b in keep:
+        last[id(b)] = n_ops
+    offsets: Dict[int, int] = {}
+    if not reuse:
+        off = 0
+        for b in L.bufs:
+            offsets[id(b)] = off
+            off += size[id(b)]
+        return offsets, off
+    order = sorted(L.bufs, key=lambda b: first[id(b)])
+    free: List[List[int]] = []          # [offset, bytes], sorted by offset, coalesced
+    live: List[Tuple[int, _Buf]] = []   # (last use, buffer)
+    top = 0
+    k = 0
+    for step in range(-1, n_ops):
+        # allocate what is first touched at this step (inputs of the step are still live: freed after it)
+        while k < len(order) and first[id(order[k])] <= step:
+            b = order[k]
+            k += 1
+            need = size[id(b)]
+            best = None
+            for blk in free:
+                if blk[1] >= need and (best is None or blk[1] < best[1]):
+                    best = blk
+            if best is not None:
+                offsets[id(b)] = best[0]
+                best[0] += need
+                best[1] -= need
+                if best[1] == 0:
+                    free.remove(best)
+            elif free and free[-1][0] + free[-1][1] == top:   # grow the trailing free block
+                offsets[id(b)] = free[-1][0]
+                top = free[-1][0] + need
+                free.pop()
+            else:
+                offsets[id(b)] = top
+                top += need
+            live.append((last[id(b)], b))
+        # release what this step read last
+        still = []
+        for lu, b in live:
+            if lu <= step:
+                free.append([offsets[id(b)], size[id(b)]])
+            else:
+                still.append((lu, b))
+        live = still
+        free.sort()
+        merged: List[List[int]] = []
+        for blk in free:
+            if merged and merged[-1][0] + merged[-1][1] == blk[0]:
+                merged[-1][1] += blk[1]
+            else:
+                merged.append(blk)
+        free = merged
+    return offsets, top
+
+
+class PlanInstance:
+    """Arena + native plan for one (N, H, W); weights come from the Engine's shared `Lowered`."""
+
+    def __init__(self, low: Lowered, N: int, H: int, W: int, post: Optional[dict] = None, keep_intermediates: bool = False):
+        L, x0, head_bufs, feats = low.L, low.x0, low.head_bufs, low.feats
         grain = max(b.div for b in L.bufs)
         if H % grain or W % grain:
             raise ValueError(f"canvas {H}x{W} must be a multiple of {grain}")
         self.N, self.H, self.W = N, H, W
         self.dtype, self.device = L.dtype, L.device
+        self.keep_intermediates = keep_intermediates
         esz = 2
-        off = 0
-        for b in L.bufs:
-            b.offset = off
-            off += _round_up(N * (H // b.div) * (W // b.div) * b.C * esz, 1024)
-        self.arena = torch.zeros((off,), dtype=torch.uint8, device=L.device)
-        self.arena_bytes = off
+        # the input canvas stays live too, so that a plan can be re-run (timing loops, tests) without re-letterboxing
+        keep = [x0] + list(head_bufs) + [v.buf for v in feats.values()]
+        offsets, total = assign_offsets(L, x0, keep, N, H, W, reuse=not keep_intermediates, esz=esz)
+        self.arena = torch.zeros((max(total, 1024),), dtype=torch.uint8, device=L.device)
+        self.arena_bytes = total
+        self.unshared_bytes = sum(_round_up(N * (H // b.div) * (W // b.div) * b.C * esz, 1024) for b in L.bufs)
         base = self.arena.data_ptr()
         code = _C.dtype_code(L.dtype)
 
         def ptr(v: _View) -> int:
-            return base + v.buf.offset + v.ch0 * esz
+            return base + offsets[id(v.buf)] + v.ch0 * esz
 
         descs = []
         self.op_names = []
@@ -445,7 +539,8 @@ class PlanInstance:
             descs.append(d)
             self.op_names.append(op.name)
             self.op_flops.append(flops)
-        self._keepalive = [op.weight for op in L.ops] + [op.bias for op in L.ops]
+        self._low = low                     # keeps the shared weights alive
+        self.n_heads = low.n_heads
         self.plan = _C.Plan(descs, L.device)
         # Second launch list whose head convolutions decode + threshold in their epilogue and append candidates to a
         # fixed NMS arena instead of storing logits (box_head.py:68-82 + :328-360,418 fused).
@@ -468,16 +563,31 @@ class PlanInstance:
         def nhwc(b: _Buf) -> torch.Tensor:
             h, w = H // b.div, W // b.div
             n = N * h * w * b.C
-            return self.arena[b.offset: b.offset + n * esz].view(L.dtype).view(N, h, w, b.C)
+            o = offsets[id(b)]
+            return self.arena[o: o + n * esz].view(L.dtype).view(N, h, w, b.C)
 
         self.input = nhwc(x0)                      # [N, H/2, W/2, 16] space-to-depth canvas
         self.heads = [nhwc(b) for b in head_bufs]  # [N, h, w, round_up(3*(nc+5), 16)]
         self.features = {k: nhwc(v.buf) for k, v in feats.items()}
+        # every buffer by name; with arena reuse (the default) only `input`, `heads` and `features` hold their data
+        # after a full run -- ask for `keep_intermediates=True` to inspect the others
         self.buffers = {b.name: nhwc(b) for b in L.bufs}
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.arena.numel())
 
     def run(self, first: int = 0, count: Optional[int] = None) -> None:
         """Backbone + PAN + heads, logits stored in `self.heads`."""
         self.plan.run(first, count)
+
+    def run_backbone(self) -> None:
+        """Everything but the detection-head convolutions (`YOLO.backbone`)."""
+        self.plan.run(0, self.plan.n_ops - self.n_heads)
+
+    def run_heads(self) -> None:
+        """The detection-head 1x1 convolutions over `self.features` (`YOLO.head`)."""
+        self.plan.run(self.plan.n_ops - self.n_heads, self.n_heads)
 
     def run_fused(self) -> None:
         """Backbone + PAN + heads with the decode epilogue (candidates land in `self.fused_post`'s arena)."""
@@ -485,9 +595,14 @@ class PlanInstance:
 
 
 class Engine:
-    """Per-model cache of plan instances keyed by (N, H, W)."""
+    """Per-model state of the native path: the weights lowered ONCE (BN folded, packed, on the device) and an LRU
+    cache of plan instances keyed by (N, H, W).  A new shape costs an arena allocation plus descriptor encoding
+    (milliseconds), never a re-lowering; the cache is bounded by a plan count and a byte budget so that a serving
+    process with dynamic canvases does not accumulate arenas without limit."""
 
-    def __init__(self, model: nn.Module, dtype: torch.dtype, device: torch.device):
+    MAX_PLANS = 32
+
+    def __init__(self, model: nn.Module, dtype: torch.dtype, device: torch.device, max_arena_bytes: Optional[int] = None):
         if device.type != "cuda":
             raise _C.NativeLibraryError(
                 f"yolort_b200 runs on sm_100a GPUs only; model parameters are on {device} (no CPU fallback)")
@@ -495,16 +610,59 @@ class Engine:
             raise _C.NativeLibraryError(f"compute dtype must be float16 or bfloat16, got {dtype}")
         _C.lib()
         self.model, self.dtype, self.device = model, dtype, device
-        self._plans: Dict[tuple, PlanInstance] = {}
+        import collections
+        self._plans: "collections.OrderedDict[tuple, PlanInstance]" = collections.OrderedDict()
+        self._low: Optional[Lowered] = None
+        self._tensors: List[torch.Tensor] = []
+        self._versions: Tuple[int, ...] = ()
+        self.max_arena_bytes = max_arena_bytes
+        self.lowerings = 0       # how many times the weights were folded/packed (tests: stays 1 across shapes)
+        self.stem_variant = "auto"
 
-    def plan(self, N: int, H: int, W: int, post: Optional[dict] = None) -> PlanInstance:
+    # -- weights -------------------------------------------------------------------------------------------------
+    def _fingerprint(self) -> Tuple[int, ...]:
+        return tuple(t._version for t in self._tensors)
+
+    def lowered(self) -> Lowered:
+        """The shared lowering; rebuilt (and every plan dropped) when a parameter or BN statistic was modified in
+        place since the last lowering (`_version` counters; `.to()` / `load_state_dict` go through YOLO's hooks)."""
+        if self._low is not None and self._fingerprint() != self._versions:
+            self.invalidate()
+        if self._low is None:
+            with _C.device_guard(self.device):
+                self._tensors = [t for t in list(self.model.parameters()) + list(self.model.buffers())]
+                self._versions = self._fingerprint()
+                self._low = Lowered(self.model, self.dtype, self.device, self.stem_variant)
+            self.lowerings += 1
+        return self._low
+
+    def invalidate(self) -> None:
+        self._plans.clear()
+        self._low = None
+
+    # -- plans ---------------------------------------------------------------------------------------------------
+    def _budget(self) -> int:
+        if self.max_arena_bytes is not None:
+            return self.max_arena_bytes
+        try:
+            return int(0.6 * torch.cuda.get_device_properties(self.device).total_memory)
+        except Exception:
+            return 64 << 30
+
+    def plan(self, N: int, H: int, W: int, post: Optional[dict] = None, keep_intermediates: bool = False) -> PlanInstance:
+        low = self.lowered()
         pkey = None if post is None else (post["score_thresh"], post["nms_thresh"], post["detections_per_img"],
                                           post["semantics"], post["num_classes"])
-        key = (N, H, W, pkey)
+        key = (N, H, W, pkey, bool(keep_intermediates))
         inst = self._plans.get(key)
-        if inst is None:
-            with torch.cuda.device(self.device):
-                L, x0, head_bufs, feats = lower_yolo(self.model, self.dtype, self.device)
-                inst = PlanInstance(L, x0, head_bufs, feats, N, H, W, post)
-            self._plans[key] = inst
+        if inst is not None:
+            self._plans.move_to_end(key)
+            return inst
+        with _C.device_guard(self.device):
+            inst = PlanInstance(low, N, H, W, post, keep_intermediates)
+        self._plans[key] = inst
+        budget = self._budget()
+        while len(self._plans) > 1 and (len(self._plans) > self.MAX_PLANS or
+                                        sum(p.device_bytes for p in self._plans.values()) > budget):
+            self._plans.popitem(last=False)      # least recently used
         return inst

@@ -22,6 +22,14 @@ class BackboneWithPAN(_PlanOnly):
         self.pan = PathAggregationNetwork(in_channels_list, depth_multiple, version=version, use_p6=use_p6)
         self.out_channels = in_channels_list
 
+    def forward(self, x):
+        """`backbone(x)` (backbone_utils.py:54-57): [N,3,H,W] -> PAN feature maps [N,C_l,H/s_l,W/s_l], executed as the
+        backbone launch range of the owning YOLO's plan (forward hooks fire: yolort/utils/hooks.py:7-26)."""
+        owner = self.__dict__.get("_yb_owner")
+        if not owner:
+            return super().forward(x)
+        return owner[0].run_backbone(x)
+
 
 def darknet_pan_backbone(
     backbone_name: str,

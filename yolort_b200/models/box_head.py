@@ -39,6 +39,14 @@ class YOLOHead(_PlanOnly):
                 b[:, 5:] += math.log(0.6 / (num_classes - 0.999999))
         self.head = blocks
 
+    def forward(self, x: List[Tensor]) -> List[Tensor]:
+        """`head(features)` (box_head.py:68-82): per level [N, A, H, W, nc+5] raw logits -- the training-mode output
+        of the detector as well -- executed as the head launch range of the owning YOLO's plan."""
+        owner = self.__dict__.get("_yb_owner")
+        if not owner:
+            return super().forward(x)
+        return owner[0].run_head(list(x))
+
 
 class PostProcess(nn.Module):
     """Decode + threshold + batched NMS + top-k on the device.

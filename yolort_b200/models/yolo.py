@@ -89,15 +89,24 @@ class YOLO(nn.Module):
                                        anchors_px=anchor_generator.anchors_px())
         self.post_process = post_process
         self._engine = None
+        # `backbone(x)` / `head(features)` are callable sub-modules like the reference's (yolo.py:163-166,
+        # utils/hooks.py:7-26): they execute the corresponding launch range of this model's plan.  The owner is
+        # reached through a list so that it is neither registered as a sub-module nor lost by deepcopy/pickle.
+        self.backbone.__dict__["_yb_owner"] = [self]
+        self.head.__dict__["_yb_owner"] = [self]
+        # Prepared (BN-folded, packed) weights must follow the parameters.  nn.Module.load_state_dict on a PARENT
+        # never calls child.load_state_dict -- it recurses through _load_from_state_dict and fires the post hooks
+        # of every sub-module -- so the invalidation is a post hook; `.to()/.half()/.cuda()` reach `_apply`; in-place
+        # edits are caught by the engine's parameter-version fingerprint.
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module._drop_engine())
 
     # -- engine lifetime -----------------------------------------------------------------------------
+    def _drop_engine(self) -> None:
+        self._engine = None
+
     def _apply(self, fn, *a, **k):  # .to()/.half()/.cuda() invalidate prepared weights
         self._engine = None
         return super()._apply(fn, *a, **k)
-
-    def load_state_dict(self, *a, **k):
-        self._engine = None
-        return super().load_state_dict(*a, **k)
 
     def engine(self):
         from ..engine import Engine
@@ -120,11 +129,61 @@ class YOLO(nn.Module):
                 "nms_thresh": float(pp.nms_thresh), "detections_per_img": int(pp.detections_per_img),
                 "semantics": int(getattr(pp, "nms_semantics", _C.NMS_TV_AUTO))}
 
-    def get_plan(self, N: int, H: int, W: int):
+    def get_plan(self, N: int, H: int, W: int, keep_intermediates: bool = False):
+        """Plan instance for a batch of N canvases of H x W.  `keep_intermediates=True` gives every activation its
+        own bytes (inspection / stage-wise tests); the default arena reuses the bytes of dead activations."""
         # The fused decode epilogue (heads emit NMS candidates instead of logits) is functional but, as measured in
         # round 1, slower than storing fp16 logits + the stand-alone decode kernel; opt-in until it is tuned.
         fuse = os.environ.get("YB_FUSED_DECODE", "0") == "1"
-        return self.engine().plan(N, H, W, self.post_config() if fuse else None)
+        return self.engine().plan(N, H, W, self.post_config() if fuse else None, keep_intermediates)
+
+    def has_hooks(self) -> bool:
+        """True when a forward (pre-)hook sits on backbone / head / post_process (yolort/utils/hooks.py:15-17): the
+        forward then goes stage by stage through the sub-modules' __call__ so that the hooks fire."""
+        return any(m._forward_hooks or m._forward_pre_hooks for m in (self.backbone, self.head, self.post_process))
+
+    def _write_samples(self, plan, samples: Tensor) -> None:
+        """A pre-letterboxed NCHW batch -> the plan's space-to-depth input (identity geometry)."""
+        N, _, H, W = (int(v) for v in samples.shape)
+        geoms = (_C.LetterboxGeom * N)()
+        for g in geoms:
+            g.src_h, g.src_w, g.new_h, g.new_w, g.top, g.left = H, W, H, W, 0, 0
+            g.ratio_h = g.ratio_w = 1.0
+        samples = samples.contiguous()
+        _C.letterbox([samples[i] for i in range(N)], geoms, H, W, 0.0, plan.input, _C.YB_LAYOUT_S2D16)
+
+    def run_backbone(self, samples: Tensor) -> List[Tensor]:
+        """`backbone(samples)`: body + PAN; NCHW feature maps (yolort/models/backbone_utils.py:54-57)."""
+        if samples.dim() != 4 or samples.shape[1] != 3:
+            raise ValueError(f"samples must be [N,3,H,W], got {tuple(samples.shape)}")
+        N, _, H, W = (int(v) for v in samples.shape)
+        plan = self.get_plan(N, H, W)
+        self._write_samples(plan, samples)
+        plan.run_backbone()
+        return [plan.features[k].permute(0, 3, 1, 2).clone() for k in sorted(plan.features)]
+
+    def run_head(self, features: List[Tensor]) -> List[Tensor]:
+        """`head(features)`: the raw per-level logits [N, A, H, W, nc+5] (yolort/models/box_head.py:68-82); the same
+        list in training and eval mode."""
+        s0 = int(self.anchor_generator.strides[0])
+        N, _, h0, w0 = (int(v) for v in features[0].shape)
+        plan = self.get_plan(N, h0 * s0, w0 * s0)
+        keys = sorted(plan.features)
+        if len(features) != len(keys):
+            raise ValueError(f"head expects {len(keys)} feature maps, got {len(features)}")
+        for k, f in zip(keys, features):
+            dst = plan.features[k]
+            if tuple(f.shape) != (dst.shape[0], dst.shape[3], dst.shape[1], dst.shape[2]):
+                raise ValueError(f"feature {k}: expected [N,{dst.shape[3]},{dst.shape[1]},{dst.shape[2]}], got {tuple(f.shape)}")
+            _C.require_cuda(f, "head")
+            dst.copy_(f.permute(0, 2, 3, 1))       # layout change only (NCHW caller tensor -> plan NHWC buffer)
+        plan.run_heads()
+        A, K = self.anchor_generator.num_anchors, self.num_classes + 5
+        outs = []
+        for hbuf in plan.heads:
+            n, h, w, _ = hbuf.shape
+            outs.append(hbuf[..., : A * K].view(n, h, w, A, K).permute(0, 3, 1, 2, 4).contiguous())
+        return outs
 
     def run_plan(self, plan) -> List[Tensor]:
         """backbone + PAN + head on the prepared input canvas; returns the raw head logits (NHWC)."""
@@ -166,18 +225,26 @@ class YOLO(nn.Module):
                              pc["detections_per_img"], pc["semantics"], rescale=rescale, num_classes=self.num_classes)
 
     def forward(self, samples: Tensor, targets: Optional[Tensor] = None):
-        if self.training or targets is not None:
-            raise NotImplementedError("the training path (SetCriterion) is out of scope of this build; call .eval()")
         if samples.dim() != 4 or samples.shape[1] != 3:
             raise ValueError(f"samples must be [N,3,H,W], got {tuple(samples.shape)}")
+        if self.training or self.has_hooks():
+            # stage by stage through the callable sub-modules, as the reference does (yolo.py:162-177)
+            features = self.backbone(samples)
+            head_outputs = self.head(features)
+            if self.training:
+                # the training-mode output of the head is the raw per-level list; the loss itself (SetCriterion,
+                # box_head.py:85-325) is out of scope, a caller-supplied criterion receives what the reference passes
+                if self.compute_loss is None:
+                    raise NotImplementedError(
+                        "training mode returns criterion(targets, head_outputs); SetCriterion is out of scope of this "
+                        "build -- construct YOLO(..., criterion=...) or call model.head(model.backbone(x)) directly")
+                return self.compute_loss(targets, head_outputs)
+            return self.post_process(head_outputs, None, None)
+        if targets is not None:
+            raise NotImplementedError("targets are only used by the training path; call .train() with a criterion")
         N, _, H, W = (int(v) for v in samples.shape)
         plan = self.get_plan(N, H, W)
-        geoms = (_C.LetterboxGeom * N)()
-        for g in geoms:
-            g.src_h, g.src_w, g.new_h, g.new_w, g.top, g.left = H, W, H, W, 0, 0
-            g.ratio_h = g.ratio_w = 1.0
-        samples = samples.contiguous()
-        _C.letterbox([samples[i] for i in range(N)], geoms, H, W, 0.0, plan.input, _C.YB_LAYOUT_S2D16)
+        self._write_samples(plan, samples)
         return self.detect(plan)
 
     @classmethod

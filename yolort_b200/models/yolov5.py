@@ -60,8 +60,23 @@ class YOLOv5(nn.Module):
         return plan, rescale
 
     def forward(self, inputs: List[Tensor], targets: Optional[List[Dict[str, Tensor]]] = None):
+        if self.training or self.model.has_hooks():
+            # The reference's own staging (yolov5.py:160-189): transform -> model (backbone -> head -> post-process
+            # through the callable sub-modules, so forward hooks fire) -> rescale.  Training mode returns what the
+            # caller's criterion returns; target resizing (transform.py:86-97) belongs to the out-of-scope loss path.
+            if targets is not None and self.training:
+                raise NotImplementedError("target transformation / SetCriterion are out of scope; call model.model(samples, "
+                                          "targets) with a criterion on pre-letterboxed batches")
+            inputs = list(inputs)
+            original_image_sizes = [(int(im.shape[-2]), int(im.shape[-1])) for im in inputs]
+            samples, _ = self.transform(inputs, None)
+            outputs = self.model(samples.tensors, None)
+            if self.training:
+                return outputs
+            hb, wb = int(samples.tensors.shape[-2]), int(samples.tensors.shape[-1])
+            return self.transform.postprocess(outputs, (hb, wb), original_image_sizes)
         if targets is not None:
-            raise NotImplementedError("the training path is out of scope of this build")
+            raise NotImplementedError("targets are only used by the training path")
         plan, rescale = self._prepare(inputs)
         return self.model.detect(plan, rescale)
 

@@ -62,6 +62,27 @@ def all_gather_detections(packed: Tensor, counts: Tensor, shard_sizes: Sequence[
     return recv[keep], recv_c[keep]
 
 
+def forward_padded_grow(model, images: List[Tensor], canvas: Tuple[int, int], max_tries: int = 8):
+    """`forward_padded` on the shard-local images letterboxed to the GLOBAL canvas, re-run with a larger candidate
+    arena until no image overflowed its share (status[1] == 0): nothing is ever truncated or dropped silently.  The
+    growth uses the same canvas as the run that overflowed (candidate counts depend on it); a plan whose fused-decode
+    arena is fixed falls back to the stored-logits path, whose arena grows."""
+    dev = next(model.parameters()).device
+    for _ in range(max_tries):
+        out = model.forward_padded(images, batch_hw=canvas)
+        st = out[4].cpu().tolist()
+        if int(st[1]) == 0:
+            return out
+        arena = _C._arenas.setdefault(dev, _C._NmsArena())
+        arena.cap_per_image = max(2 * arena.cap_per_image, int(st[2]))
+        arena.ws = None
+        plan = model.model.get_plan(len(images), canvas[0], canvas[1])
+        if plan.fused_post is not None:      # fixed arena inside the plan: use the growable stand-alone decode
+            plan.fused_post = None
+    raise _C.NativeLibraryError(f"predict_sharded: candidate arena still overflows after {max_tries} growth steps "
+                                f"(needs {int(st[2])} candidates per image)")
+
+
 def predict_sharded(model, images: List[Tensor], group=None) -> List[Dict[str, Tensor]]:
     """Every rank passes the SAME full list of images (host tensors or tensors on its device); each rank runs
     its contiguous shard on its own GPU and all ranks return the full, ordered detection list."""
@@ -75,10 +96,7 @@ def predict_sharded(model, images: List[Tensor], group=None) -> List[Dict[str, T
     D = model.model.post_process.detections_per_img
     if hi > lo:
         mine = model.collate_images(images[lo:hi], None)
-        boxes, scores, labels, counts, status = model.forward_padded(mine, batch_hw=canvas)
-        if int(status[1].item()) != 0:   # candidate arena overflow: grow and retry (never truncate)
-            model.forward(mine)          # the list API grows the arena
-            boxes, scores, labels, counts, status = model.forward_padded(mine, batch_hw=canvas)
+        boxes, scores, labels, counts, status = forward_padded_grow(model, mine, canvas)
         packed = pack_detections(boxes, scores, labels)
     else:
         packed = torch.zeros((0, D, 6), dtype=torch.float32, device=p.device)
