@@ -209,6 +209,11 @@ int yb_nms_begin(const yb_nms_params* p, const yb_head_level* levels, int64_t* s
 int yb_nms_finish(const yb_nms_params* p, const yb_head_level* levels, const float* rescale_dev, float* boxes_dev,
                   float* scores_dev, int64_t* labels_dev, int32_t* counts_dev, int64_t* status_dev,
                   void* workspace_dev, size_t workspace_bytes, void* stream);
+/* The decode + multi-label threshold step alone (box_head.py:328-360, :418): appends the candidates of `levels` to the
+ * workspace arena between yb_nms_begin and yb_nms_finish.  yb_decode_nms == begin + decode_candidates + finish; the
+ * split exists so that a caller can time (or overlap) the three steps separately. */
+int yb_decode_candidates(const yb_nms_params* p, const yb_head_level* levels, void* workspace_dev,
+                         size_t workspace_bytes, void* stream);
 
 /* Dense decode, no threshold / NMS (replaces LogitsDecoder.forward: yolort/relay/logits_decoder.py:26-61, the
  * output the reference hands to TensorRT's EfficientNMS plugin): boxes_dev [n_images, anchors_per_image, 4] fp32

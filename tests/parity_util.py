@@ -63,8 +63,16 @@ def _iou_matrix(a, b):
     return inter / (aa[:, None] + ab[None, :] - inter + 1e-12)
 
 
-def match_fraction(got, ref, iou_thr=0.9):
-    """Fraction of reference detections that have a same-label detection with IoU > iou_thr."""
+def match_fraction(got, ref, iou_thr=0.9, side=None, box_rel=None):
+    """Fraction of reference detections that have a same-label detection with IoU > iou_thr.
+    With `side` (canvas / image side in pixels) the one-to-one matched pairs must also agree to `box_rel` x side in
+    every coordinate (default BOX_REL_TOL = 1e-3, north_star's tolerance); labels of matched pairs are equal by
+    construction."""
+    if side is not None:
+        st = pair_stats(got, ref, float(side), iou_thr)
+        tol = BOX_REL_TOL if box_rel is None else box_rel
+        assert st["max_box_rel"] <= tol, f"matched boxes differ by {st['max_box_rel']:.2e} x side (> {tol:.0e}): {st}"
+        return st["matched"]
     if len(ref["scores"]) == 0:
         return 1.0 if len(got["scores"]) == 0 else 0.0
     if len(got["scores"]) == 0:

@@ -25,16 +25,24 @@ def _act(y, code):
 
 
 def check_plan_stagewise(model_yolo, plan, verbose=True):
-    """`plan` must have been created with keep_intermediates=True and run once.  Returns [(name, violations, max_err)]."""
+    """`plan` must have been created with keep_intermediates=True and its input canvas written.  Launches the plan ONE
+    op at a time and checks each launch right after it ran (C3 blocks overwrite channel windows in place -- the last
+    bottleneck writes over cv1's half of the concat buffer, its own residual -- so inputs are only valid at that
+    moment; the residual is snapshotted before the launch).  Returns [(name, violations, max_err)]."""
     assert plan.keep_intermediates
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     L = plan._low.L
     tol = TOL[plan.dtype]
     out = []
-    for op in L.ops:
+    for i, op in enumerate(L.ops):
         src = plan.buffers[op.src.buf.name][..., op.src.ch0: op.src.ch0 + op.src.C]
         dst = plan.buffers[op.dst.buf.name][..., op.dst.ch0: op.dst.ch0 + op.dst.C]
+        res_snapshot = None
+        if op.residual is not None:
+            res_snapshot = plan.buffers[op.residual.buf.name][..., op.residual.ch0: op.residual.ch0 + op.residual.C].clone()
+        plan.run(i, 1)
+        torch.cuda.synchronize()
         got = _nchw(dst)
         if op.kind == _C.YB_OP_SPP_POOL:
             x = _nchw(src)
@@ -56,9 +64,8 @@ def check_plan_stagewise(model_yolo, plan, verbose=True):
             co, ci, k = op.dst.C, op.src.C, op.ksize
             w = op.weight[:co, :, :ci].float().view(co, k, k, ci).permute(0, 3, 1, 2).contiguous()
             ref = _act(F.conv2d(_nchw(src), w, op.bias[:co], op.stride, op.pad), op.act)
-            if op.residual is not None:
-                r = plan.buffers[op.residual.buf.name][..., op.residual.ch0: op.residual.ch0 + op.residual.C]
-                ref = ref + _nchw(r)
+            if res_snapshot is not None:
+                ref = ref + _nchw(res_snapshot)
         err = (got - ref).abs()
         bad = int((err > tol * (1.0 + ref.abs())).sum().item())
         mx = float(err.max().item())

@@ -31,11 +31,27 @@ def _bench_model():
 
 
 def _zoo(ctor, name, gain, dtype=None, **kw):
-    sd = util.synth_state_dict(util.layouts()[name], knob_obj=7.0, knob_cls=4.5, seed=1, gain=gain)
+    """Model + weights of bench.py's configs c3-c5 (He gain < 2, the bench's head load knob)."""
+    import bench
+
     m = ctor(**kw).eval()
+    sd = bench.zoo_state_dict(m, gain)
     m.load_state_dict(sd)
     m = m.to(DEV)
     return (m.to(dtype) if dtype is not None else m), sd
+
+
+def _calibrated_thresh(sd, im, size, target=1200):
+    """Score threshold that lets ~`target` candidates of image `im` through (midway between two neighbouring oracle
+    scores, so that the threshold itself sits in a gap): a realistic NMS load -- detections below the 300 cap, no
+    top-k lottery among near-tied scores -- whatever the logit spread of the random weights is."""
+    batch, _, _ = R.letterbox([im], float(size[0]), float(size[1]))
+    net = R.Net(sd)
+    with torch.no_grad():
+        heads = net.head(net.backbone(batch))
+    _, scores = R.decode(heads)
+    s = np.sort(scores[0].numpy().ravel())[::-1]
+    return float((s[target - 1] + s[target]) / 2)
 
 
 def _stagewise(m, x_u8_list, n, h, w):
@@ -44,7 +60,6 @@ def _stagewise(m, x_u8_list, n, h, w):
     geoms, (Hb, Wb) = m.transform.geometry(x_u8_list)
     assert (Hb, Wb) == (h, w)
     m.transform.letterbox_into(x_u8_list, geoms, Hb, Wb, plan.input, 1)
-    plan.run()
     torch.cuda.synchronize()
     res = check_plan_stagewise(m.model, plan)
     bad = [(nm, b, e) for nm, b, e in res if b]
@@ -67,33 +82,39 @@ def test_c2_yolov5s_bs32_640_fp16_detections_vs_oracle():
     ims = bench.make_images(32, 1234)
     out = m([im.to(DEV) for im in ims])
     ref = R.detect(sd, ims[:8], score_thresh=bench.SCORE_THRESH)
-    util.assert_e2e_parity("c2 yolov5s bs32 640 fp16", out[:8], ref, 640.0, min_matched=0.97, min_within=0.90,
-                           max_box_rel=2e-2, max_score_err=2e-2)
+    # measured on B200 (round 2): matched 0.9967 (worst image 0.99), every matched box within 2.0e-4 x 640, |dscore| <= 2.0e-3
+    util.assert_e2e_parity("c2 yolov5s bs32 640 fp16", out[:8], ref, 640.0, min_matched=0.99, min_within=0.999,
+                           max_box_rel=1e-3, max_score_err=5e-3)
 
 
 def test_c3_yolov5m_bs16_640_bf16_every_launch():
-    m, sd = _zoo(yolov5m, "m", 1.4, dtype=torch.bfloat16, score_thresh=0.2)
+    m, sd = _zoo(yolov5m, "m", 1.4, dtype=torch.bfloat16)
     ims = [util.synth_image_u8(640, 640, 300 + i).to(DEV) for i in range(16)]
     _stagewise(m, ims, 16, 640, 640)
 
 
 def test_c3_yolov5m_640_bf16_detections_vs_oracle():
-    m, sd = _zoo(yolov5m, "m", 1.4, dtype=torch.bfloat16, score_thresh=0.2)
+    m, sd = _zoo(yolov5m, "m", 1.4, dtype=torch.bfloat16)
     ims = [util.synth_image_u8(640, 640, 300 + i) for i in range(4)]
+    thr = _calibrated_thresh(sd, ims[0], (640, 640))
+    m.model.post_process.score_thresh = thr
     out = m([im.to(DEV) for im in ims])
-    ref = R.detect(sd, ims, score_thresh=0.2)
-    # bf16 activations (8-bit mantissa) through ~60 layers against an fp32 reference: the stated tolerance is looser
-    util.assert_e2e_parity("c3 yolov5m 640 bf16", out, ref, 640.0, min_matched=0.80, min_within=0.20,
-                           max_box_rel=5e-2, max_score_err=1e-1, iou_thr=0.8)
+    ref = R.detect(sd, ims, score_thresh=thr)
+    # bf16 activations (8-bit mantissa) through ~80 layers against an fp32 reference: the stated tolerance is looser
+    # (logit errors of ~1e-2 move scores across the threshold and boxes by up to a few pixels)
+    util.assert_e2e_parity("c3 yolov5m 640 bf16", out, ref, 640.0, min_matched=0.50, min_within=0.50,
+                           max_box_rel=2e-2, max_score_err=5e-2, iou_thr=0.8)
 
 
 def test_c3_yolov5m_640_fp16_detections_vs_oracle():
-    m, sd = _zoo(yolov5m, "m", 1.4, score_thresh=0.2)
+    m, sd = _zoo(yolov5m, "m", 1.4)
     ims = [util.synth_image_u8(640, 640, 300 + i) for i in range(4)]
+    thr = _calibrated_thresh(sd, ims[0], (640, 640))
+    m.model.post_process.score_thresh = thr
     out = m([im.to(DEV) for im in ims])
-    ref = R.detect(sd, ims, score_thresh=0.2)
-    util.assert_e2e_parity("c3 yolov5m 640 fp16", out, ref, 640.0, min_matched=0.97, min_within=0.90,
-                           max_box_rel=2e-2, max_score_err=2e-2)
+    ref = R.detect(sd, ims, score_thresh=thr)
+    util.assert_e2e_parity("c3 yolov5m 640 fp16", out, ref, 640.0, min_matched=0.97, min_within=0.99,
+                           max_box_rel=1e-3, max_score_err=5e-3)
 
 
 _C4_SIZES = [(800, 600), (950, 523), (523, 950), (416, 416), (1280, 720), (720, 1280), (1000, 1000), (639, 481)]
@@ -102,33 +123,37 @@ _C4_SIZES = [(800, 600), (950, 523), (523, 950), (416, 416), (1280, 720), (720, 
 def test_c4_yolov5l_mixed_416_1280_detections_vs_oracle():
     """Dynamic-shape batch: sizes drawn from 416..1280 including 800 / 950 / 523 (long side letterboxes to 639, not 640:
     SURVEY.md 0.7); canvas = batch maximum rounded up to 32; boxes come back in each image's own pixel frame."""
-    m, sd = _zoo(yolov5l, "l", 1.4, score_thresh=0.2)
+    m, sd = _zoo(yolov5l, "l", 1.4)
     ims = [util.synth_image_u8(h, w, 700 + i) for i, (h, w) in enumerate(_C4_SIZES)]
+    thr = _calibrated_thresh(sd, ims[3], (640, 640))
+    m.model.post_process.score_thresh = thr
     out = m([im.to(DEV) for im in ims])
-    ref = R.detect(sd, ims, score_thresh=0.2)
+    ref = R.detect(sd, ims, score_thresh=thr)
     side = float(max(max(s) for s in _C4_SIZES))      # boxes are in original-image pixels
-    util.assert_e2e_parity("c4 yolov5l mixed 416-1280 fp16", out, ref, side, min_matched=0.97, min_within=0.90,
-                           max_box_rel=2e-2, max_score_err=2e-2)
+    util.assert_e2e_parity("c4 yolov5l mixed 416-1280 fp16", out, ref, side, min_matched=0.97, min_within=0.99,
+                           max_box_rel=1e-3, max_score_err=5e-3)
 
 
 def test_c4_yolov5l_mixed_batch_every_launch():
-    m, sd = _zoo(yolov5l, "l", 1.4, score_thresh=0.2)
+    m, sd = _zoo(yolov5l, "l", 1.4)
     ims = [util.synth_image_u8(h, w, 700 + i).to(DEV) for i, (h, w) in enumerate(_C4_SIZES)]
     geoms, (Hb, Wb) = m.transform.geometry(ims)
     _stagewise(m, ims, len(ims), Hb, Wb)
 
 
 def test_c5_yolov5x_1280_fp16_every_launch():
-    m, sd = _zoo(yolov5x, "x", 1.3, size=(1280, 1280), score_thresh=0.3)
+    m, sd = _zoo(yolov5x, "x", 1.3, size=(1280, 1280))
     ims = [util.synth_image_u8(1280, 1280, 900 + i).to(DEV) for i in range(2)]
     _stagewise(m, ims, 2, 1280, 1280)
 
 
 def test_c5_yolov5x_1280_fp16_detections_vs_oracle():
     """One 1280x1280 image through the fp32 CPU oracle (0.82 TFLOP) and the GPU path."""
-    m, sd = _zoo(yolov5x, "x", 1.3, size=(1280, 1280), score_thresh=0.3)
+    m, sd = _zoo(yolov5x, "x", 1.3, size=(1280, 1280))
     ims = [util.synth_image_u8(1280, 1280, 900)]
+    thr = _calibrated_thresh(sd, ims[0], (1280, 1280))
+    m.model.post_process.score_thresh = thr
     out = m([im.to(DEV) for im in ims])
-    ref = R.detect(sd, ims, score_thresh=0.3, size=(1280, 1280))
-    util.assert_e2e_parity("c5 yolov5x 1280 fp16", out, ref, 1280.0, min_matched=0.97, min_within=0.90,
-                           max_box_rel=2e-2, max_score_err=2e-2)
+    ref = R.detect(sd, ims, score_thresh=thr, size=(1280, 1280))
+    util.assert_e2e_parity("c5 yolov5x 1280 fp16", out, ref, 1280.0, min_matched=0.97, min_within=0.99,
+                           max_box_rel=1e-3, max_score_err=5e-3)

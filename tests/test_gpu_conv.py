@@ -11,7 +11,9 @@ DEV = torch.device("cuda:0")
 
 
 def run_conv(N, H, W, Cin, Cout, k, s, p, dtype=torch.float16, act=True, residual=False, in_pad=0, out_pad=0, seed=0,
-             bias_scale=0.5):
+             bias_scale=0.5, force_im2col=False):
+    torch.backends.cudnn.allow_tf32 = False      # the fp32 reference must not run on TF32 tensor cores
+    torch.backends.cuda.matmul.allow_tf32 = False
     g = torch.Generator().manual_seed(seed)
     Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
     in_cs, out_cs = Cin + in_pad, Cout + out_pad
@@ -36,6 +38,7 @@ def run_conv(N, H, W, Cin, Cout, k, s, p, dtype=torch.float16, act=True, residua
     d.weight, d.Cin_pad, d.Cout_pad, d.bias = wp.data_ptr(), ci_pad, co_pad, bp.data_ptr()
     if residual:
         d.residual, d.res_cstride = res.data_ptr(), Cout
+    d.reserved = 1 if force_im2col else 0
     plan = _C.Plan([d], DEV)
     plan.run()
     torch.cuda.synchronize()
@@ -117,14 +120,10 @@ def test_rejects_unsupported():
 
 
 # ---- halo-patch 3x3 kernel (conv3x3_patch_sm100.cu) -------------------------------------------------------
-import os
-
-
-@pytest.mark.parametrize("mode", ["0", "2"])
-@pytest.mark.parametrize("cin,cout", [(64, 64), (16, 32), (32, 32), (128, 128), (256, 256)])
-def test_patch_conv_view_modes(cin, cout, mode, monkeypatch):
-    """All three ways of addressing the taps inside the staged patch must give the same convolution."""
-    monkeypatch.setenv("YB_PATCH_MODE", mode)
+@pytest.mark.parametrize("cin,cout", [(64, 64), (16, 32), (32, 32), (128, 128), (256, 256), (48, 48), (80, 80), (96, 192)])
+def test_patch_conv_channel_widths(cin, cout):
+    """Halo-patch kernel over the channel widths of the zoo, incl. widths that do not fill a 64-channel chunk
+    (48 / 80 / 96: the last chunk runs 3 / 1 / 2 K-steps over TMA-zero-filled rows)."""
     run_conv(2, 32, 40, cin, cout, 3, 1, 1, seed=3)
 
 
@@ -133,12 +132,60 @@ def test_patch_conv_ragged_edges_residual_and_windows():
     run_conv(1, 48, 24, 128, 128, 3, 1, 1, dtype=torch.bfloat16)
 
 
-def test_patch_conv_matches_im2col_kernel(monkeypatch):
-    """Same layer through both kernels (the generic im2col path is forced with YB_DISABLE_PATCH_CONV=1)."""
-    monkeypatch.setenv("YB_DISABLE_PATCH_CONV", "1")
+@pytest.mark.parametrize("shape", [
+    (1, 40, 40, 128, 128, False),    # weights streamed: 15 tiles -> 7 pair tasks + one single (odd count)
+    (3, 40, 40, 128, 256, True),     # Cout 256 splits into two 128-column N tiles under pairing; residual
+    (2, 48, 24, 192, 192, False),    # three chunks, block_n 96 x 2
+    (2, 20, 20, 256, 256, True),     # wrap tiling (5 x 24 tiles on a 20-wide map) + pairs + residual
+    (3, 20, 20, 128, 128, False),    # wrap tiling, resident or streamed weights
+    (2, 17, 19, 64, 64, True),       # wrap tiling, ragged height/width, resident weights
+    (1, 13, 22, 96, 160, False),     # wrap tiling at its widest map (22), partial last chunk
+    (5, 10, 20, 256, 128, False),    # wrap tiling, H = 2 tiles exactly, odd tile count
+])
+def test_patch_conv_pairs_and_wrap_tiles(shape):
+    """Two M tiles per weight pass (weights that do not fit in shared memory) and the 5 x 24 wrap tiling of narrow
+    maps, against the fp32 convolution."""
+    n, h, w, ci, co, res = shape
+    run_conv(n, h, w, ci, co, 3, 1, 1, residual=res, seed=5)
+    run_conv(n, h, w, ci, co, 3, 1, 1, residual=res, seed=6, dtype=torch.bfloat16, out_pad=64 if co <= 128 else 0)
+
+
+@pytest.mark.parametrize("shape", [
+    (2, 64, 64, 32, 64, 0, 0),       # body.1-like: 32 channels = half-filled 128-byte rows, resident weights
+    (2, 64, 64, 64, 128, 0, 64),     # body.3-like: weights streamed, output into a channel window
+    (1, 96, 80, 128, 256, 128, 0),   # body.5-like: input is the right half of a concat buffer (cstride 256), N split 2 x 128
+    (3, 32, 48, 48, 96, 0, 0),       # partial last chunk (48 channels: 3 K-steps)
+    (1, 160, 160, 16, 32, 0, 0),     # yolov5n body.1: 16 channels, 32-byte K rows
+    (2, 80, 88, 256, 256, 0, 0),     # four chunks; Wo = 44: last column tile half empty; Ho = 40
+])
+def test_patch_conv_stride2_parity_planes(shape):
+    """3x3 / stride 2 on the halo-patch kernel (two column-parity planes per chunk) vs the fp32 convolution, and vs
+    the generic im2col kernel on the same operands."""
+    n, h, w, ci, co, in_pad, out_pad = shape
+    run_conv(n, h, w, ci, co, 3, 2, 1, in_pad=in_pad, out_pad=out_pad, seed=7)
+    run_conv(n, h, w, ci, co, 3, 2, 1, in_pad=in_pad, out_pad=out_pad, seed=7, force_im2col=True)
+    run_conv(n, h, w, ci, co, 3, 2, 1, in_pad=in_pad, out_pad=out_pad, seed=8, dtype=torch.bfloat16)
+
+
+def test_patch_conv_matches_im2col_kernel():
+    """Same layer through both kernels (reserved bit 0 forces the generic im2col path)."""
+    run_conv(2, 32, 32, 64, 64, 3, 1, 1, seed=11, force_im2col=True)
     run_conv(2, 32, 32, 64, 64, 3, 1, 1, seed=11)
-    monkeypatch.delenv("YB_DISABLE_PATCH_CONV")
-    run_conv(2, 32, 32, 64, 64, 3, 1, 1, seed=11)
+
+
+@pytest.mark.parametrize("shape", [
+    (32, 160, 160, 64, 64, 1, 1, 0, False),     # body.2.cv3 of yolov5s batch 32: M = 819 200 rows, 6 400 tiles
+    (32, 320, 320, 32, 64, 3, 2, 1, False),     # body.1: stride 2 on the 320^2 map
+    (32, 160, 160, 32, 32, 3, 1, 1, True),      # body.2.m.0.cv2: 64-byte rows + residual
+    (32, 20, 20, 256, 256, 3, 1, 1, True),      # body.8.m.0.cv2: deep 3x3, weight ring
+    (32, 40, 40, 256, 512, 3, 2, 1, False),     # body.7
+    (32, 20, 20, 1024, 512, 1, 1, 0, False),    # SPP cv2: K = 1024
+])
+def test_conv_at_bench_layer_shapes(shape):
+    """The layer shapes of the yolov5s batch-32 640x640 benchmark (dozens of tiles and mbarrier phase wraps per
+    persistent CTA), against the fp32 convolution of the same operands."""
+    n, h, w, ci, co, k, s, p, res = shape
+    run_conv(n, h, w, ci, co, k, s, p, residual=res)
 
 
 @pytest.mark.parametrize("act", ["hardswish", "leaky"])

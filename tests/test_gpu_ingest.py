@@ -45,10 +45,10 @@ def test_predict_paths_equals_predict_tensors_and_oracle(tmp_path):
     one = m.predict(paths[0])                  # a single path string (yolov5.py:236)
     assert len(one) == 1 and one[0]["boxes"].shape[1] == 4
     ref = R.detect(sd, [d.contiguous() for d in decoded], score_thresh=0.15, size=(128, 128))
-    for a, r in zip(got, ref):
-        frac = util.match_fraction(util.to_np(a), r, iou_thr=0.9)
+    for a, r, d in zip(got, ref, decoded):
+        frac = util.match_fraction(util.to_np(a), r, iou_thr=0.9, side=max(int(v) for v in d.shape[1:]))
         print("ingest matched", round(frac, 3), len(a["scores"]), len(r["scores"]))
-        assert frac >= 0.8
+        assert frac >= 0.96      # measured 0.987 .. 1.0
 
 
 def test_custom_loader_is_respected(tmp_path):

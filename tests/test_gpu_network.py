@@ -44,9 +44,9 @@ def test_features_and_heads_vs_reference_fixture():
         mx, rr = _stats(f"head{i}", got, z[f"h{i}"])
         assert rr < 1.5e-2
     ref = util.dets_from_npz(z, 1)[0]
-    frac = util.match_fraction(util.to_np(dets[0]), ref, iou_thr=0.9)
+    frac = util.match_fraction(util.to_np(dets[0]), ref, iou_thr=0.9, side=128)
     print("network dets matched:", frac, len(dets[0]["scores"]), len(ref["scores"]))
-    assert frac >= 0.8
+    assert frac >= 0.97      # measured 0.993; matched boxes within 1e-3 x canvas (asserted inside)
 
 
 def test_per_layer_stagewise_parity_yolov5n():
@@ -79,9 +79,9 @@ def test_end_to_end_vs_reference_fixture():
     out = m(ims)
     for got, ref in zip(out, util.dets_from_npz(z, 2)):
         got = util.to_np(got)
-        frac = util.match_fraction(got, ref, iou_thr=0.9)
+        frac = util.match_fraction(got, ref, iou_thr=0.9, side=128)
         print("e2e matched fraction:", frac, "n_got", len(got["scores"]), "n_ref", len(ref["scores"]))
-        assert frac >= 0.8
+        assert frac >= 0.97      # measured 1.0 / 0.997
     # float inputs in [0,1] (the reference's own input contract) give the same detections as uint8 inputs
     # (the CUDA `/255` may differ from the CPU LUT by 1 ulp, so near-tied scores may swap places)
     out_f = m([im.float() / 255.0 for im in ims])
@@ -108,9 +108,9 @@ def test_mixed_size_batch_vs_oracle():
     out = m([im.to(DEV) for im in ims])
     for got, want, im in zip(out, ref, ims):
         got = util.to_np(got)
-        frac = util.match_fraction(got, want, iou_thr=0.9)
+        frac = util.match_fraction(got, want, iou_thr=0.9, side=128)
         print("mixed batch", tuple(im.shape[1:]), "matched", frac, len(got["scores"]), len(want["scores"]))
-        assert frac >= 0.8
+        assert frac >= 0.95      # measured 0.977 .. 1.0 (300 detections cut out of a dense, near-tied candidate set)
 
 
 def test_bf16_model_end_to_end():
@@ -122,7 +122,7 @@ def test_bf16_model_end_to_end():
     for got, ref in zip(out, util.dets_from_npz(z, 2)):
         frac = util.match_fraction(util.to_np(got), ref, iou_thr=0.8)
         print("bf16 e2e matched fraction:", frac)
-        assert frac >= 0.5      # bf16 activations: 8 mantissa bits through ~25 layers
+        assert frac >= 0.93     # measured 0.963 / 0.99; bf16 activations: 8 mantissa bits through ~25 layers
 
 
 def test_fused_head_decode_equals_unfused(monkeypatch):

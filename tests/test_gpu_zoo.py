@@ -33,7 +33,7 @@ def _check_dets(m, sd, ims, min_frac, iou=0.9, **kw):
     ref = R.detect(sd, ims, **kw)
     out = m([im.to(DEV) for im in ims])
     for got, want, im in zip(out, ref, ims):
-        frac = util.match_fraction(util.to_np(got), want, iou_thr=iou)
+        frac = util.match_fraction(util.to_np(got), want, iou_thr=iou, side=max(im.shape[1:]))
         print(tuple(im.shape[1:]), "matched", round(frac, 3), len(got["scores"]), len(want["scores"]))
         assert len(want["scores"]) > 0
         assert frac >= min_frac
@@ -85,19 +85,19 @@ def test_yolov5m_bf16_heads():
 def test_yolov5m_detections():
     m, sd = _build(yolov5m, "m", _STABLE["m"], size=(160, 160), score_thresh=0.2)
     ims = [util.synth_image_u8(120, 160, 1), util.synth_image_u8(160, 96, 2)]
-    _check_dets(m, sd, ims, 0.8, score_thresh=0.2, size=(160, 160))
+    _check_dets(m, sd, ims, 0.93, score_thresh=0.2, size=(160, 160))      # measured 0.95 / 0.99
 
 
 def test_yolov5l_detections_mixed_sizes():
     m, sd = _build(yolov5l, "l", _STABLE["l"], size=(192, 192), score_thresh=0.2)
     ims = [util.synth_image_u8(h, w, 10 + i) for i, (h, w) in enumerate([(150, 192), (192, 100), (97, 131)])]
-    _check_dets(m, sd, ims, 0.8, score_thresh=0.2, size=(192, 192))
+    _check_dets(m, sd, ims, 0.96, score_thresh=0.2, size=(192, 192))      # measured 0.98 .. 0.993
 
 
 def test_yolov5x_detections():
     m, sd = _build(yolov5x, "x", _STABLE["x"], size=(128, 128), score_thresh=0.2)
     ims = [util.synth_image_u8(128, 128, 5)]
-    _check_dets(m, sd, ims, 0.8, score_thresh=0.2, size=(128, 128))
+    _check_dets(m, sd, ims, 0.97, score_thresh=0.2, size=(128, 128))      # measured 1.0
 
 
 def test_yolov5x_1280_canvas_runs():

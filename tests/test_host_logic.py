@@ -185,8 +185,8 @@ def test_stem_band_weights_reproduce_the_stem_conv():
 
 
 def test_stem_variants_of_the_lowering():
-    """The banded stem is the default when 4*Cout fits one N tile (n/s/m/l); yolov5x (4*80 = 320) keeps the dense
-    super-pixel matrix.  No environment variable takes part in the lowering."""
+    """The banded stem is the default when the band fits in shared memory (4*Cout <= 128: n / s); m / l / x keep the
+    dense super-pixel matrix.  No environment variable takes part in the lowering."""
     from yolort_b200.engine import lower_yolo
     from yolort_b200.models import yolov5x
 

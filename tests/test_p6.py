@@ -120,9 +120,9 @@ def test_gpu_end_to_end_vs_reference_fixture_p6():
     ims = [torch.from_numpy(z["img0"]).to(DEV), torch.from_numpy(z["img1"]).to(DEV)]
     out = m(ims)
     for got, ref in zip(out, util.dets_from_npz(z, 2)):
-        frac = util.match_fraction(util.to_np(got), ref, iou_thr=0.9)
+        frac = util.match_fraction(util.to_np(got), ref, iou_thr=0.9, side=192)
         print("p6 e2e matched:", frac, len(got["scores"]), len(ref["scores"]))
-        assert frac >= 0.8
+        assert frac >= 0.95      # measured 0.973 / 0.997; matched boxes within 1e-3 x canvas
 
 
 @pytest.mark.gpu

@@ -129,7 +129,7 @@ def test_gpu_heads_vs_reference_fixture_v4(tag, ver):
     ref = util.dets_from_npz(z, 1)[0]
     frac = util.match_fraction(util.to_np(dets[0]), ref, iou_thr=0.9)
     print(tag, "network dets matched:", frac)
-    assert frac >= 0.8
+    assert frac >= 0.97      # measured 0.993 / 1.0
 
 
 @pytest.mark.gpu
@@ -142,4 +142,4 @@ def test_gpu_end_to_end_vs_reference_fixture_v4(tag, ver):
     for got, ref in zip(out, util.dets_from_npz(z, 2)):
         frac = util.match_fraction(util.to_np(got), ref, iou_thr=0.9)
         print(tag, "e2e matched:", frac, len(got["scores"]), len(ref["scores"]))
-        assert frac >= 0.8
+        assert frac >= 0.95      # measured 0.973 .. 1.0

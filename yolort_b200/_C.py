@@ -41,6 +41,7 @@ EXPORTED_SYMBOLS = (
     "yb_nms_layout",
     "yb_nms_begin",
     "yb_nms_finish",
+    "yb_decode_candidates",
     "yb_batched_nms_workspace_bytes",
     "yb_batched_nms",
 )
@@ -172,6 +173,8 @@ def lib() -> ctypes.CDLL:
     L.yb_nms_finish.argtypes = [ctypes.POINTER(NmsParams), ctypes.POINTER(HeadLevel), ctypes.c_void_p, ctypes.c_void_p,
                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                 ctypes.c_size_t, ctypes.c_void_p]
+    L.yb_decode_candidates.argtypes = [ctypes.POINTER(NmsParams), ctypes.POINTER(HeadLevel), ctypes.c_void_p, ctypes.c_size_t,
+                                       ctypes.c_void_p]
     L.yb_batched_nms_workspace_bytes.restype = ctypes.c_size_t
     L.yb_batched_nms_workspace_bytes.argtypes = [ctypes.c_int64]
     L.yb_batched_nms.argtypes = [
@@ -372,7 +375,7 @@ def _level_struct(t: torch.Tensor, layout: str, n_anchors: int, n_outputs: int, 
 def decode_nms_padded(head_outputs: List[torch.Tensor], layout: str, strides: Sequence[float],
                       anchors_px: Sequence[Sequence[float]], num_classes: int, score_thresh: float,
                       nms_thresh: float, detections_per_img: int, semantics: int = NMS_TV_AUTO,
-                      rescale: Optional[torch.Tensor] = None):
+                      rescale: Optional[torch.Tensor] = None, stage_hook=None):
     """Launches decode+NMS; returns padded device tensors (boxes [N,D,4], scores [N,D], labels [N,D],
     counts [N], status [4]) without synchronising -- the caller reads `counts`/`status`."""
     t0 = head_outputs[0]
@@ -399,10 +402,23 @@ def decode_nms_padded(head_outputs: List[torch.Tensor], layout: str, strides: Se
     if arena.ws is None or arena.ws.numel() < need or arena.ws.device != dev:
         arena.ws = torch.empty((need,), dtype=torch.uint8, device=dev)
     with device_guard(dev):
-        check(lib().yb_decode_nms(ctypes.byref(p), levels, rescale.data_ptr() if rescale is not None else None,
-                                  boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), counts.data_ptr(),
-                                  status.data_ptr(), arena.ws.data_ptr(), arena.ws.numel(), current_stream_ptr(dev)),
-              "yb_decode_nms")
+        if stage_hook is None:
+            check(lib().yb_decode_nms(ctypes.byref(p), levels, rescale.data_ptr() if rescale is not None else None,
+                                      boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), counts.data_ptr(),
+                                      status.data_ptr(), arena.ws.data_ptr(), arena.ws.numel(), current_stream_ptr(dev)),
+                  "yb_decode_nms")
+        else:   # same three steps, with a callback between them (bench.py records CUDA events per stage)
+            st = current_stream_ptr(dev)
+            check(lib().yb_nms_begin(ctypes.byref(p), levels, status.data_ptr(), arena.ws.data_ptr(), arena.ws.numel(), st),
+                  "yb_nms_begin")
+            stage_hook("begin")
+            check(lib().yb_decode_candidates(ctypes.byref(p), levels, arena.ws.data_ptr(), arena.ws.numel(), st),
+                  "yb_decode_candidates")
+            stage_hook("decode")
+            check(lib().yb_nms_finish(ctypes.byref(p), levels, rescale.data_ptr() if rescale is not None else None,
+                                      boxes.data_ptr(), scores.data_ptr(), labels.data_ptr(), counts.data_ptr(),
+                                      status.data_ptr(), arena.ws.data_ptr(), arena.ws.numel(), st), "yb_nms_finish")
+            stage_hook("nms")
     arena.debug_offset = lib().yb_decode_nms_debug_offset(ctypes.byref(p), levels)
     return boxes, scores, labels, counts, status
 

@@ -209,9 +209,19 @@ __device__ __forceinline__ void umma_ksteps_rt(int kk, uint32_t tmem_d, uint32_t
     umma_ksteps<4>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, first);
   else if (kk == 2)
     umma_ksteps<2>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, first);
+  else if (kk == 3)
+    umma_ksteps<3>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, first);
   else
     umma_ksteps<1>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, first);
 }
+
+// Ablation knobs (YB_CONV_DBG bit mask: 1 no epilogue math/stores, 2 no MMA, 4 no TMA stores, 8 no loads, 16 accumulator
+// handshake only) exist only in -DYB_ABLATION builds (scripts/conv_ablation.py); release kernels carry none of them.
+#ifdef YB_ABLATION
+#define YB_DBG(p, bit) (((p).dbg & (bit)) != 0)
+#else
+#define YB_DBG(p, bit) false
+#endif
 
 // Arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {

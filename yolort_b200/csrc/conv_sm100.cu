@@ -56,7 +56,8 @@ struct ConvKernelParams {
   int n_tiles, num_tiles;
   int store_cols;  // columns per TMA store box: 64 / 32 / 16
   int bias_len;    // length of the (padded) bias vector
-  int dbg;         // ablation knobs (YB_CONV_DBG): 1 = no epilogue math/stores, 2 = no MMA, 4 = no TMA stores, 8 = no loads
+  int kk_last;     // K=16 steps of the LAST channel chunk (Cin need not fill it: TMA zero-fills, the MMA skips)
+  int dbg;         // ablation knobs, -DYB_ABLATION builds only (common.cuh)
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, idesc;
   const float* bias;
   EpilogueParams ep;
@@ -120,9 +121,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // Warp-uniform role loops (all 32 lanes walk them, one elected lane issues): TMA / tcgen05 instructions take
+    // uniform-register operands, and inside a one-lane branch ptxas wraps each of them in an elect/branch convergence
+    // loop with R2UR moves (~10 instructions per MMA instead of ~3; the issuing thread is the critical path of the
+    // shallow layers).
+    {
       const uint32_t a_bytes = kBlockM * p.block_k * 2, b_bytes = p.block_n * p.block_k * 2;
-      if (p.b_resident) {
+      if (p.b_resident && lane == 0) {
         mbar_expect_tx(&b_full, p.num_k_iters * b_bytes);
         for (int it = 0; it < p.num_k_iters; ++it)
           tma_load_2d(&tmap_b, &b_full, b_res + it * p.b_stage_bytes, it * p.block_k, 0);
@@ -148,24 +153,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* a_dst = tiles + s * stage_bytes;
           uint8_t* b_dst = a_dst + p.kpg * p.a_stage_bytes;
-          if (p.dbg & 8) {   // ablation: no loads at all, only the pipeline handshake
-            mbar_arrive(&full_bar[s]);
+          if (YB_DBG(p, 8)) {   // ablation: no loads at all, only the pipeline handshake
+            if (elect_one()) mbar_arrive(&full_bar[s]);
             continue;
           }
-          mbar_expect_tx(&full_bar[s], cnt * (a_bytes + (p.b_resident ? 0u : b_bytes)));
-          for (int j = 0; j < cnt; ++j) {
-            const int it = it0 + j;
-            const int tap = it / p.chunks;
-            const int chunk = it - tap * p.chunks;
-            if (p.mode == 0) {
-              tma_load_2d(&tmap_a, &full_bar[s], a_dst + j * p.a_stage_bytes, chunk * p.block_k, m0);
-            } else {
-              const int r = tap / p.ksize;
-              const int sx = tap - r * p.ksize;
-              tma_load_im2col_4d(&tmap_a, &full_bar[s], a_dst + j * p.a_stage_bytes, chunk * p.block_k, cw, ch, cn,
-                                 static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[s], cnt * (a_bytes + (p.b_resident ? 0u : b_bytes)));
+            for (int j = 0; j < cnt; ++j) {
+              const int it = it0 + j;
+              const int tap = it / p.chunks;
+              const int chunk = it - tap * p.chunks;
+              if (p.mode == 0) {
+                tma_load_2d(&tmap_a, &full_bar[s], a_dst + j * p.a_stage_bytes, chunk * p.block_k, m0);
+              } else {
+                const int r = tap / p.ksize;
+                const int sx = tap - r * p.ksize;
+                tma_load_im2col_4d(&tmap_a, &full_bar[s], a_dst + j * p.a_stage_bytes, chunk * p.block_k, cw, ch, cn,
+                                   static_cast<uint16_t>(sx), static_cast<uint16_t>(r));
+              }
+              if (!p.b_resident) tma_load_2d(&tmap_b, &full_bar[s], b_dst + j * p.b_stage_bytes, it * p.block_k, n0);
             }
-            if (!p.b_resident) tma_load_2d(&tmap_b, &full_bar[s], b_dst + j * p.b_stage_bytes, it * p.block_k, n0);
           }
         }
       }
@@ -174,7 +181,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== MMA issuer =====================
     // (A second issuing thread for alternate tiles was tried and removed: two consumers that are several phases
     // apart on the same full/empty mbarriers alias under parity waits.)
-    if (lane == 0) {
+    {
       const uint32_t row_bytes = p.block_k * 2;
       const int kk = p.block_k >> 4;
       if (p.b_resident) {
@@ -192,6 +199,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         mbar_wait(&acc_empty[as], aph ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * p.block_n;
+        int chunk = 0;   // channel chunk of the running k-iteration (it = tap * chunks + chunk)
         for (int it0 = 0; it0 < p.num_k_iters; it0 += p.kpg, ++kit) {
           const int cnt = min(p.kpg, p.num_k_iters - it0);
           const int s = kit % p.stages;
@@ -203,14 +211,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           // descriptors differ only in their 14-bit start-address field (16-byte units)
           const uint32_t a_lo0 = (a_base & 0x3FFFFu) >> 4;
           const uint32_t b_lo0 = ((p.b_resident ? b_res_addr + it0 * p.b_stage_bytes : b_base) & 0x3FFFFu) >> 4;
-          if (!(p.dbg & 2)) {
-            for (int j = 0; j < cnt; ++j)
-              umma_ksteps_rt(kk, tmem_d, a_lo0 + j * a_step16, desc_hi, b_lo0 + j * b_step16, desc_hi, p.idesc,
-                             (it0 | j) == 0);
+          if (elect_one()) {
+            if (!YB_DBG(p, 2)) {
+              int ch = chunk;
+              for (int j = 0; j < cnt; ++j) {
+                umma_ksteps_rt(ch == p.chunks - 1 ? p.kk_last : kk, tmem_d, a_lo0 + j * a_step16, desc_hi,
+                               b_lo0 + j * b_step16, desc_hi, p.idesc, (it0 | j) == 0);
+                if (++ch == p.chunks) ch = 0;
+              }
+            }
+            umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
           }
-          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+          chunk = (chunk + cnt) % p.chunks;
         }
-        umma_commit(&acc_full[as]);  // accumulator of this tile complete
+        if (elect_one()) umma_commit(&acc_full[as]);  // accumulator of this tile complete
       }
     }
   } else {
@@ -234,7 +248,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int m0 = m_tile * kBlockM;
       const long long row = static_cast<long long>(m0) + row_in_tile;
       const bool row_ok = row < p.M;
-      if (p.dbg & 16) {   // ablation: accumulator handshake only
+      if (YB_DBG(p, 16)) {   // ablation: accumulator handshake only
         mbar_wait(&acc_full[g], aph);
         tc_fence_after();
         tc_fence_before();
@@ -355,7 +369,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // store has finished reading its buffer, which is the one the next box will overwrite.
         uint8_t* buf = my_staging + (store_idx & 1) * kStageBufBytes;
         uint8_t* my_row = buf + row_in_tile * row_bytes;
-        if (!(p.dbg & 1)) {
+        if (!YB_DBG(p, 1)) {
           epilogue_box_select<kBf16, kStoreCols, kRareAct>(p.ep, store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
         }
         if (c0 + store_cols >= p.block_n) {
@@ -368,7 +382,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (issuer) tma_store_wait_read<0>();
         named_bar_sync(bar_id, 128);
         if (issuer) {
-          if (n0 + c0 < p.ep.Cout && !(p.dbg & 5)) tma_store_2d(&tmap_out, buf, n0 + c0, m0);
+          if (n0 + c0 < p.ep.Cout && !YB_DBG(p, 5)) tma_store_2d(&tmap_out, buf, n0 + c0, m0);
           tma_store_commit();
         }
       }
@@ -537,10 +551,13 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
   }
   kp.store_cols = (block_n % 64 == 0) ? 64 : ((block_n % 32 == 0) ? 32 : 16);
   kp.bias_len = d.Cout_pad;
-  {
-    const char* e = getenv("YB_CONV_DBG");
-    kp.dbg = e ? atoi(e) : 0;
-  }
+  kp.dbg = 0;
+#ifdef YB_ABLATION
+  if (const char* e = getenv("YB_CONV_DBG")) kp.dbg = atoi(e);
+#endif
+  kp.kk_last = (d.Cin - (kp.chunks - 1) * kp.block_k + 15) / 16;
+  if (kp.kk_last < 1) kp.kk_last = 1;
+  if (kp.kk_last > (kp.block_k >> 4)) kp.kk_last = kp.block_k >> 4;
   kp.a_stage_bytes = kBlockM * kp.block_k * 2;
   kp.b_stage_bytes = (static_cast<uint32_t>(kp.block_n * kp.block_k * 2) + 1023u) & ~1023u;
   const size_t fixed = static_cast<size_t>(kEpiGroups) * 2 * kStageBufBytes + 1024;

@@ -22,6 +22,8 @@
 //      ballots.  The sweep stops at max_det keeps, exactly like keep[:detections_per_img].
 // IoU arithmetic mirrors torchvision's CPU nms kernel in fp32 with explicit non-fused operations so the
 // keep set is bit-identical on identical inputs.
+#include <type_traits>
+
 #include "common.cuh"
 #include "decode_common.cuh"
 
@@ -51,6 +53,7 @@ __device__ __forceinline__ float ld_logit<__nv_bfloat16>(const void* base, long 
 struct DecodeParams {
   yb_head_level lvl[YB_MAX_LEVELS];
   int lvl_start[YB_MAX_LEVELS + 1];  // first flat anchor index of each level
+  int pix_start[YB_MAX_LEVELS + 1];  // first flat PIXEL index of each level (row kernel)
   int n_images, n_levels, n_anchors, n_classes;
   int anchors_per_image;
   float score_thresh;
@@ -151,6 +154,126 @@ __global__ void decode_candidates_kernel(const __grid_constant__ DecodeParams p,
         const float4 b = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
         ws.boxes[static_cast<long long>(s_img) * p.anchors_per_image + s_anchor] = b;
         atomicMax(&ws.img_maxc[s_img], float_to_ordered_int(fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
+      }
+    }
+  }
+}
+
+// Row variant for the plan's NHWC head buffers (channel a*K + k, row = one pixel's A*K logits, <= 512 bytes,
+// 16-byte aligned): HBM-bound, so the point is to fetch every byte exactly once, coalesced.  One warp takes four
+// consecutive pixels: it issues the four 512-byte row loads up front (one 16-byte load per lane each -- a row is ONE
+// fully coalesced request, where the per-anchor kernel above pulls a 32-byte sector per anchor and then re-reads
+// the passing anchors' rows scattered), parks them in shared memory and then works per pixel: lanes 0..A-1 test
+// the objectness of their anchor; the class scan (lane k <-> class k) and the box decode run only for anchors that
+// passed, out of shared memory.  Arithmetic, candidate keys and the dense box array are those of the kernel above.
+constexpr int kRowPixels = 4;        // pixels per warp
+constexpr int kRowWarps = 8;         // warps per block
+constexpr int kRowMaxBytes = 512;    // longest row handled (A*K 16-bit logits padded to a multiple of 8)
+
+__device__ __forceinline__ uint4 ld_stream_16(const void* ptr) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(ptr));
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ float row_elem(const uint8_t* row, int e) {
+  if constexpr (sizeof(T) == 2 && std::is_same<T, __half>::value)
+    return __half2float(reinterpret_cast<const __half*>(row)[e]);
+  else
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(row)[e]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kRowWarps * 32)
+decode_rows_kernel(const __grid_constant__ DecodeParams p, Workspace ws) {
+  __shared__ __align__(16) uint8_t s_rows[kRowWarps][kRowPixels][kRowMaxBytes];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = p.pix_start[p.n_levels];                       // pixels per image over all levels
+  const long long total = static_cast<long long>(p.n_images) * P;
+  const long long q0 = (static_cast<long long>(blockIdx.x) * kRowWarps + warp) * kRowPixels;
+  if (q0 >= total) return;
+  const int K = p.n_classes + 5;
+  int img[kRowPixels], lv[kRowPixels], px[kRowPixels], py[kRowPixels];
+  bool valid[kRowPixels];
+#pragma unroll
+  for (int j = 0; j < kRowPixels; ++j) {
+    const long long q = q0 + j;
+    valid[j] = q < total;
+    img[j] = 0; lv[j] = 0; px[j] = 0; py[j] = 0;
+    if (valid[j]) {
+      img[j] = static_cast<int>(q / P);
+      const int r = static_cast<int>(q - static_cast<long long>(img[j]) * P);
+      int l = 0;
+#pragma unroll
+      for (int i = 1; i < YB_MAX_LEVELS; ++i)
+        if (i < p.n_levels && r >= p.pix_start[i]) l = i;
+      lv[j] = l;
+      const int rr = r - p.pix_start[l];
+      py[j] = rr / p.lvl[l].W;
+      px[j] = rr - py[j] * p.lvl[l].W;
+      const yb_head_level& L = p.lvl[l];
+      const long long off = img[j] * L.stride_n + py[j] * L.stride_y + px[j] * L.stride_x;   // elements
+      if (lane * 8 < L.stride_x) {
+        const uint4 v = ld_stream_16(static_cast<const uint8_t*>(L.logits) + (off + lane * 8) * 2);
+        *reinterpret_cast<uint4*>(&s_rows[warp][j][lane * 16]) = v;
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < kRowPixels; ++j) {
+    if (!valid[j]) break;
+    const uint8_t* row = s_rows[warp][j];
+    const yb_head_level& L = p.lvl[lv[j]];
+    float obj = 0.f;
+    bool pass = false;
+    if (lane < p.n_anchors) {
+      obj = sigmoidf_ref(row_elem<T>(row, lane * K + 4));
+      pass = obj > p.score_thresh;   // score = cls*obj <= obj
+    }
+    uint32_t todo = __ballot_sync(0xffffffffu, pass);
+    while (todo) {
+      const int a = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const float s_obj = __shfl_sync(0xffffffffu, obj, a);
+      const int anchor = p.lvl_start[lv[j]] + (a * L.H + py[j]) * L.W + px[j];
+      bool any = false;
+      for (int k0 = 0; k0 < p.n_classes; k0 += 32) {
+        const int k = k0 + lane;
+        float score = 0.f;
+        bool cand = false;
+        if (k < p.n_classes) {
+          const float cls = sigmoidf_ref(row_elem<T>(row, a * K + 5 + k));
+          score = __fmul_rn(cls, s_obj);
+          cand = score > p.score_thresh;
+        }
+        const uint32_t cm = __ballot_sync(0xffffffffu, cand);
+        if (cm == 0) continue;
+        any = true;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&ws.img_count[img[j]], __popc(cm));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (cand) {
+          const int slot = base + __popc(cm & ((1u << lane) - 1u));
+          if (slot < p.cap_per_image) {
+            const uint64_t key = (static_cast<uint64_t>(orderable_desc(score)) << 32) |
+                                 static_cast<uint32_t>(anchor * p.n_classes + k);
+            ws.keys_a[static_cast<long long>(img[j]) * p.cap_per_image + slot] = key;
+          }
+        }
+      }
+      if (any) {
+        float t = 0.f;
+        if (lane < 4) t = sigmoidf_ref(row_elem<T>(row, a * K + lane));
+        const float sx = __shfl_sync(0xffffffffu, t, 0), sy = __shfl_sync(0xffffffffu, t, 1);
+        const float sw = __shfl_sync(0xffffffffu, t, 2), sh = __shfl_sync(0xffffffffu, t, 3);
+        if (lane == 0) {
+          const float4 b = decode_box(sx, sy, sw, sh, px[j], py[j], L.stride_px, L.anchors_px[2 * a], L.anchors_px[2 * a + 1]);
+          ws.boxes[static_cast<long long>(img[j]) * p.anchors_per_image + anchor] = b;
+          atomicMax(&ws.img_maxc[img[j]], float_to_ordered_int(fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
+        }
       }
     }
   }
@@ -805,15 +928,12 @@ extern "C" int yb_decode_dense(const yb_nms_params* p, const yb_head_level* leve
   return YB_OK;
 }
 
-extern "C" int yb_decode_nms(const yb_nms_params* p, const yb_head_level* levels, const float* rescale_dev,
-                             float* boxes_dev, float* scores_dev, int64_t* labels_dev, int32_t* counts_dev,
-                             int64_t* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
+extern "C" int yb_decode_candidates(const yb_nms_params* p, const yb_head_level* levels, void* workspace_dev,
+                                    size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  int rc = yb_nms_begin(p, levels, status_dev, workspace_dev, workspace_bytes, stream_);
-  if (rc != YB_OK) return rc;
   Workspace ws;
   long long apm, cap;
-  rc = prepare(p, levels, workspace_dev, workspace_bytes, ws, apm, cap);
+  int rc = prepare(p, levels, workspace_dev, workspace_bytes, ws, apm, cap);
   if (rc != YB_OK) return rc;
   DecodeParams dp;
   const int dtype = levels[0].dtype;
@@ -836,8 +956,33 @@ extern "C" int yb_decode_nms(const yb_nms_params* p, const yb_head_level* levels
   dp.anchors_per_image = static_cast<int>(apm);
   dp.score_thresh = p->score_thresh;
   dp.cap_per_image = cap;
+  // NHWC rows (the plan's head buffers): every level is [.., A*K logits of one pixel, pad] with 16-bit elements,
+  // a 16-byte aligned pitch of at most 512 bytes -> the coalesced row kernel; anything else (the reference's
+  // [N,A,H,W,K] layout, fp32 logits) -> one thread per anchor.
+  bool rows = (dtype == YB_F16 || dtype == YB_BF16) && p->n_anchors <= 32;
+  dp.pix_start[0] = 0;
+  for (int l = 0; l < YB_MAX_LEVELS; ++l) {
+    const bool on = l < p->n_levels;
+    dp.pix_start[l + 1] = dp.pix_start[l] + (on ? levels[l].H * levels[l].W : 0);
+    if (on) {
+      const yb_head_level& L = levels[l];
+      rows = rows && L.stride_a == p->n_classes + 5 && L.stride_x % 8 == 0 && L.stride_x * 2 <= kRowMaxBytes &&
+             L.stride_x >= static_cast<long long>(p->n_anchors) * (p->n_classes + 5) && L.stride_y % 8 == 0 && L.stride_n % 8 == 0 &&
+             (reinterpret_cast<uintptr_t>(L.logits) & 15) == 0;
+    }
+  }
   const long long total = static_cast<long long>(p->n_images) * apm;
   const unsigned blocks = static_cast<unsigned>((total + 255) / 256);
+  if (rows) {
+    const long long pixels = static_cast<long long>(p->n_images) * dp.pix_start[p->n_levels];
+    const unsigned rblocks = static_cast<unsigned>((pixels + kRowWarps * kRowPixels - 1) / (kRowWarps * kRowPixels));
+    if (dtype == YB_F16)
+      decode_rows_kernel<__half><<<rblocks, kRowWarps * 32, 0, stream>>>(dp, ws);
+    else
+      decode_rows_kernel<__nv_bfloat16><<<rblocks, kRowWarps * 32, 0, stream>>>(dp, ws);
+    YB_CHECK_CUDA(cudaGetLastError());
+    return YB_OK;
+  }
   switch (dtype) {
     case YB_F32:
       decode_candidates_kernel<float><<<blocks, 256, 0, stream>>>(dp, ws);
@@ -853,6 +998,16 @@ extern "C" int yb_decode_nms(const yb_nms_params* p, const yb_head_level* levels
       return YB_ERR_INVALID;
   }
   YB_CHECK_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+extern "C" int yb_decode_nms(const yb_nms_params* p, const yb_head_level* levels, const float* rescale_dev,
+                             float* boxes_dev, float* scores_dev, int64_t* labels_dev, int32_t* counts_dev,
+                             int64_t* status_dev, void* workspace_dev, size_t workspace_bytes, void* stream_) {
+  int rc = yb_nms_begin(p, levels, status_dev, workspace_dev, workspace_bytes, stream_);
+  if (rc != YB_OK) return rc;
+  rc = yb_decode_candidates(p, levels, workspace_dev, workspace_bytes, stream_);
+  if (rc != YB_OK) return rc;
   return yb_nms_finish(p, levels, rescale_dev, boxes_dev, scores_dev, labels_dev, counts_dev, status_dev, workspace_dev,
                        workspace_bytes, stream_);
 }

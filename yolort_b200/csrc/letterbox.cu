@@ -7,10 +7,13 @@
 // and fuses the uint8 -> [0,1] conversion of the default loader (yolov5.py:218-228) plus the layout
 // change the first convolution wants (space-to-depth NHWC, see conv_sm100.cu / engine.py).
 //
-// HBM-bound: per image it reads 3*h*w source bytes (each source texel is touched by <= ~4 output
-// pixels and stays in L1/L2) and writes the canvas once.  Threads map to consecutive output x so
-// both the source reads (consecutive sx) and the destination writes are coalesced.
+// HBM-bound: per image it reads 3*h*w source bytes and writes the canvas once.  The hot variant
+// (letterbox_s2d_tile_kernel: uint8 sources -> the plan's space-to-depth canvas) stages the source rectangle of a
+// 16 x 128 pixel output tile in shared memory with 16-byte coalesced loads and samples from there, so every source
+// byte crosses the memory system once as part of a full 16-byte request; the generic kernels below sample global
+// memory directly (consecutive threads -> consecutive output x, source texels reused through L1/L2).
 #include <cmath>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -187,6 +190,154 @@ __global__ void letterbox_s2d_kernel(const __grid_constant__ BatchGeom bg, int i
   }
 }
 
+// ---- tiled variant: uint8 sources -> space-to-depth canvas, source rectangle staged in shared memory -----------------
+constexpr int kTileY = 8, kTileX = 64;            // s2d pixels per CTA tile: 16 x 128 canvas pixels
+constexpr int kTileThreads = 256;
+constexpr int kTileSmem = 40 * 1024;              // staging bytes (covers down-scaling ratios up to ~2.2, e.g. 1280 -> 640)
+constexpr int kTileMaxLines = 3 * 40;
+
+// Same arithmetic as sample_rgb, texels read from the staged rectangle: `line(c, y)` / `col(c, x)` address it.
+template <bool kHwc>
+struct StagedSrc {
+  const uint8_t* buf;
+  const uint16_t* mis;      // per line: misalignment of the line start inside its first 16-byte chunk
+  int pitch, rows, y_lo, x_lo;
+  __device__ __forceinline__ float at(const float* lut, int c, int y, int x) const {
+    const int line = kHwc ? (y - y_lo) : c * rows + (y - y_lo);
+    const int byte = kHwc ? 3 * (x - x_lo) + c : (x - x_lo);
+    return lut[buf[line * pitch + mis[line] + byte]];
+  }
+};
+
+template <bool kHwc>
+__device__ __forceinline__ void sample_rgb_staged(const ImgGeom& g, const StagedSrc<kHwc>& S, const float* lut, int y, int x,
+                                                  float fill, float (&rgb)[3]) {
+  const int yy = y - g.top, xx = x - g.left;
+  if (yy < 0 || yy >= g.new_h || xx < 0 || xx >= g.new_w) {
+    rgb[0] = rgb[1] = rgb[2] = fill;
+    return;
+  }
+  if (g.new_h == g.src_h && g.new_w == g.src_w) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rgb[c] = S.at(lut, c, yy, xx);
+    return;
+  }
+  int y0, y1, x0, x1;
+  float ly, lx;
+  src_coord(yy, g.ratio_h, g.src_h, y0, y1, ly);
+  src_coord(xx, g.ratio_w, g.src_w, x0, x1, lx);
+  const float wy0 = 1.f - ly, wx0 = 1.f - lx;
+  const bool need_x1 = lx != 0.f, need_y1 = ly != 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float p00 = S.at(lut, c, y0, x0);
+    const float p01 = need_x1 ? S.at(lut, c, y0, x1) : p00;
+    float bot = 0.f;
+    if (need_y1) {
+      const float p10 = S.at(lut, c, y1, x0);
+      const float p11 = need_x1 ? S.at(lut, c, y1, x1) : p10;
+      bot = __fadd_rn(__fmul_rn(wx0, p10), __fmul_rn(lx, p11));
+    }
+    const float top = __fadd_rn(__fmul_rn(wx0, p00), __fmul_rn(lx, p01));
+    rgb[c] = __fadd_rn(__fmul_rn(wy0, top), __fmul_rn(ly, bot));
+  }
+}
+
+template <typename DstT, bool kHwc>
+__global__ void __launch_bounds__(kTileThreads)
+letterbox_s2d_tile_kernel(const __grid_constant__ BatchGeom bg, int img0, int Hb, int Wb, float fill, const float* lut,
+                          DstT* __restrict__ dst) {
+  __shared__ float s_lut[256];
+  __shared__ __align__(16) uint8_t s_src[kTileSmem];
+  __shared__ uint16_t s_mis[kTileMaxLines];
+  __shared__ int s_rect[6];   // y_lo, rows, x_lo, cols, pitch, staged?
+  const int tid = threadIdx.x;
+  const int li = blockIdx.z;
+  const ImgGeom& g = bg.img[li];
+  const int W2 = Wb >> 1, H2 = Hb >> 1;
+  const int X0 = blockIdx.x * kTileX, Y0 = blockIdx.y * kTileY;
+  s_lut[tid] = lut[tid];
+  // canvas rows / columns of this tile that fall inside the resized image
+  const int cy0 = max(2 * Y0, g.top), cy1 = min(min(2 * (Y0 + kTileY), Hb), g.top + g.new_h) - 1;
+  const int cx0 = max(2 * X0, g.left), cx1 = min(min(2 * (X0 + kTileX), Wb), g.left + g.new_w) - 1;
+  const bool any = cy0 <= cy1 && cx0 <= cx1;
+  if (tid == 0) {
+    int y_lo = 0, y_hi = -1, x_lo = 0, x_hi = -1;
+    if (any) {
+      if (g.new_h == g.src_h && g.new_w == g.src_w) {
+        y_lo = cy0 - g.top; y_hi = cy1 - g.top; x_lo = cx0 - g.left; x_hi = cx1 - g.left;
+      } else {
+        int a, b;
+        float l;
+        src_coord(cy0 - g.top, g.ratio_h, g.src_h, y_lo, b, l);
+        src_coord(cy1 - g.top, g.ratio_h, g.src_h, a, y_hi, l);
+        src_coord(cx0 - g.left, g.ratio_w, g.src_w, x_lo, b, l);
+        src_coord(cx1 - g.left, g.ratio_w, g.src_w, a, x_hi, l);
+      }
+    }
+    const int rows = y_hi - y_lo + 1, cols = x_hi - x_lo + 1;
+    const int line_bytes = kHwc ? 3 * cols : cols;
+    const int pitch = (line_bytes + 15 + 15) / 16 * 16;     // room for the leading misalignment
+    const int lines = kHwc ? rows : 3 * rows;
+    s_rect[0] = y_lo; s_rect[1] = rows; s_rect[2] = x_lo; s_rect[3] = cols; s_rect[4] = pitch;
+    s_rect[5] = (any && lines <= kTileMaxLines && lines * pitch <= kTileSmem) ? 1 : 0;
+  }
+  __syncthreads();
+  const int y_lo = s_rect[0], rows = s_rect[1], x_lo = s_rect[2], cols = s_rect[3], pitch = s_rect[4];
+  const bool staged = s_rect[5] != 0;
+  const uint8_t* base = static_cast<const uint8_t*>(g.src);
+  if (staged) {
+    const int lines = kHwc ? rows : 3 * rows;
+    const int line_bytes = kHwc ? 3 * cols : cols;
+    const int cpl = pitch >> 4;                                // 16-byte chunks per staged line
+    const size_t plane = static_cast<size_t>(g.src_h) * g.src_w;
+    for (int idx = tid; idx < lines * cpl; idx += kTileThreads) {
+      const int line = idx / cpl, ch = idx - line * cpl;
+      const int c = kHwc ? 0 : line / rows, r = kHwc ? line : line - c * rows;
+      const size_t off = kHwc ? (static_cast<size_t>(y_lo + r) * g.src_w + x_lo) * 3
+                              : static_cast<size_t>(c) * plane + static_cast<size_t>(y_lo + r) * g.src_w + x_lo;
+      const uintptr_t a0 = reinterpret_cast<uintptr_t>(base + off);
+      const uintptr_t al = a0 & ~static_cast<uintptr_t>(15);
+      if (ch == 0) s_mis[line] = static_cast<uint16_t>(a0 - al);
+      const uintptr_t p = al + static_cast<uintptr_t>(ch) * 16;
+      // an aligned 16-byte chunk that holds at least one byte of the line lies inside the mapped page of that byte
+      if (p < a0 + line_bytes)
+        *reinterpret_cast<uint4*>(&s_src[line * pitch + ch * 16]) = __ldg(reinterpret_cast<const uint4*>(p));
+    }
+  }
+  __syncthreads();
+  StagedSrc<kHwc> S{s_src, s_mis, pitch, rows, y_lo, x_lo};
+  const int X = X0 + (tid & (kTileX - 1));
+  if (X >= W2) return;
+#pragma unroll
+  for (int k = 0; k < (kTileY * kTileX) / kTileThreads; ++k) {
+    const int Y = Y0 + (tid / kTileX) + k * (kTileThreads / kTileX);
+    if (Y >= H2) break;
+    __align__(16) DstT v[16];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        float rgb[3];
+        if (staged)
+          sample_rgb_staged<kHwc>(g, S, s_lut, 2 * Y + dy, 2 * X + dx, fill, rgb);
+        else if (any)
+          sample_rgb<uint8_t, kHwc>(g, s_lut, 2 * Y + dy, 2 * X + dx, fill, rgb);
+        else
+          rgb[0] = rgb[1] = rgb[2] = fill;
+        const int q = (dy * 2 + dx) * 4;
+        v[q + 0] = cvt_out<DstT>(rgb[0]);
+        v[q + 1] = cvt_out<DstT>(rgb[1]);
+        v[q + 2] = cvt_out<DstT>(rgb[2]);
+        v[q + 3] = cvt_out<DstT>(0.f);
+      }
+    }
+    DstT* o = dst + ((static_cast<size_t>(img0 + li) * H2 + Y) * W2 + X) * 16;
+    reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(v)[0];
+    reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(v)[1];
+  }
+}
+
 template <typename SrcT, typename DstT, bool kHwc>
 int launch_typed(const BatchGeom& bg, int img0, int count, int Hb, int Wb, float fill, const float* lut,
                  void* dst, int layout, cudaStream_t stream) {
@@ -195,6 +346,9 @@ int launch_typed(const BatchGeom& bg, int img0, int count, int Hb, int Wb, float
     dim3 grid((Wb + threads - 1) / threads, Hb, count);
     letterbox_nchw_kernel<SrcT, DstT, kHwc><<<grid, threads, 0, stream>>>(bg, img0, Hb, Wb, fill, lut,
                                                                     static_cast<DstT*>(dst));
+  } else if constexpr (std::is_same<SrcT, uint8_t>::value && sizeof(DstT) == 2) {
+    dim3 grid((Wb / 2 + kTileX - 1) / kTileX, (Hb / 2 + kTileY - 1) / kTileY, count);
+    letterbox_s2d_tile_kernel<DstT, kHwc><<<grid, kTileThreads, 0, stream>>>(bg, img0, Hb, Wb, fill, lut, static_cast<DstT*>(dst));
   } else {
     dim3 grid((Wb / 2 + threads - 1) / threads, (Hb / 2 + kRowsPerBlock - 1) / kRowsPerBlock, count);
     letterbox_s2d_kernel<SrcT, DstT, kHwc><<<grid, threads, 0, stream>>>(bg, img0, Hb, Wb, fill, lut,

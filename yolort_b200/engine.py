@@ -160,9 +160,12 @@ def stem_band(w: torch.Tensor, b: torch.Tensor) -> Tuple[torch.Tensor, torch.Ten
 
 
 def pack_weight(w: torch.Tensor, dtype: torch.dtype, device: torch.device) -> Tuple[torch.Tensor, int, int]:
-    """[Co,Ci,k,k] -> K-major [Co_pad, k*k, Ci_pad] (zero padded, both multiples of 16)."""
+    """[Co,Ci,k,k] -> K-major [Co_pad, k*k, Ci_pad], zero padded.  Ci_pad is a multiple of 64 once Ci > 32, so that the
+    kernels always fetch 128-byte (SWIZZLE_128B) operand rows: 48-, 80- or 96-channel layers (yolov5m / x) would
+    otherwise fall to 32- or 64-byte TMA rows, which the TMA unit moves at a fraction of the rate.  The padding costs no
+    tensor work: the kernels issue only ceil(Ci/16) K-steps of the last chunk (`kk_last`)."""
     co, ci, kh, kw = w.shape
-    ci_pad, co_pad = _round_up(ci, 16), _round_up(co, 16)
+    ci_pad, co_pad = (_round_up(ci, 64) if ci > 32 else _round_up(ci, 16)), _round_up(co, 16)
     p = torch.zeros((co_pad, kh * kw, ci_pad), dtype=torch.float64, device=w.device)
     p[:co, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, kh * kw, ci)
     return p.to(dtype).to(device).contiguous(), ci_pad, co_pad
@@ -305,11 +308,12 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device, stem_
         w_s2d = stem_to_s2d(w)
     t0 = L.buf("body.0", 2, w.shape[0])
     # The stem runs over "super-pixels" of 4 horizontally adjacent s2d pixels (128-byte TMA rows instead of 32).  Its
-    # expanded weight matrix is block-banded, and when 4*Cout fits one N tile the banded kernel variant multiplies only
-    # the band (measured on B200, yolov5s batch 32: 164 -> 88 us); wider stems (yolov5x) use the dense super-pixel form.
+    # expanded weight matrix is block-banded, and when the band (6 slabs of 4*Cout x 64) fits in shared memory next to
+    # two patches (4*Cout <= 128: yolov5n / s) the banded kernel variant multiplies only the band (measured on B200,
+    # yolov5s batch 32: 164 -> 88 us); wider stems (m / l / x) use the dense super-pixel form.
     spk = 4
     co4 = spk * w.shape[0]
-    if stem_variant == "band" or (stem_variant == "auto" and co4 % 64 == 0 and co4 <= 256
+    if stem_variant == "band" or (stem_variant == "auto" and co4 % 64 == 0 and co4 <= 128
                                   and act_code(stem.act) in (_C.YB_ACT_SILU, _C.YB_ACT_NONE)):
         w_b, b_b = stem_band(w_s2d, b)
         L.conv_band("body.0(stem: banded 3x3 over s2d super-pixels)", w_b, b_b, _View(x0, 0, 16), _View(t0, 0, w.shape[0]),

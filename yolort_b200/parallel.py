@@ -29,10 +29,16 @@ def global_canvas(sizes: Sequence[Tuple[int, int]], min_size: float, max_size: f
     return hw
 
 
-def pack_detections(boxes: Tensor, scores: Tensor, labels: Tensor) -> Tensor:
-    """[n, D, 6] fp32 rows (x1, y1, x2, y2, score, label) -- the all-gather payload (24 B per detection slot).
-    Labels < 2^24 are exact in fp32."""
-    return torch.cat([boxes, scores.unsqueeze(-1), labels.to(torch.float32).unsqueeze(-1)], dim=-1).contiguous()
+def pack_detections(boxes: Tensor, scores: Tensor, labels: Tensor, counts: Optional[Tensor] = None) -> Tensor:
+    """[n, D(+1), 6] fp32 rows (x1, y1, x2, y2, score, label) -- the all-gather payload (24 B per detection slot).
+    Labels < 2^24 are exact in fp32.  With `counts`, one more row per image carries the detection count in column 0, so
+    a single collective moves everything."""
+    packed = torch.cat([boxes, scores.unsqueeze(-1), labels.to(torch.float32).unsqueeze(-1)], dim=-1)
+    if counts is not None:
+        tail = packed.new_zeros((packed.shape[0], 1, 6))
+        tail[:, 0, 0] = counts.to(torch.float32)
+        packed = torch.cat([packed, tail], dim=1)
+    return packed.contiguous()
 
 
 def unpack_detections(packed: Tensor, counts: Tensor) -> List[Dict[str, Tensor]]:
@@ -45,21 +51,20 @@ def unpack_detections(packed: Tensor, counts: Tensor) -> List[Dict[str, Tensor]]
 
 
 def all_gather_detections(packed: Tensor, counts: Tensor, shard_sizes: Sequence[int], group=None) -> Tuple[Tensor, Tensor]:
-    """One collective pair over equal-sized buffers: shards are padded to the largest shard so that
-    all_gather_into_tensor (NCCL all-gather over NVLink) can be used; returns ([N_total, D, 6], [N_total])."""
+    """ONE collective over equal-sized buffers: shards are padded to the largest shard and the counts ride in an extra
+    row of the payload, so that a single all_gather_into_tensor (NCCL all-gather over NVLink) moves everything;
+    returns ([N_total, D, 6], [N_total])."""
     world = dist.get_world_size(group)
     n_max = max(shard_sizes)
     D = packed.shape[1]
-    send = packed.new_zeros((n_max, D, 6))
-    send[: packed.shape[0]] = packed
-    send_c = counts.new_zeros((n_max,))
-    send_c[: counts.shape[0]] = counts
-    recv = packed.new_empty((world * n_max, D, 6))
-    recv_c = counts.new_empty((world * n_max,))
+    send = packed.new_zeros((n_max, D + 1, 6))
+    send[: packed.shape[0], :D] = packed
+    send[: counts.shape[0], D, 0] = counts.to(torch.float32)
+    recv = packed.new_empty((world * n_max, D + 1, 6))
     dist.all_gather_into_tensor(recv, send, group=group)
-    dist.all_gather_into_tensor(recv_c, send_c, group=group)
     keep = torch.cat([torch.arange(r * n_max, r * n_max + s) for r, s in enumerate(shard_sizes)]).to(recv.device)
-    return recv[keep], recv_c[keep]
+    sel = recv[keep]
+    return sel[:, :D], sel[:, D, 0].to(torch.int32)
 
 
 def forward_padded_grow(model, images: List[Tensor], canvas: Tuple[int, int], max_tries: int = 8):
