@@ -130,8 +130,9 @@ typedef struct {
   const float* bias;            /* [Cout_pad] fp32 (folded BN shift, or the head's conv bias)     */
   const void* residual;         /* optional NHWC view added after the activation (Bottleneck)    */
   int32_t res_cstride;
-  int32_t reserved;             /* bit 0: keep a 3x3/s1 conv on the generic im2col kernel; bit 1 (experimental): `weight`
-                                   is the banded super-pixel stem matrix [Cout_pad][3][128] (engine.stem_band)          */
+  int32_t reserved;             /* bit 0: keep a 3x3 conv on the generic im2col kernel; bit 1: `weight` is the banded
+                                   super-pixel stem matrix [Cout_pad][3][128] (engine.stem_band); bit 2: take the
+                                   halo-patch kernel's stride-2 parity-plane variant whatever the channel counts (tests) */
   const yb_head_decode* decode; /* optional (host pointer, copied at plan creation): fused decode epilogue */
 } yb_op_desc;
 

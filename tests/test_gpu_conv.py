@@ -11,7 +11,7 @@ DEV = torch.device("cuda:0")
 
 
 def run_conv(N, H, W, Cin, Cout, k, s, p, dtype=torch.float16, act=True, residual=False, in_pad=0, out_pad=0, seed=0,
-             bias_scale=0.5, force_im2col=False):
+             bias_scale=0.5, force_im2col=False, force_planes=False):
     torch.backends.cudnn.allow_tf32 = False      # the fp32 reference must not run on TF32 tensor cores
     torch.backends.cuda.matmul.allow_tf32 = False
     g = torch.Generator().manual_seed(seed)
@@ -38,7 +38,7 @@ def run_conv(N, H, W, Cin, Cout, k, s, p, dtype=torch.float16, act=True, residua
     d.weight, d.Cin_pad, d.Cout_pad, d.bias = wp.data_ptr(), ci_pad, co_pad, bp.data_ptr()
     if residual:
         d.residual, d.res_cstride = res.data_ptr(), Cout
-    d.reserved = 1 if force_im2col else 0
+    d.reserved = (1 if force_im2col else 0) | (4 if force_planes else 0)
     plan = _C.Plan([d], DEV)
     plan.run()
     torch.cuda.synchronize()
@@ -162,9 +162,10 @@ def test_patch_conv_stride2_parity_planes(shape):
     """3x3 / stride 2 on the halo-patch kernel (two column-parity planes per chunk) vs the fp32 convolution, and vs
     the generic im2col kernel on the same operands."""
     n, h, w, ci, co, in_pad, out_pad = shape
-    run_conv(n, h, w, ci, co, 3, 2, 1, in_pad=in_pad, out_pad=out_pad, seed=7)
+    run_conv(n, h, w, ci, co, 3, 2, 1, in_pad=in_pad, out_pad=out_pad, seed=7, force_planes=True)
     run_conv(n, h, w, ci, co, 3, 2, 1, in_pad=in_pad, out_pad=out_pad, seed=7, force_im2col=True)
-    run_conv(n, h, w, ci, co, 3, 2, 1, in_pad=in_pad, out_pad=out_pad, seed=8, dtype=torch.bfloat16)
+    run_conv(n, h, w, ci, co, 3, 2, 1, in_pad=in_pad, out_pad=out_pad, seed=8, dtype=torch.bfloat16, force_planes=True)
+    run_conv(n, h, w, ci, co, 3, 2, 1, in_pad=in_pad, out_pad=out_pad, seed=9)      # the plan's own choice
 
 
 def test_patch_conv_matches_im2col_kernel():

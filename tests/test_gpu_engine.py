@@ -160,3 +160,21 @@ def test_training_mode_hands_the_head_outputs_to_the_criterion():
     with pytest.raises(NotImplementedError):
         m.model(x, targets="T")
     m.model.eval()
+
+
+def test_plan_replayed_as_a_cuda_graph_gives_the_same_logits():
+    m, sd = _model_n()
+    ims = [util.synth_image_u8(90, 128, 21).to(DEV), util.synth_image_u8(100, 75, 22).to(DEV)]
+    want = m(ims)
+    plan = m.model.get_plan(2, 128, 128)
+    heads = [h.clone() for h in plan.heads]
+    for h in plan.heads:
+        h.zero_()
+    plan.run_graph()
+    plan.run_graph()
+    torch.cuda.synchronize()
+    for a, b in zip(plan.heads, heads):
+        assert torch.equal(a, b)
+    m.model.engine().graphs = True
+    m.model.engine()._plans.clear()
+    assert _same(want, m(ims)) and m.model.get_plan(2, 128, 128).use_graph

@@ -215,6 +215,17 @@ __device__ __forceinline__ void umma_ksteps_rt(int kk, uint32_t tmem_d, uint32_t
     umma_ksteps<1>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, first);
 }
 
+// Role loops: warp-uniform with one elected issuing lane (default), or the whole role inside a one-lane branch
+// (-DYB_SINGLE_LANE_ISSUE, kept for A/B timing: scripts/ab_step.sh).  tcgen05 / TMA instructions take uniform-register
+// operands; inside a one-lane branch ptxas wraps each of them in an elect/branch convergence loop with R2UR moves.
+#ifdef YB_SINGLE_LANE_ISSUE
+#define YB_ROLE_LANES(lane) ((lane) == 0)
+#define YB_ELECT() true
+#else
+#define YB_ROLE_LANES(lane) true
+#define YB_ELECT() yb::elect_one()
+#endif
+
 // Ablation knobs (YB_CONV_DBG bit mask: 1 no epilogue math/stores, 2 no MMA, 4 no TMA stores, 8 no loads, 16 accumulator
 // handshake only) exist only in -DYB_ABLATION builds (scripts/conv_ablation.py); release kernels carry none of them.
 #ifdef YB_ABLATION

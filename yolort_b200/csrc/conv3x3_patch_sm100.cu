@@ -125,6 +125,78 @@ __device__ __forceinline__ void tile_coords(const PatchParams& p, int m_tile, in
   x0 = tx * p.tg.x_step;
 }
 
+// The nine taps of one channel chunk as straight-line code: KK K=16 steps per tap, no run-time dispatch inside.
+//   kMode 0: one tile; 1: two tiles sharing every weight slab (second accumulator block_n columns further);
+//   2: stride 2, one accumulator, the tap picks its column-parity plane (a0 = even plane, a1 = odd plane).
+template <int KK, int kMode>
+__device__ __forceinline__ void issue_tap(int tap, bool first, uint32_t tmem_d0, uint32_t block_n, uint32_t a0, uint32_t a1,
+                                          uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+  if constexpr (kMode == 2) {
+    umma_ksteps<KK>(tmem_d0, ((tap % 3) == 1 ? a0 : a1), a_hi, b_lo, b_hi, idesc, first);
+  } else {
+    umma_ksteps<KK>(tmem_d0, a0, a_hi, b_lo, b_hi, idesc, first);
+    if constexpr (kMode == 1) umma_ksteps<KK>(tmem_d0 + block_n, a1, a_hi, b_lo, b_hi, idesc, first);
+  }
+}
+template <int KK, int kMode>
+__device__ __forceinline__ void issue_chunk_resident(bool first_chunk, uint32_t tmem_d0, uint32_t block_n, uint32_t a_lo0,
+                                                     uint32_t a_lo1, const uint32_t (&tap_off16)[9], uint32_t a_hi,
+                                                     uint32_t b_lo_chunk, uint32_t b_step16, uint32_t b_hi, uint32_t idesc) {
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+    issue_tap<KK, kMode>(tap, first_chunk && tap == 0, tmem_d0, block_n, a_lo0 + tap_off16[tap], a_lo1 + tap_off16[tap], a_hi,
+                         b_lo_chunk + tap * b_step16, b_hi, idesc);
+}
+template <int kMode>
+__device__ __forceinline__ void issue_chunk_resident_kk(int kc, bool first_chunk, uint32_t tmem_d0, uint32_t block_n,
+                                                        uint32_t a_lo0, uint32_t a_lo1, const uint32_t (&tap_off16)[9],
+                                                        uint32_t a_hi, uint32_t b_lo_chunk, uint32_t b_step16, uint32_t b_hi,
+                                                        uint32_t idesc) {
+  if (kc == 4)
+    issue_chunk_resident<4, kMode>(first_chunk, tmem_d0, block_n, a_lo0, a_lo1, tap_off16, a_hi, b_lo_chunk, b_step16, b_hi, idesc);
+  else if (kc == 2)
+    issue_chunk_resident<2, kMode>(first_chunk, tmem_d0, block_n, a_lo0, a_lo1, tap_off16, a_hi, b_lo_chunk, b_step16, b_hi, idesc);
+  else if (kc == 3)
+    issue_chunk_resident<3, kMode>(first_chunk, tmem_d0, block_n, a_lo0, a_lo1, tap_off16, a_hi, b_lo_chunk, b_step16, b_hi, idesc);
+  else
+    issue_chunk_resident<1, kMode>(first_chunk, tmem_d0, block_n, a_lo0, a_lo1, tap_off16, a_hi, b_lo_chunk, b_step16, b_hi, idesc);
+}
+// Weights streamed through the ring: per tap wait for its slab, issue, release the slab -- still straight-line per (KK, mode).
+template <int KK, int kMode>
+__device__ __forceinline__ void issue_chunk_streaming(bool first_chunk, bool no_mma, uint32_t tmem_d0, uint32_t block_n,
+                                                      uint32_t a_lo0, uint32_t a_lo1, const uint32_t (&tap_off16)[9],
+                                                      uint32_t a_hi, uint32_t b_ring_lo0, uint32_t b_step16, uint32_t b_hi,
+                                                      uint32_t idesc, uint64_t* b_full, uint64_t* b_empty, int b_stages,
+                                                      int& kb) {
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap, ++kb) {
+    const int sb = kb % b_stages;
+    mbar_wait(&b_full[sb], (kb / b_stages) & 1);
+    tc_fence_after();
+    if (YB_ELECT()) {
+      if (!no_mma)
+        issue_tap<KK, kMode>(tap, first_chunk && tap == 0, tmem_d0, block_n, a_lo0 + tap_off16[tap], a_lo1 + tap_off16[tap], a_hi,
+                             b_ring_lo0 + static_cast<uint32_t>(sb) * b_step16, b_hi, idesc);
+      umma_commit(&b_empty[sb]);
+    }
+  }
+}
+template <int kMode>
+__device__ __forceinline__ void issue_chunk_streaming_kk(int kc, bool first_chunk, bool no_mma, uint32_t tmem_d0,
+                                                         uint32_t block_n, uint32_t a_lo0, uint32_t a_lo1,
+                                                         const uint32_t (&tap_off16)[9], uint32_t a_hi, uint32_t b_ring_lo0,
+                                                         uint32_t b_step16, uint32_t b_hi, uint32_t idesc, uint64_t* b_full,
+                                                         uint64_t* b_empty, int b_stages, int& kb) {
+  if (kc == 4)
+    issue_chunk_streaming<4, kMode>(first_chunk, no_mma, tmem_d0, block_n, a_lo0, a_lo1, tap_off16, a_hi, b_ring_lo0, b_step16, b_hi, idesc, b_full, b_empty, b_stages, kb);
+  else if (kc == 2)
+    issue_chunk_streaming<2, kMode>(first_chunk, no_mma, tmem_d0, block_n, a_lo0, a_lo1, tap_off16, a_hi, b_ring_lo0, b_step16, b_hi, idesc, b_full, b_empty, b_stages, kb);
+  else if (kc == 3)
+    issue_chunk_streaming<3, kMode>(first_chunk, no_mma, tmem_d0, block_n, a_lo0, a_lo1, tap_off16, a_hi, b_ring_lo0, b_step16, b_hi, idesc, b_full, b_empty, b_stages, kb);
+  else
+    issue_chunk_streaming<1, kMode>(first_chunk, no_mma, tmem_d0, block_n, a_lo0, a_lo1, tap_off16, a_hi, b_ring_lo0, b_step16, b_hi, idesc, b_full, b_empty, b_stages, kb);
+}
+
 template <bool kBf16, int kStoreCols, bool kRareAct, bool kBand = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -179,7 +251,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     // The role loops are WARP-UNIFORM (all 32 lanes walk them, one elected lane issues): TMA and tcgen05 instructions
     // take their operands from uniform registers, and inside a one-lane branch ptxas wraps every such instruction
     // in an elect/branch convergence loop with R2UR moves (~10 instructions per MMA instead of ~3).
-    {
+    if (YB_ROLE_LANES(lane)) {
       int ka = 0;   // patches issued so far (ring position)
       for (int task = blockIdx.x; task < p.num_tasks; task += gridDim.x) {
         const int m_first = (task / p.n_tiles) * p.pair;
@@ -192,10 +264,10 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const uint32_t ph = (ka / p.a_slots) & 1;
             mbar_wait(&a_empty[s], ph ^ 1);
             if (YB_DBG(p, 8)) {   // ablation: no loads at all, only the pipeline handshake
-              if (elect_one()) mbar_arrive(&a_full[s]);
+              if (YB_ELECT()) mbar_arrive(&a_full[s]);
               continue;
             }
-            if (elect_one()) {
+            if (YB_ELECT()) {
               mbar_expect_tx(&a_full[s], p.a_bytes);
               uint8_t* dst = a_buf + static_cast<size_t>(s) * p.a_stride;
               if (p.s2)   // plane j (0 = even columns, 1 = odd): pair-columns x0-1 .., input rows 2*y0-1 ..
@@ -209,7 +281,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
   } else if (warp == 2) {
     // ===================== weight (B) producer =====================
-    {
+    if (YB_ROLE_LANES(lane)) {
       const uint32_t b_bytes = p.block_n * p.block_k * 2;
       if constexpr (kBand) {
         // banded stem weights: 3 filter rows x 2 blocks of 64 K-columns, consecutive in the weight matrix
@@ -233,7 +305,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const int s = kb % p.b_stages;
             const uint32_t ph = (kb / p.b_stages) & 1;
             mbar_wait(&b_empty[s], ph ^ 1);
-            if (elect_one()) {
+            if (YB_ELECT()) {
               mbar_expect_tx(&b_full[s], b_bytes);
               tma_load_2d(&tmap_b, &b_full[s], b_buf + static_cast<size_t>(s) * p.b_sub_bytes,
                           ((i % 9) * p.chunks + i / 9) * p.block_k, n0);
@@ -244,7 +316,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    {
+    if (YB_ROLE_LANES(lane)) {
       const uint32_t row_bytes = p.block_k * 2;
       const int pitch = p.tg.pitch;   // pixel-rows per patch row
       const uint32_t sbo = p.tg.sbo_rows * row_bytes;
@@ -293,7 +365,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             // those K-slices: [ky][2 blocks of 64], the last 32 columns of the second block are zero padding that
             // is never multiplied.  18 MMAs per tile instead of 36, 96 KB of resident weights instead of a
             // 147 KB ring that is re-streamed from L2 for every tile.
-            if (!YB_DBG(p, 2) && elect_one()) {
+            if (!YB_DBG(p, 2) && YB_ELECT()) {
               const uint32_t row16 = (static_cast<uint32_t>(pitch) * row_bytes) >> 4;
 #pragma unroll
               for (int ky = 0; ky < 3; ++ky) {
@@ -311,41 +383,35 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           } else {
             const int kc = c == p.chunks - 1 ? p.kk_last : kk;
             const bool first_chunk = c == 0;
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              uint32_t b_lo;
-              int sb = 0;
-              if (p.b_resident) {
-                b_lo = b_res_lo0 + static_cast<uint32_t>(c * 9 + tap) * b_step16;
-              } else {
-                sb = kb % p.b_stages;
-                mbar_wait(&b_full[sb], (kb / p.b_stages) & 1);
-                tc_fence_after();
-                b_lo = b_res_lo0 + static_cast<uint32_t>(sb) * b_step16;
+            const int tmode = mode == 1 && cnt == 1 ? 0 : mode;   // the odd last pair holds one tile
+            if (p.b_resident) {
+              // all nine weight slabs are in shared memory: one elected region, straight-line MMAs
+              if (!YB_DBG(p, 2) && YB_ELECT()) {
+                const uint32_t b_lo_chunk = b_res_lo0 + static_cast<uint32_t>(c * 9) * b_step16;
+                if (tmode == 0)
+                  issue_chunk_resident_kk<0>(kc, first_chunk, tmem_d0, p.block_n, a_lo0, a_lo1, tap_off16, a_hi, b_lo_chunk, b_step16, b_hi, p.idesc);
+                else if (tmode == 1)
+                  issue_chunk_resident_kk<1>(kc, first_chunk, tmem_d0, p.block_n, a_lo0, a_lo1, tap_off16, a_hi, b_lo_chunk, b_step16, b_hi, p.idesc);
+                else
+                  issue_chunk_resident_kk<2>(kc, first_chunk, tmem_d0, p.block_n, a_lo0, a_lo1, tap_off16, a_hi, b_lo_chunk, b_step16, b_hi, p.idesc);
               }
-              if (elect_one()) {
-                if (!YB_DBG(p, 2)) {
-                  const bool first = first_chunk && tap == 0;
-                  if (mode == 2) {   // stride 2: one accumulator, the tap picks its plane (slot 0 = even columns, 1 = odd)
-                    umma_ksteps_rt(kc, tmem_d0, ((tap % 3) == 1 ? a_lo0 : a_lo1) + tap_off16[tap], a_hi, b_lo, b_hi, p.idesc, first);
-                  } else {
-                    umma_ksteps_rt(kc, tmem_d0, a_lo0 + tap_off16[tap], a_hi, b_lo, b_hi, p.idesc, first);
-                    if (cnt == 2)
-                      umma_ksteps_rt(kc, tmem_d0 + p.block_n, a_lo1 + tap_off16[tap], a_hi, b_lo, b_hi, p.idesc, first);
-                  }
-                }
-                if (!p.b_resident) umma_commit(&b_empty[sb]);
-              }
-              if (!p.b_resident) ++kb;
+            } else {
+              const bool no_mma = YB_DBG(p, 2);
+              if (tmode == 0)
+                issue_chunk_streaming_kk<0>(kc, first_chunk, no_mma, tmem_d0, p.block_n, a_lo0, a_lo1, tap_off16, a_hi, b_res_lo0, b_step16, b_hi, p.idesc, b_full, b_empty, p.b_stages, kb);
+              else if (tmode == 1)
+                issue_chunk_streaming_kk<1>(kc, first_chunk, no_mma, tmem_d0, p.block_n, a_lo0, a_lo1, tap_off16, a_hi, b_res_lo0, b_step16, b_hi, p.idesc, b_full, b_empty, p.b_stages, kb);
+              else
+                issue_chunk_streaming_kk<2>(kc, first_chunk, no_mma, tmem_d0, p.block_n, a_lo0, a_lo1, tap_off16, a_hi, b_res_lo0, b_step16, b_hi, p.idesc, b_full, b_empty, p.b_stages, kb);
             }
           }
-          if (elect_one()) {
+          if (YB_ELECT()) {
             umma_commit(&a_empty[sa0]);
             if (cnt == 2) umma_commit(&a_empty[sa1]);
           }
           ka += cnt;
         }
-        if (elect_one()) umma_commit(&acc_full[as]);
+        if (YB_ELECT()) umma_commit(&acc_full[as]);
       }
     }
   } else if (warp >= kFirstEpiWarp) {
@@ -493,8 +559,12 @@ TileGeom pick_geom(int H, int W, bool allow_wrap, bool s2) {
 bool patch_conv_eligible(const yb_op_desc& d) {
   if (d.kind != YB_OP_CONV || d.ksize != 3 || d.pad != 1) return false;
   if (d.reserved & 1) return false;   // caller asked for the generic im2col kernel
-  if (d.stride == 2)   // two column-parity planes: even width, and an output map that 16 x 8 tiles cover well
-    return (d.reserved & 2) == 0 && d.W % 2 == 0 && d.H % 2 == 0 && classic_eff(d.Ho, d.Wo) >= 0.7;
+  if (d.stride == 2)   // two column-parity planes: even width, and an output map that 16 x 8 tiles cover well.
+    // Measured on B200 (yolov5s batch 32): 64 -> 128 at 80 x 80 out 70.7 -> 61.5 us, 32 -> 64 at 160 x 160 149 -> 143 us;
+    // with two channel chunks (four 38 KB planes per tile) or a split N tile the im2col kernel is as fast or faster
+    // (128 -> 256 at 40 x 40: 45 us im2col vs 65 us), so those stay there unless the caller forces the variant (bit 2).
+    return (d.reserved & 2) == 0 && d.W % 2 == 0 && d.H % 2 == 0 && classic_eff(d.Ho, d.Wo) >= 0.7 &&
+           ((d.Cin <= 64 && d.Cout <= 128) || (d.reserved & 4));
   if (d.stride != 1) return false;
   const bool band = (d.reserved & 2) != 0;
   const double eff = band ? classic_eff(d.H, d.W) : (classic_eff(d.H, d.W) > wrap_eff(d.H, d.W) ? classic_eff(d.H, d.W) : wrap_eff(d.H, d.W));

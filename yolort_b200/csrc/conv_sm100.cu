@@ -66,6 +66,15 @@ struct ConvKernelParams {
   yb_head_decode dec;   // copied from the op descriptor
 };
 
+// The k-iterations of one pipeline stage as (near) straight-line code: KK K=16 steps each, constant stride between the
+// operand sub-tiles of consecutive iterations.
+template <int KK>
+__device__ __forceinline__ void issue_group(int cnt, bool first_group, uint32_t tmem_d, uint32_t a_lo0, uint32_t a_step16,
+                                            uint32_t b_lo0, uint32_t b_step16, uint32_t desc_hi, uint32_t idesc) {
+  umma_ksteps<KK>(tmem_d, a_lo0, desc_hi, b_lo0, desc_hi, idesc, first_group);
+  for (int j = 1; j < cnt; ++j) umma_ksteps<KK>(tmem_d, a_lo0 + j * a_step16, desc_hi, b_lo0 + j * b_step16, desc_hi, idesc, false);
+}
+
 template <bool kBf16, int kStoreCols, bool kRareAct, bool kDecode>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -125,7 +134,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // uniform-register operands, and inside a one-lane branch ptxas wraps each of them in an elect/branch convergence
     // loop with R2UR moves (~10 instructions per MMA instead of ~3; the issuing thread is the critical path of the
     // shallow layers).
-    {
+    if (YB_ROLE_LANES(lane)) {
       const uint32_t a_bytes = kBlockM * p.block_k * 2, b_bytes = p.block_n * p.block_k * 2;
       if (p.b_resident && lane == 0) {
         mbar_expect_tx(&b_full, p.num_k_iters * b_bytes);
@@ -154,10 +163,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* a_dst = tiles + s * stage_bytes;
           uint8_t* b_dst = a_dst + p.kpg * p.a_stage_bytes;
           if (YB_DBG(p, 8)) {   // ablation: no loads at all, only the pipeline handshake
-            if (elect_one()) mbar_arrive(&full_bar[s]);
+            if (YB_ELECT()) mbar_arrive(&full_bar[s]);
             continue;
           }
-          if (elect_one()) {
+          if (YB_ELECT()) {
             mbar_expect_tx(&full_bar[s], cnt * (a_bytes + (p.b_resident ? 0u : b_bytes)));
             for (int j = 0; j < cnt; ++j) {
               const int it = it0 + j;
@@ -181,7 +190,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== MMA issuer =====================
     // (A second issuing thread for alternate tiles was tried and removed: two consumers that are several phases
     // apart on the same full/empty mbarriers alias under parity waits.)
-    {
+    if (YB_ROLE_LANES(lane)) {
       const uint32_t row_bytes = p.block_k * 2;
       const int kk = p.block_k >> 4;
       if (p.b_resident) {
@@ -211,20 +220,29 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           // descriptors differ only in their 14-bit start-address field (16-byte units)
           const uint32_t a_lo0 = (a_base & 0x3FFFFu) >> 4;
           const uint32_t b_lo0 = ((p.b_resident ? b_res_addr + it0 * p.b_stage_bytes : b_base) & 0x3FFFFu) >> 4;
-          if (elect_one()) {
+          if (YB_ELECT()) {
             if (!YB_DBG(p, 2)) {
-              int ch = chunk;
-              for (int j = 0; j < cnt; ++j) {
-                umma_ksteps_rt(ch == p.chunks - 1 ? p.kk_last : kk, tmem_d, a_lo0 + j * a_step16, desc_hi,
-                               b_lo0 + j * b_step16, desc_hi, p.idesc, (it0 | j) == 0);
-                if (++ch == p.chunks) ch = 0;
+              if (p.kk_last == kk) {   // every chunk is full (the common case): no per-iteration dispatch
+                if (kk == 4)
+                  issue_group<4>(cnt, it0 == 0, tmem_d, a_lo0, a_step16, b_lo0, b_step16, desc_hi, p.idesc);
+                else if (kk == 2)
+                  issue_group<2>(cnt, it0 == 0, tmem_d, a_lo0, a_step16, b_lo0, b_step16, desc_hi, p.idesc);
+                else
+                  issue_group<1>(cnt, it0 == 0, tmem_d, a_lo0, a_step16, b_lo0, b_step16, desc_hi, p.idesc);
+              } else {
+                int ch = chunk;
+                for (int j = 0; j < cnt; ++j) {
+                  umma_ksteps_rt(ch == p.chunks - 1 ? p.kk_last : kk, tmem_d, a_lo0 + j * a_step16, desc_hi,
+                                 b_lo0 + j * b_step16, desc_hi, p.idesc, (it0 | j) == 0);
+                  if (++ch == p.chunks) ch = 0;
+                }
               }
             }
             umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
           }
           chunk = (chunk + cnt) % p.chunks;
         }
-        if (elect_one()) umma_commit(&acc_full[as]);  // accumulator of this tile complete
+        if (YB_ELECT()) umma_commit(&acc_full[as]);  // accumulator of this tile complete
       }
     }
   } else {
