@@ -141,18 +141,27 @@ def test_fused_head_decode_equals_unfused(monkeypatch):
         assert frac >= 0.97      # logits rounded to fp16 in the unfused path move scores by <= 1e-3
 
 
-def test_pipelined_host_predict_equals_device_forward(monkeypatch):
-    """predict() on >= 16 host images copies the second half while the first is processed; results must equal the
-    unsplit device-resident call (both halves are letterboxed to the whole batch's canvas)."""
+def test_pipelined_host_predict_equals_device_forward():
+    """predict() on >= 16 host images (a multiple of 4) copies them in four chunks and runs letterbox + the front of
+    the plan per chunk while later chunks are still in flight; results must equal the device-resident call bit for
+    bit (mixed sizes: every chunk is letterboxed to the whole batch's canvas)."""
     m, sd = _model_n()
-    ims = [util.synth_image_u8(64 + 8 * (i % 5), 128 - 8 * (i % 3), 70 + i) for i in range(18)]
+    ims = [util.synth_image_u8(64 + 8 * (i % 5), 128 - 8 * (i % 3), 70 + i) for i in range(20)]
     ref = m([im.to(DEV) for im in ims])
     pinned = [im.pin_memory() for im in ims]
-    monkeypatch.setenv("YB_PIPELINE_H2D", "1")
-    got = m.predict(pinned)
-    assert len(got) == len(ref) == 18
-    for a, b in zip(got, ref):
-        assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["scores"], b["scores"])
+    assert m._predict_pipelined(pinned) is not None          # the chunked path is the one predict() takes here
+    Hb, Wb = m.transform.geometry(ims)[1]
+    plan = m.model.get_plan(20, Hb, Wb, chunked=True)
+    assert plan.front_chunks == 4 and plan.front_ops == 13
+    for _ in range(2):                                        # twice: staging / arena reuse across calls
+        got = m.predict(pinned)
+        assert len(got) == len(ref) == 20
+        for a, b in zip(got, ref):
+            assert torch.equal(a["labels"], b["labels"]) and torch.equal(a["scores"], b["scores"])
+            assert torch.equal(a["boxes"], b["boxes"])
+    assert m._predict_pipelined(pinned[:18]) is None          # 18 images: not a multiple of 4 -> plain path
+    got = m.predict(pinned[:18])
+    for a, b in zip(got, m([im.to(DEV) for im in ims[:18]])):
         assert torch.equal(a["boxes"], b["boxes"])
 
 

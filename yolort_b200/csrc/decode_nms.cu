@@ -160,26 +160,22 @@ __global__ void decode_candidates_kernel(const __grid_constant__ DecodeParams p,
 }
 
 // Row variant for the plan's NHWC head buffers (channel a*K + k, row = one pixel's A*K logits, <= 512 bytes,
-// 16-byte aligned): HBM-bound, so the point is to fetch every byte exactly once, coalesced.  One warp takes four
-// consecutive pixels: it issues the four 512-byte row loads up front (one 16-byte load per lane each -- a row is ONE
-// fully coalesced request, where the per-anchor kernel above pulls a 32-byte sector per anchor and then re-reads
-// the passing anchors' rows scattered), parks them in shared memory and then works per pixel: lanes 0..A-1 test
-// the objectness of their anchor; the class scan (lane k <-> class k) and the box decode run only for anchors that
-// passed, out of shared memory.  Arithmetic, candidate keys and the dense box array are those of the kernel above.
-constexpr int kRowPixels = 4;        // pixels per warp
-constexpr int kRowWarps = 8;         // warps per block
+// 16-byte aligned): HBM-bound, so the point is to fetch every byte exactly once, coalesced, and to spend almost no
+// instructions per pixel.  One warp takes 32 consecutive pixels: it copies their 32 rows into shared memory with
+// cp.async (per row one 512-byte fully coalesced request, 16 KB in flight per warp, no register staging), then LANE l
+// OWNS PIXEL l: it tests the objectness of its pixel's anchors (the sigmoid / index arithmetic runs 32 pixels wide
+// instead of once per warp).  Only anchors that pass -- a few per cent -- are then scanned by the whole warp, lane k <->
+// class k, out of shared memory, and their box decoded.  (A first version handled 4 pixels per warp serially and was
+// instruction-bound: 113 us against the 92 us of the per-anchor kernel above; measured on B200, yolov5s batch 32.)
+// Arithmetic, candidate keys and the dense box array are those of the kernel above.
+constexpr int kRowPixels = 32;       // pixels per warp
+constexpr int kRowWarps = 4;         // warps per block
 constexpr int kRowMaxBytes = 512;    // longest row handled (A*K 16-bit logits padded to a multiple of 8)
+constexpr int kRowPitch = kRowMaxBytes + 16;   // shared-memory row pitch: 132 words -> lanes spread over 8 banks
 
-__device__ __forceinline__ uint4 ld_stream_16(const void* ptr) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(ptr));
-  return r;
-}
 template <typename T>
 __device__ __forceinline__ float row_elem(const uint8_t* row, int e) {
-  if constexpr (sizeof(T) == 2 && std::is_same<T, __half>::value)
+  if constexpr (std::is_same<T, __half>::value)
     return __half2float(reinterpret_cast<const __half*>(row)[e]);
   else
     return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(row)[e]);
@@ -188,57 +184,76 @@ __device__ __forceinline__ float row_elem(const uint8_t* row, int e) {
 template <typename T>
 __global__ void __launch_bounds__(kRowWarps * 32)
 decode_rows_kernel(const __grid_constant__ DecodeParams p, Workspace ws) {
-  __shared__ __align__(16) uint8_t s_rows[kRowWarps][kRowPixels][kRowMaxBytes];
+  extern __shared__ __align__(16) uint8_t s_rows_raw[];     // [kRowWarps][kRowPixels][kRowPitch]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* s_rows = s_rows_raw + static_cast<size_t>(warp) * kRowPixels * kRowPitch;
   const int P = p.pix_start[p.n_levels];                       // pixels per image over all levels
   const long long total = static_cast<long long>(p.n_images) * P;
   const long long q0 = (static_cast<long long>(blockIdx.x) * kRowWarps + warp) * kRowPixels;
   if (q0 >= total) return;
   const int K = p.n_classes + 5;
-  int img[kRowPixels], lv[kRowPixels], px[kRowPixels], py[kRowPixels];
-  bool valid[kRowPixels];
+  // this lane's pixel
+  const long long q = q0 + lane;
+  const bool valid = q < total;
+  int img = 0, lv = 0, px = 0, py = 0;
+  long long off = 0;
+  int row_chunks = 0;                                          // 16-byte chunks of this pixel's row
+  if (valid) {
+    img = static_cast<int>(q / P);
+    const int r = static_cast<int>(q - static_cast<long long>(img) * P);
 #pragma unroll
+    for (int i = 1; i < YB_MAX_LEVELS; ++i)
+      if (i < p.n_levels && r >= p.pix_start[i]) lv = i;
+    const yb_head_level& L = p.lvl[lv];
+    const int rr = r - p.pix_start[lv];
+    py = rr / L.W;
+    px = rr - py * L.W;
+    off = img * L.stride_n + py * L.stride_y + px * L.stride_x;   // elements
+    row_chunks = static_cast<int>(L.stride_x >> 3);
+  }
+  // rows -> shared memory: for row j all lanes copy that row's 16-byte chunks (one coalesced request)
+  const uint32_t s_base = smem_u32(s_rows);
+#pragma unroll 8
   for (int j = 0; j < kRowPixels; ++j) {
-    const long long q = q0 + j;
-    valid[j] = q < total;
-    img[j] = 0; lv[j] = 0; px[j] = 0; py[j] = 0;
-    if (valid[j]) {
-      img[j] = static_cast<int>(q / P);
-      const int r = static_cast<int>(q - static_cast<long long>(img[j]) * P);
-      int l = 0;
-#pragma unroll
-      for (int i = 1; i < YB_MAX_LEVELS; ++i)
-        if (i < p.n_levels && r >= p.pix_start[i]) l = i;
-      lv[j] = l;
-      const int rr = r - p.pix_start[l];
-      py[j] = rr / p.lvl[l].W;
-      px[j] = rr - py[j] * p.lvl[l].W;
-      const yb_head_level& L = p.lvl[l];
-      const long long off = img[j] * L.stride_n + py[j] * L.stride_y + px[j] * L.stride_x;   // elements
-      if (lane * 8 < L.stride_x) {
-        const uint4 v = ld_stream_16(static_cast<const uint8_t*>(L.logits) + (off + lane * 8) * 2);
-        *reinterpret_cast<uint4*>(&s_rows[warp][j][lane * 16]) = v;
-      }
+    const long long off_j = __shfl_sync(0xffffffffu, off, j);
+    const int lv_j = __shfl_sync(0xffffffffu, lv, j);
+    const int chunks_j = __shfl_sync(0xffffffffu, row_chunks, j);
+    if (lane < chunks_j) {
+      const uint8_t* src = static_cast<const uint8_t*>(p.lvl[lv_j].logits) + (off_j + lane * 8) * 2;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s_base + j * kRowPitch + lane * 16), "l"(src) : "memory");
     }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncwarp();
+  // objectness of this lane's pixel, all anchors
+  const uint8_t* my_row = s_rows + lane * kRowPitch;
+  float obj[YB_MAX_ANCHORS];
+  uint32_t pass_bits = 0;
 #pragma unroll
-  for (int j = 0; j < kRowPixels; ++j) {
-    if (!valid[j]) break;
-    const uint8_t* row = s_rows[warp][j];
-    const yb_head_level& L = p.lvl[lv[j]];
-    float obj = 0.f;
-    bool pass = false;
-    if (lane < p.n_anchors) {
-      obj = sigmoidf_ref(row_elem<T>(row, lane * K + 4));
-      pass = obj > p.score_thresh;   // score = cls*obj <= obj
+  for (int a = 0; a < YB_MAX_ANCHORS; ++a) {
+    obj[a] = 0.f;
+    if (a < p.n_anchors && valid) {
+      obj[a] = sigmoidf_ref(row_elem<T>(my_row, a * K + 4));
+      if (obj[a] > p.score_thresh) pass_bits |= 1u << a;   // score = cls*obj <= obj
     }
-    uint32_t todo = __ballot_sync(0xffffffffu, pass);
+  }
+  // passing (pixel, anchor) pairs: the whole warp scans the classes of one pair at a time
+#pragma unroll
+  for (int a = 0; a < YB_MAX_ANCHORS; ++a) {
+    if (a >= p.n_anchors) break;
+    uint32_t todo = __ballot_sync(0xffffffffu, (pass_bits >> a) & 1u);
     while (todo) {
-      const int a = __ffs(todo) - 1;
+      const int src = __ffs(todo) - 1;
       todo &= todo - 1;
-      const float s_obj = __shfl_sync(0xffffffffu, obj, a);
-      const int anchor = p.lvl_start[lv[j]] + (a * L.H + py[j]) * L.W + px[j];
+      const float s_obj = __shfl_sync(0xffffffffu, obj[a], src);
+      const int s_img = __shfl_sync(0xffffffffu, img, src);
+      const int s_lv = __shfl_sync(0xffffffffu, lv, src);
+      const int s_px = __shfl_sync(0xffffffffu, px, src);
+      const int s_py = __shfl_sync(0xffffffffu, py, src);
+      const yb_head_level& L = p.lvl[s_lv];
+      const uint8_t* row = s_rows + src * kRowPitch;
+      const int anchor = p.lvl_start[s_lv] + (a * L.H + s_py) * L.W + s_px;
       bool any = false;
       for (int k0 = 0; k0 < p.n_classes; k0 += 32) {
         const int k = k0 + lane;
@@ -253,14 +268,14 @@ decode_rows_kernel(const __grid_constant__ DecodeParams p, Workspace ws) {
         if (cm == 0) continue;
         any = true;
         int base = 0;
-        if (lane == 0) base = atomicAdd(&ws.img_count[img[j]], __popc(cm));
+        if (lane == 0) base = atomicAdd(&ws.img_count[s_img], __popc(cm));
         base = __shfl_sync(0xffffffffu, base, 0);
         if (cand) {
           const int slot = base + __popc(cm & ((1u << lane) - 1u));
           if (slot < p.cap_per_image) {
             const uint64_t key = (static_cast<uint64_t>(orderable_desc(score)) << 32) |
                                  static_cast<uint32_t>(anchor * p.n_classes + k);
-            ws.keys_a[static_cast<long long>(img[j]) * p.cap_per_image + slot] = key;
+            ws.keys_a[static_cast<long long>(s_img) * p.cap_per_image + slot] = key;
           }
         }
       }
@@ -270,9 +285,9 @@ decode_rows_kernel(const __grid_constant__ DecodeParams p, Workspace ws) {
         const float sx = __shfl_sync(0xffffffffu, t, 0), sy = __shfl_sync(0xffffffffu, t, 1);
         const float sw = __shfl_sync(0xffffffffu, t, 2), sh = __shfl_sync(0xffffffffu, t, 3);
         if (lane == 0) {
-          const float4 b = decode_box(sx, sy, sw, sh, px[j], py[j], L.stride_px, L.anchors_px[2 * a], L.anchors_px[2 * a + 1]);
-          ws.boxes[static_cast<long long>(img[j]) * p.anchors_per_image + anchor] = b;
-          atomicMax(&ws.img_maxc[img[j]], float_to_ordered_int(fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
+          const float4 b = decode_box(sx, sy, sw, sh, s_px, s_py, L.stride_px, L.anchors_px[2 * a], L.anchors_px[2 * a + 1]);
+          ws.boxes[static_cast<long long>(s_img) * p.anchors_per_image + anchor] = b;
+          atomicMax(&ws.img_maxc[s_img], float_to_ordered_int(fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w))));
         }
       }
     }
@@ -959,7 +974,7 @@ extern "C" int yb_decode_candidates(const yb_nms_params* p, const yb_head_level*
   // NHWC rows (the plan's head buffers): every level is [.., A*K logits of one pixel, pad] with 16-bit elements,
   // a 16-byte aligned pitch of at most 512 bytes -> the coalesced row kernel; anything else (the reference's
   // [N,A,H,W,K] layout, fp32 logits) -> one thread per anchor.
-  bool rows = (dtype == YB_F16 || dtype == YB_BF16) && p->n_anchors <= 32;
+  bool rows = (dtype == YB_F16 || dtype == YB_BF16) && p->n_anchors <= YB_MAX_ANCHORS;
   dp.pix_start[0] = 0;
   for (int l = 0; l < YB_MAX_LEVELS; ++l) {
     const bool on = l < p->n_levels;
@@ -976,10 +991,17 @@ extern "C" int yb_decode_candidates(const yb_nms_params* p, const yb_head_level*
   if (rows) {
     const long long pixels = static_cast<long long>(p->n_images) * dp.pix_start[p->n_levels];
     const unsigned rblocks = static_cast<unsigned>((pixels + kRowWarps * kRowPixels - 1) / (kRowWarps * kRowPixels));
+    constexpr int kRowSmem = kRowWarps * kRowPixels * kRowPitch;   // 66 KB
+    static bool configured = false;
+    if (!configured) {
+      YB_CHECK_CUDA(cudaFuncSetAttribute(decode_rows_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem));
+      YB_CHECK_CUDA(cudaFuncSetAttribute(decode_rows_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem));
+      configured = true;
+    }
     if (dtype == YB_F16)
-      decode_rows_kernel<__half><<<rblocks, kRowWarps * 32, 0, stream>>>(dp, ws);
+      decode_rows_kernel<__half><<<rblocks, kRowWarps * 32, kRowSmem, stream>>>(dp, ws);
     else
-      decode_rows_kernel<__nv_bfloat16><<<rblocks, kRowWarps * 32, 0, stream>>>(dp, ws);
+      decode_rows_kernel<__nv_bfloat16><<<rblocks, kRowWarps * 32, kRowSmem, stream>>>(dp, ws);
     YB_CHECK_CUDA(cudaGetLastError());
     return YB_OK;
   }

@@ -413,7 +413,19 @@ class Lowered:
                                 for op in self.L.ops if op.weight is not None)
 
 
-def assign_offsets(L: _Lowering, x0: _Buf, keep: List[_Buf], N: int, H: int, W: int, reuse: bool, esz: int = 2):
+def front_op_count(L: _Lowering) -> int:
+    """Number of leading ops that only touch the stride-2/4/8 levels (stem .. the first tapped C3): the part of the plan
+    `YOLOv5.predict` can run per image chunk while later chunks are still crossing PCIe."""
+    n = 0
+    for op in L.ops:
+        if op.dst.buf.div > 8 or op.src.buf.div > 8 or op.kind != _C.YB_OP_CONV:
+            break
+        n += 1
+    return n
+
+
+def assign_offsets(L: _Lowering, x0: _Buf, keep: List[_Buf], N: int, H: int, W: int, reuse: bool, esz: int = 2,
+                   front_ops: int = 0):
     """Arena layout for one (N, H, W): byte offset per buffer and the arena size.
 
     With `reuse`, a buffer occupies its bytes only from its first writer to its last reader (launch order is the op
@@ -434,6 +446,13 @@ def assign_offsets(L: _Lowering, x0: _Buf, keep: List[_Buf], N: int, H: int, W: 
                 first[id(v.buf)] = min(first[id(v.buf)], i)
     for b in keep:
         last[id(b)] = n_ops
+    # chunked front (PlanInstance.run_front_chunk): the first `front_ops` ops run once per image chunk, so every buffer
+    # they touch must keep its bytes until the last chunk has passed through all of them
+    for i, op in enumerate(L.ops[:front_ops]):
+        for v in (op.dst, op.src, op.residual):
+            if v is not None:
+                first[id(v.buf)] = -1
+                last[id(v.buf)] = max(last[id(v.buf)], front_ops - 1)
     offsets: Dict[int, int] = {}
     if not reuse:
         off = 0
@@ -492,7 +511,8 @@ def assign_offsets(L: _Lowering, x0: _Buf, keep: List[_Buf], N: int, H: int, W: 
 class PlanInstance:
     """Arena + native plan for one (N, H, W); weights come from the Engine's shared `Lowered`."""
 
-    def __init__(self, low: Lowered, N: int, H: int, W: int, post: Optional[dict] = None, keep_intermediates: bool = False):
+    def __init__(self, low: Lowered, N: int, H: int, W: int, post: Optional[dict] = None, keep_intermediates: bool = False,
+                 chunked: bool = False):
         L, x0, head_bufs, feats = low.L, low.x0, low.head_bufs, low.feats
         grain = max(b.div for b in L.bufs)
         if H % grain or W % grain:
@@ -503,7 +523,11 @@ class PlanInstance:
         esz = 2
         # the input canvas stays live too, so that a plan can be re-run (timing loops, tests) without re-letterboxing
         keep = [x0] + list(head_bufs) + [v.buf for v in feats.values()]
-        offsets, total = assign_offsets(L, x0, keep, N, H, W, reuse=not keep_intermediates, esz=esz)
+        # chunked front: 4 chunks when the batch divides (>= 4 images per chunk)
+        self.front_ops = front_op_count(L) if (chunked and N % 4 == 0 and N >= 16 and not keep_intermediates) else 0
+        self.front_chunks = 4 if self.front_ops else 0
+        offsets, total = assign_offsets(L, x0, keep, N, H, W, reuse=not keep_intermediates, esz=esz,
+                                        front_ops=self.front_ops)
         self.arena = torch.zeros((max(total, 1024),), dtype=torch.uint8, device=L.device)
         self.arena_bytes = total
         self.unshared_bytes = sum(_round_up(N * (H // b.div) * (W // b.div) * b.C * esz, 1024) for b in L.bufs)
@@ -546,6 +570,8 @@ class PlanInstance:
         self._low = low                     # keeps the shared weights alive
         self.n_heads = low.n_heads
         self.plan = _C.Plan(descs, L.device)
+        self._descs = descs
+        self._front_plans: Optional[List[_C.Plan]] = None
         # Second launch list whose head convolutions decode + threshold in their epilogue and append candidates to a
         # fixed NMS arena instead of storing logits (box_head.py:68-82 + :328-360,418 fused).
         self.fused_post = None
@@ -604,6 +630,44 @@ class PlanInstance:
                     self.plan.run()
             self.__dict__["_graph"] = g
         g.replay()
+
+    # -- chunked front ----------------------------------------------------------------------------------------------
+    def _build_front_plans(self) -> None:
+        """Launch lists of ops [0, front_ops) restricted to the images of one chunk: same descriptors, N = chunk and
+        every tensor pointer advanced by the chunk's images (activations are NHWC, image-major)."""
+        import ctypes as _ct
+
+        L = self._low.L
+        c = self.N // self.front_chunks
+        esz = 2
+        plans = []
+        for k in range(self.front_chunks):
+            ds = []
+            for op, d in zip(L.ops[: self.front_ops], self._descs[: self.front_ops]):
+                d2 = _C.OpDesc.from_buffer_copy(d)
+                d2.N = c
+
+                def adv(view):
+                    return k * c * (self.H // view.buf.div) * (self.W // view.buf.div) * view.buf.C * esz
+
+                d2.in_ = d.in_ + adv(op.src)
+                d2.out = d.out + adv(op.dst)
+                if op.residual is not None:
+                    d2.residual = d.residual + adv(op.residual)
+                ds.append(d2)
+            plans.append(_C.Plan(ds, self.device))
+        self._front_plans = plans
+
+    def run_front_chunk(self, k: int) -> None:
+        """Ops [0, front_ops) over the images of chunk k only (their slice of `self.input` must be written)."""
+        if self._front_plans is None:
+            with _C.device_guard(self.device):
+                self._build_front_plans()
+        self._front_plans[k].run()
+
+    def run_rest(self) -> None:
+        """Ops [front_ops, end) over the whole batch, after every chunk went through `run_front_chunk`."""
+        self.plan.run(self.front_ops, self.plan.n_ops - self.front_ops)
 
     def run_backbone(self) -> None:
         """Everything but the detection-head convolutions (`YOLO.backbone`)."""
@@ -674,17 +738,21 @@ class Engine:
         except Exception:
             return 64 << 30
 
-    def plan(self, N: int, H: int, W: int, post: Optional[dict] = None, keep_intermediates: bool = False) -> PlanInstance:
+    def plan(self, N: int, H: int, W: int, post: Optional[dict] = None, keep_intermediates: bool = False,
+             chunked: bool = False) -> PlanInstance:
+        """`chunked`: a plan whose first ops can also run per image chunk (PlanInstance.run_front_chunk; the arena keeps
+        the front buffers live, so it is a separate instance from the plain plan of the same shape)."""
         low = self.lowered()
         pkey = None if post is None else (post["score_thresh"], post["nms_thresh"], post["detections_per_img"],
                                           post["semantics"], post["num_classes"])
-        key = (N, H, W, pkey, bool(keep_intermediates))
+        chunked = bool(chunked and N % 4 == 0 and N >= 16 and not keep_intermediates)
+        key = (N, H, W, pkey, bool(keep_intermediates), chunked)
         inst = self._plans.get(key)
         if inst is not None:
             self._plans.move_to_end(key)
             return inst
         with _C.device_guard(self.device):
-            inst = PlanInstance(low, N, H, W, post, keep_intermediates)
+            inst = PlanInstance(low, N, H, W, post, keep_intermediates, chunked)
         inst.use_graph = bool(self.graphs)
         self._plans[key] = inst
         budget = self._budget()

@@ -129,13 +129,14 @@ class YOLO(nn.Module):
                 "nms_thresh": float(pp.nms_thresh), "detections_per_img": int(pp.detections_per_img),
                 "semantics": int(getattr(pp, "nms_semantics", _C.NMS_TV_AUTO))}
 
-    def get_plan(self, N: int, H: int, W: int, keep_intermediates: bool = False):
+    def get_plan(self, N: int, H: int, W: int, keep_intermediates: bool = False, chunked: bool = False):
         """Plan instance for a batch of N canvases of H x W.  `keep_intermediates=True` gives every activation its
-        own bytes (inspection / stage-wise tests); the default arena reuses the bytes of dead activations."""
+        own bytes (inspection / stage-wise tests); the default arena reuses the bytes of dead activations.
+        `chunked=True`: the variant `YOLOv5.predict` uses for host inputs (front ops runnable per image chunk)."""
         # The fused decode epilogue (heads emit NMS candidates instead of logits) is functional but, as measured in
         # round 1, slower than storing fp16 logits + the stand-alone decode kernel; opt-in until it is tuned.
         fuse = os.environ.get("YB_FUSED_DECODE", "0") == "1"
-        return self.engine().plan(N, H, W, self.post_config() if fuse else None, keep_intermediates)
+        return self.engine().plan(N, H, W, self.post_config() if fuse else None, keep_intermediates, chunked and not fuse)
 
     def has_hooks(self) -> bool:
         """True when a forward (pre-)hook sits on backbone / head / post_process (yolort/utils/hooks.py:15-17): the
@@ -189,6 +190,13 @@ class YOLO(nn.Module):
         """backbone + PAN + head on the prepared input canvas; returns the raw head logits (NHWC)."""
         plan.run()
         return plan.heads
+
+    def post_padded(self, plan, rescale: Optional[Tensor] = None):
+        """Post-processing over the head logits a plan has already produced; padded device outputs."""
+        pc = self.post_config()
+        return _C.decode_nms_padded(plan.heads, "nhwc", pc["strides"], pc["anchors_px"], pc["num_classes"],
+                                    pc["score_thresh"], pc["nms_thresh"], pc["detections_per_img"], pc["semantics"],
+                                    rescale)
 
     def detect_padded(self, plan, rescale: Optional[Tensor] = None):
         """Runs the plan and the post-processing; padded device outputs, no host synchronisation."""

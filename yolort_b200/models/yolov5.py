@@ -167,60 +167,66 @@ class YOLOv5(nn.Module):
         while pending:
             yield finish(pending.popleft())
 
-    # Opt-in (YB_PIPELINE_H2D=1): host batches are processed in two halves, the PCIe copy of the second half (copy
-    # stream) overlapping the letterbox + backbone + NMS of the first (compute stream); both halves are letterboxed
-    # to the canvas of the WHOLE batch, so the detections are those of the unsplit call.  Measured on B200 at
-    # batch 32 it LOSES (8.3 k vs 9.7 k img/s): two half-size plans under-fill the 148 SMs by more than the
-    # ~0.4 ms of hidden copy time, so the default stays off.
+    # -- predict() on host tensors: the H2D copy hidden behind the front of the network ---------------------------------
+    # A synchronous predict(list of host images) used to be  H2D (0.8 ms for 32 x 640^2 uint8)  ->  compute  ->  read
+    # back, the PCIe copy fully exposed.  Now the batch crosses PCIe in four chunks on a copy stream; as soon as a chunk
+    # has landed the compute stream letterboxes it and runs the front of the plan on those images only (stem ..
+    # first tapped C3: the stride-2/4/8 levels, thousands of tiles even for 8 images), so the front of chunk k overlaps
+    # the copy of chunk k+1; the rest of the plan, the decode and the NMS run once over the whole batch.  Same kernels
+    # on the same per-image data: the detections are bit-identical to the device-resident call.
     _PIPELINE_MIN_IMAGES = 16
 
     def _predict_pipelined(self, x: Any) -> Optional[List[Dict[str, Tensor]]]:
-        import os
-
-        if os.environ.get("YB_PIPELINE_H2D", "0") != "1" or self.training:
+        if self.training or self.model.has_hooks():
             return None
-        if not (isinstance(x, (list, tuple)) and len(x) >= self._PIPELINE_MIN_IMAGES
-                and all(isinstance(t, Tensor) and not t.is_cuda and t.dim() == 3 for t in x)):
+        if not (isinstance(x, (list, tuple)) and len(x) >= self._PIPELINE_MIN_IMAGES and len(x) % 4 == 0
+                and all(isinstance(t, Tensor) and not t.is_cuda and t.dim() == 3 and t.dtype == x[0].dtype for t in x)):
             return None
         p = next(self.parameters())
         if p.device.type != "cuda":
             return None
+        from ..relay.logits_decoder import LogitsDecoder
+
+        if isinstance(self.model.post_process, LogitsDecoder):
+            return None
+        n = len(x)
         sizes = [(int(t.shape[-2]), int(t.shape[-1])) for t in x]
         tr = self.transform
-        _, canvas = _C.letterbox_geometry(sizes, float(tr.min_size), float(tr.max_size), tr.size_divisible, tr.fixed_shape)
-        half = (len(x) + 1) // 2
-        parts = [list(x[:half]), list(x[half:])]
-        compute = torch.cuda.current_stream(p.device)
-        if not hasattr(self, "_copy_stream"):
-            self._copy_stream = torch.cuda.Stream(p.device)
-        copy = self._copy_stream
-        copy.wait_stream(compute)
-        staged = []
-        for part in parts:
-            with torch.cuda.stream(copy):
-                dev = self.collate_images(part, None)
-                ev = torch.cuda.Event()
-                ev.record(copy)
-            staged.append((dev, ev))
-        outs = []
-        for dev, ev in staged:
-            compute.wait_event(ev)
-            for t in dev:
-                t.record_stream(compute)
-            outs.append(self.forward_padded(dev, batch_hw=canvas))
-        counts = torch.cat([o[3].to(torch.int64) for o in outs] + [o[4] for o in outs]).cpu()
-        n0, n1 = len(parts[0]), len(parts[1])
-        st = counts[n0 + n1:].view(2, 4)
-        if int(st[0, 1]) != 0 or int(st[1, 1]) != 0:
-            return None   # candidate arena overflow: let the synchronous path grow it
-        res, k = [], 0
-        for o, n in zip(outs, (n0, n1)):
-            boxes, scores, labels = o[0], o[1], o[2]
-            for i in range(n):
-                c = int(counts[k])
-                k += 1
-                res.append({"scores": scores[i, :c], "labels": labels[i, :c], "boxes": boxes[i, :c]})
-        return res
+        geoms, (Hb, Wb) = _C.letterbox_geometry(sizes, float(tr.min_size), float(tr.max_size), tr.size_divisible, tr.fixed_shape)
+        plan = self.model.get_plan(n, Hb, Wb, chunked=True)
+        if not plan.front_chunks or plan.fused_post is not None:
+            return None
+        dev = p.device
+        with _C.device_guard(dev):
+            compute = torch.cuda.current_stream(dev)
+            if not hasattr(self, "_copy_stream"):
+                self._copy_stream = torch.cuda.Stream(dev)
+            copy = self._copy_stream
+            copy.wait_stream(compute)          # the previous call's reads of recycled staging memory are done
+            c = n // plan.front_chunks
+            staged = []
+            for k in range(plan.front_chunks):
+                with torch.cuda.stream(copy):
+                    part = self.collate_images(list(x[k * c:(k + 1) * c]), None)
+                    ev = torch.cuda.Event()
+                    ev.record(copy)
+                staged.append((part, ev))
+            GeomArr = _C.LetterboxGeom * c
+            for k, (part, ev) in enumerate(staged):
+                compute.wait_event(ev)
+                for t in part:
+                    t.record_stream(compute)
+                gk = GeomArr(*[geoms[k * c + j] for j in range(c)])
+                self.transform.letterbox_into(part, gk, Hb, Wb, plan.input[k * c:(k + 1) * c], _C.YB_LAYOUT_S2D16)
+                plan.run_front_chunk(k)
+            plan.run_rest()
+            rescale = self.transform.rescale_params((Hb, Wb), sizes).to(dev, non_blocking=True)
+            boxes, scores, labels, counts, status = self.model.post_padded(plan, rescale)
+            host = torch.cat([counts.to(torch.int64), status]).cpu()
+        if int(host[n + 1]) != 0:
+            return None       # candidate arena overflow: the plain path grows it
+        return [{"scores": scores[i, :int(host[i])], "labels": labels[i, :int(host[i])], "boxes": boxes[i, :int(host[i])]}
+                for i in range(n)]
 
     def default_loader(self, img_path: str) -> Tensor:
         """uint8 RGB [3,H,W]; the `/ 255.0` of the reference loader (yolov5.py:228) happens in the kernel."""
