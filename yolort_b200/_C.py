@@ -300,8 +300,15 @@ def letterbox(images: List[torch.Tensor], geoms, Hb: int, Wb: int, fill: float, 
                                          int(Hb), int(Wb), float(fill), lut.data_ptr() if lut is not None else None,
                                          out.data_ptr(), dtype_code(out.dtype), int(layout), current_stream_ptr(dev)),
               "yb_letterbox")
-    for im in keep:  # the kernel reads the sources asynchronously on this stream
-        im.record_stream(torch.cuda.current_stream(dev))
+    # the kernel reads the sources asynchronously on this stream: one record per distinct storage (the images of a
+    # packed batch are views of one buffer)
+    stream = torch.cuda.current_stream(dev)
+    seen = set()
+    for im in keep:
+        key = im.untyped_storage().data_ptr()
+        if key not in seen:
+            seen.add(key)
+            im.record_stream(stream)
     return out
 
 
@@ -470,18 +477,14 @@ def decode_nms(head_outputs: List[torch.Tensor], layout: str, strides, anchors_p
         boxes, scores, labels, counts, status = decode_nms_padded(
             head_outputs, layout, strides, anchors_px, num_classes, score_thresh, nms_thresh,
             detections_per_img, semantics, rescale)
-        host = torch.cat([counts.to(torch.int64), status]).cpu()
+        host = torch.cat([counts.to(torch.int64), status]).tolist()     # one D2H + one conversion for the whole batch
         n = counts.numel()
-        if int(host[n + 1]) == 0:
+        if host[n + 1] == 0:
             break
         arena = _arenas[dev]
         arena.cap_per_image = max(2 * arena.cap_per_image, int(host[n + 2]))
         arena.ws = None
-    out = []
-    for i in range(n):
-        c = int(host[i])
-        out.append({"scores": scores[i, :c], "labels": labels[i, :c], "boxes": boxes[i, :c]})
-    return out
+    return [{"scores": scores[i, :host[i]], "labels": labels[i, :host[i]], "boxes": boxes[i, :host[i]]} for i in range(n)]
 
 
 class FusedPost:

@@ -243,7 +243,15 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_slot;
+  // Programmatic dependent launch: everything above overlapped the tail of the previous kernel in the stream.  The
+  // weight producer (warp 2) does not wait at all -- weights do not depend on the previous kernel, so the resident set
+  // (or the first slabs of the ring) streams in while the previous kernel drains; every other warp touches activations
+  // (or stores over them) and waits for the previous grid to complete first.
+#ifdef YB_NO_WEIGHT_PREFETCH      // A/B build: every warp waits (scripts/ab_step.sh)
   asm volatile("griddepcontrol.wait;" ::: "memory");
+#else
+  if (warp != 2) asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {

@@ -125,8 +125,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   // Programmatic dependent launch: everything above overlapped the tail of the previous kernel in the
   // stream; from here on we touch memory it produced.  Let our own dependent start its prologue too.
+  // Resident weights do not depend on the previous kernel: their loads are issued BEFORE the grid-dependency wait
+  // and stream in while the previous kernel drains.
+#ifndef YB_NO_WEIGHT_PREFETCH
+  if (warp == 0 && lane == 0 && p.b_resident) {
+    const uint32_t b_bytes = p.block_n * p.block_k * 2;
+    mbar_expect_tx(&b_full, p.num_k_iters * b_bytes);
+    for (int it = 0; it < p.num_k_iters; ++it)
+      tma_load_2d(&tmap_b, &b_full, b_res + it * p.b_stage_bytes, it * p.block_k, 0);
+  }
+#endif
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#ifdef YB_NO_WEIGHT_PREFETCH      // A/B build: weights fetched after the wait (scripts/ab_step.sh)
+  if (warp == 0 && lane == 0 && p.b_resident) {
+    const uint32_t b_bytes = p.block_n * p.block_k * 2;
+    mbar_expect_tx(&b_full, p.num_k_iters * b_bytes);
+    for (int it = 0; it < p.num_k_iters; ++it)
+      tma_load_2d(&tmap_b, &b_full, b_res + it * p.b_stage_bytes, it * p.block_k, 0);
+  }
+#endif
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -136,11 +154,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // shallow layers).
     if (YB_ROLE_LANES(lane)) {
       const uint32_t a_bytes = kBlockM * p.block_k * 2, b_bytes = p.block_n * p.block_k * 2;
-      if (p.b_resident && lane == 0) {
-        mbar_expect_tx(&b_full, p.num_k_iters * b_bytes);
-        for (int it = 0; it < p.num_k_iters; ++it)
-          tma_load_2d(&tmap_b, &b_full, b_res + it * p.b_stage_bytes, it * p.block_k, 0);
-      }
       int kit = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles;

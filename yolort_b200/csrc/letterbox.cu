@@ -246,17 +246,19 @@ __device__ __forceinline__ void sample_rgb_staged(const ImgGeom& g, const Staged
 template <typename DstT, bool kHwc>
 __global__ void __launch_bounds__(kTileThreads)
 letterbox_s2d_tile_kernel(const __grid_constant__ BatchGeom bg, int img0, int Hb, int Wb, float fill, const float* lut,
-                          DstT* __restrict__ dst) {
+                          DstT* __restrict__ dst, int smem_bytes) {
   __shared__ float s_lut[256];
-  __shared__ __align__(16) uint8_t s_src[kTileSmem];
+  __shared__ DstT s_lut_out[256];             // the same table already rounded to the output dtype (copy fast path)
+  extern __shared__ __align__(16) uint8_t s_src[];   // staging bytes: `smem_bytes` (sized by the host for this batch)
   __shared__ uint16_t s_mis[kTileMaxLines];
-  __shared__ int s_rect[6];   // y_lo, rows, x_lo, cols, pitch, staged?
+  __shared__ int s_rect[7];   // y_lo, rows, x_lo, cols, pitch, staged?, identity tile fully inside the image?
   const int tid = threadIdx.x;
   const int li = blockIdx.z;
   const ImgGeom& g = bg.img[li];
   const int W2 = Wb >> 1, H2 = Hb >> 1;
   const int X0 = blockIdx.x * kTileX, Y0 = blockIdx.y * kTileY;
   s_lut[tid] = lut[tid];
+  s_lut_out[tid] = cvt_out<DstT>(lut[tid]);
   // canvas rows / columns of this tile that fall inside the resized image
   const int cy0 = max(2 * Y0, g.top), cy1 = min(min(2 * (Y0 + kTileY), Hb), g.top + g.new_h) - 1;
   const int cx0 = max(2 * X0, g.left), cx1 = min(min(2 * (X0 + kTileX), Wb), g.left + g.new_w) - 1;
@@ -280,7 +282,11 @@ letterbox_s2d_tile_kernel(const __grid_constant__ BatchGeom bg, int img0, int Hb
     const int pitch = (line_bytes + 15 + 15) / 16 * 16;     // room for the leading misalignment
     const int lines = kHwc ? rows : 3 * rows;
     s_rect[0] = y_lo; s_rect[1] = rows; s_rect[2] = x_lo; s_rect[3] = cols; s_rect[4] = pitch;
-    s_rect[5] = (any && lines <= kTileMaxLines && lines * pitch <= kTileSmem) ? 1 : 0;
+    s_rect[5] = (any && lines <= kTileMaxLines && lines * pitch <= smem_bytes) ? 1 : 0;
+    // identity resize and every canvas pixel of the tile inside the image: the copy fast path below (no per-pixel
+    // bounds / interpolation logic; the 640 x 640 headline case is all such tiles)
+    s_rect[6] = (s_rect[5] && g.new_h == g.src_h && g.new_w == g.src_w && cy0 == 2 * Y0 && cx0 == 2 * X0 &&
+                 cy1 == 2 * (Y0 + kTileY) - 1 && cx1 == 2 * (X0 + kTileX) - 1) ? 1 : 0;
   }
   __syncthreads();
   const int y_lo = s_rect[0], rows = s_rect[1], x_lo = s_rect[2], cols = s_rect[3], pitch = s_rect[4];
@@ -309,6 +315,33 @@ letterbox_s2d_tile_kernel(const __grid_constant__ BatchGeom bg, int img0, int Hb
   StagedSrc<kHwc> S{s_src, s_mis, pitch, rows, y_lo, x_lo};
   const int X = X0 + (tid & (kTileX - 1));
   if (X >= W2) return;
+  if (s_rect[6]) {
+    // copy fast path: this thread's 2x2 canvas block = source pixels (2Y+dy - top, 2X+dx - left); per (row, channel)
+    // the two horizontally adjacent bytes sit side by side in the staged line
+    const int bx = 2 * (X - X0);                                   // x offset inside the staged rectangle
+#pragma unroll
+    for (int k = 0; k < (kTileY * kTileX) / kTileThreads; ++k) {
+      const int Yl = (tid / kTileX) + k * (kTileThreads / kTileX);     // s2d row inside the tile
+      __align__(16) DstT v[16];
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int r = 2 * Yl + dy;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int line = kHwc ? r : c * rows + r;
+          const uint8_t* ln = s_src + line * pitch + s_mis[line] + (kHwc ? 3 * bx + c : bx);
+          v[(dy * 2 + 0) * 4 + c] = s_lut_out[ln[0]];
+          v[(dy * 2 + 1) * 4 + c] = s_lut_out[ln[kHwc ? 3 : 1]];
+        }
+        v[(dy * 2 + 0) * 4 + 3] = cvt_out<DstT>(0.f);
+        v[(dy * 2 + 1) * 4 + 3] = cvt_out<DstT>(0.f);
+      }
+      DstT* o = dst + ((static_cast<size_t>(img0 + li) * H2 + (Y0 + Yl)) * W2 + X) * 16;
+      reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(v)[0];
+      reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(v)[1];
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < (kTileY * kTileX) / kTileThreads; ++k) {
     const int Y = Y0 + (tid / kTileX) + k * (kTileThreads / kTileX);
@@ -348,7 +381,19 @@ int launch_typed(const BatchGeom& bg, int img0, int count, int Hb, int Wb, float
                                                                     static_cast<DstT*>(dst));
   } else if constexpr (std::is_same<SrcT, uint8_t>::value && sizeof(DstT) == 2) {
     dim3 grid((Wb / 2 + kTileX - 1) / kTileX, (Hb / 2 + kTileY - 1) / kTileY, count);
-    letterbox_s2d_tile_kernel<DstT, kHwc><<<grid, kTileThreads, 0, stream>>>(bg, img0, Hb, Wb, fill, lut, static_cast<DstT*>(dst));
+    // staging bytes for the largest source rectangle of a 16 x 128 output tile in this batch (identity resizes need
+    // 8 KB, a 2x down-scale ~31 KB): small footprints let more CTAs share an SM and hide the load -> sample latency
+    int need = 0;
+    for (int j = 0; j < count; ++j) {
+      const ImgGeom& g = bg.img[j];
+      const int rows = static_cast<int>(2 * kTileY * g.ratio_h) + 3, cols = static_cast<int>(2 * kTileX * g.ratio_w) + 3;
+      const int line_bytes = kHwc ? 3 * cols : cols;
+      const int bytes = (kHwc ? rows : 3 * rows) * ((line_bytes + 30) / 16 * 16);
+      if (bytes > need) need = bytes;
+    }
+    if (need > kTileSmem) need = kTileSmem;       // larger rectangles take the direct-sampling path inside the kernel
+    need = (need + 1023) / 1024 * 1024;
+    letterbox_s2d_tile_kernel<DstT, kHwc><<<grid, kTileThreads, need, stream>>>(bg, img0, Hb, Wb, fill, lut, static_cast<DstT*>(dst), need);
   } else {
     dim3 grid((Wb / 2 + threads - 1) / threads, (Hb / 2 + kRowsPerBlock - 1) / kRowsPerBlock, count);
     letterbox_s2d_kernel<SrcT, DstT, kHwc><<<grid, threads, 0, stream>>>(bg, img0, Hb, Wb, fill, lut,

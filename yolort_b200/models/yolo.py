@@ -222,10 +222,10 @@ class YOLO(nn.Module):
         if plan.fused_post is not None:
             boxes, scores, labels, counts, status = self.detect_padded(plan, rescale)
             n = counts.numel()
-            host = torch.cat([counts.to(torch.int64), status]).cpu()
-            if int(host[n + 1]) == 0:
-                return [{"scores": scores[i, :int(host[i])], "labels": labels[i, :int(host[i])],
-                         "boxes": boxes[i, :int(host[i])]} for i in range(n)]
+            host = torch.cat([counts.to(torch.int64), status]).tolist()     # one D2H + one conversion for the whole batch
+            if host[n + 1] == 0:
+                return [{"scores": scores[i, :host[i]], "labels": labels[i, :host[i]], "boxes": boxes[i, :host[i]]}
+                        for i in range(n)]
             # an image overflowed its share of the fixed arena: redo the post-processing on stored logits with the
             # growable arena (never truncate)
         heads = self.run_plan(plan)

@@ -56,7 +56,7 @@ class YOLOv5(nn.Module):
         geoms, (Hb, Wb) = self.transform.geometry(inputs, batch_hw)
         plan = self.model.get_plan(len(inputs), Hb, Wb)
         self.transform.letterbox_into(inputs, geoms, Hb, Wb, plan.input, _C.YB_LAYOUT_S2D16)
-        rescale = self.transform.rescale_params((Hb, Wb), original_image_sizes).to(plan.device, non_blocking=True)
+        rescale = self.transform.rescale_params_device((Hb, Wb), original_image_sizes, plan.device)
         return plan, rescale
 
     def forward(self, inputs: List[Tensor], targets: Optional[List[Dict[str, Tensor]]] = None):
@@ -128,11 +128,12 @@ class YOLOv5(nn.Module):
         def finish(item):
             done, host_packed, host_meta, n, batch = item
             done.synchronize()
-            if int(host_meta[n + 1]) != 0:       # candidate arena overflow: the synchronous path grows it
+            meta = host_meta.tolist()
+            if meta[n + 1] != 0:       # candidate arena overflow: the synchronous path grows it
                 return [{k: v.cpu() for k, v in d.items()} for d in self.predict(batch)]
             out = []
             for i in range(n):
-                c = int(host_meta[i])
+                c = meta[i]
                 row = host_packed[i, :c]
                 out.append({"scores": row[:, 4].clone(), "labels": row[:, 5].to(torch.int64), "boxes": row[:, :4].clone()})
             return out
@@ -220,13 +221,12 @@ class YOLOv5(nn.Module):
                 self.transform.letterbox_into(part, gk, Hb, Wb, plan.input[k * c:(k + 1) * c], _C.YB_LAYOUT_S2D16)
                 plan.run_front_chunk(k)
             plan.run_rest()
-            rescale = self.transform.rescale_params((Hb, Wb), sizes).to(dev, non_blocking=True)
+            rescale = self.transform.rescale_params_device((Hb, Wb), sizes, dev)
             boxes, scores, labels, counts, status = self.model.post_padded(plan, rescale)
-            host = torch.cat([counts.to(torch.int64), status]).cpu()
-        if int(host[n + 1]) != 0:
+            host = torch.cat([counts.to(torch.int64), status]).tolist()
+        if host[n + 1] != 0:
             return None       # candidate arena overflow: the plain path grows it
-        return [{"scores": scores[i, :int(host[i])], "labels": labels[i, :int(host[i])], "boxes": boxes[i, :int(host[i])]}
-                for i in range(n)]
+        return [{"scores": scores[i, :host[i]], "labels": labels[i, :host[i]], "boxes": boxes[i, :host[i]]} for i in range(n)]
 
     def default_loader(self, img_path: str) -> Tensor:
         """uint8 RGB [3,H,W]; the `/ 255.0` of the reference loader (yolov5.py:228) happens in the kernel."""
