@@ -72,11 +72,12 @@ def test_nms_semantic_corner_cases():
 
 
 def test_candidate_arena_grows_instead_of_truncating():
-    # ~190k candidates in one image (> default per-image share of the arena): must re-run, not truncate
+    # ~86k candidates in one image (> the default 16 384 per-image share of the arena): must re-run, not truncate
+    # (the oracle's per-class NMS is quadratic: a 16x larger version of this test took 50 s of CPU)
     g = torch.Generator().manual_seed(8)
-    heads = [torch.randn(1, 3, 160 // s * 4, 160 // s * 4, 85, generator=g) * 1.5 + 1.0 for s in (8, 16, 32)]
+    heads = [torch.randn(1, 3, 160 // s, 160 // s, 85, generator=g) * 1.5 + 1.0 for s in (8, 16, 32)]
     ref = R.postprocess(heads, 0.3, 0.45, 300)[0]
-    assert ref["n_candidates"] > 100000
+    assert ref["n_candidates"] > 30000
     out = PostProcess([8, 16, 32], 0.3, 0.45, 300, anchors_px=[[float(v) for v in a] for a in ANCH])(
         [h.to(DEV) for h in heads])[0]
     util.assert_dets_close(util.to_np(out), ref, box_atol=5e-4, score_atol=2e-6, allow_tie_swaps=True)

@@ -271,3 +271,13 @@ def test_training_mode_contract():
     m = yolov5n().train()
     with pytest.raises((NotImplementedError, _C.NativeLibraryError)):
         m.model(torch.rand(1, 3, 64, 64), None)
+
+
+def test_u8_scaling_by_reciprocal_equals_division_after_16bit_rounding():
+    """csrc/letterbox.cu copy fast path: fp16 / bf16 of `byte * (1/255)` equals fp16 / bf16 of torch's own
+    `byte / 255.0` (yolov5.py:228) for every byte value (the fp32 values differ for 126 of the 256)."""
+    v = torch.arange(256, dtype=torch.uint8)
+    div = v / 255.0
+    mul = v.float() * torch.tensor(1.0 / 255.0, dtype=torch.float32)
+    assert torch.equal(div.half(), mul.half()) and torch.equal(div.bfloat16(), mul.bfloat16())
+    assert not torch.equal(div, mul)

@@ -248,7 +248,6 @@ __global__ void __launch_bounds__(kTileThreads)
 letterbox_s2d_tile_kernel(const __grid_constant__ BatchGeom bg, int img0, int Hb, int Wb, float fill, const float* lut,
                           DstT* __restrict__ dst, int smem_bytes) {
   __shared__ float s_lut[256];
-  __shared__ DstT s_lut_out[256];             // the same table already rounded to the output dtype (copy fast path)
   extern __shared__ __align__(16) uint8_t s_src[];   // staging bytes: `smem_bytes` (sized by the host for this batch)
   __shared__ uint16_t s_mis[kTileMaxLines];
   __shared__ int s_rect[7];   // y_lo, rows, x_lo, cols, pitch, staged?, identity tile fully inside the image?
@@ -258,7 +257,6 @@ letterbox_s2d_tile_kernel(const __grid_constant__ BatchGeom bg, int img0, int Hb
   const int W2 = Wb >> 1, H2 = Hb >> 1;
   const int X0 = blockIdx.x * kTileX, Y0 = blockIdx.y * kTileY;
   s_lut[tid] = lut[tid];
-  s_lut_out[tid] = cvt_out<DstT>(lut[tid]);
   // canvas rows / columns of this tile that fall inside the resized image
   const int cy0 = max(2 * Y0, g.top), cy1 = min(min(2 * (Y0 + kTileY), Hb), g.top + g.new_h) - 1;
   const int cx0 = max(2 * X0, g.left), cx1 = min(min(2 * (X0 + kTileX), Wb), g.left + g.new_w) - 1;
@@ -330,8 +328,10 @@ letterbox_s2d_tile_kernel(const __grid_constant__ BatchGeom bg, int img0, int Hb
         for (int c = 0; c < 3; ++c) {
           const int line = kHwc ? r : c * rows + r;
           const uint8_t* ln = s_src + line * pitch + s_mis[line] + (kHwc ? 3 * bx + c : bx);
-          v[(dy * 2 + 0) * 4 + c] = s_lut_out[ln[0]];
-          v[(dy * 2 + 1) * 4 + c] = s_lut_out[ln[kHwc ? 3 : 1]];
+          // fp16 / bf16 of byte * (1/255) equals fp16 / bf16 of torch's byte / 255.0 for all 256 byte values
+          // (tests/test_host_logic.py checks the table), so the copy path needs no LUT round trip through shared memory
+          v[(dy * 2 + 0) * 4 + c] = cvt_out<DstT>(__fmul_rn(static_cast<float>(ln[0]), 1.0f / 255.0f));
+          v[(dy * 2 + 1) * 4 + c] = cvt_out<DstT>(__fmul_rn(static_cast<float>(ln[kHwc ? 3 : 1]), 1.0f / 255.0f));
         }
         v[(dy * 2 + 0) * 4 + 3] = cvt_out<DstT>(0.f);
         v[(dy * 2 + 1) * 4 + 3] = cvt_out<DstT>(0.f);
