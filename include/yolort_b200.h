@@ -112,6 +112,29 @@ typedef struct {
   int32_t* img_maxc;          /* [n] ordered-int max box coordinate                          */
 } yb_head_decode;
 
+/* Optional pointwise tail chained onto a convolution INSIDE the same kernel: the 1x1 convolution that consumes the
+ * first convolution's output tile straight from shared memory (the epilogue's swizzled staging box is exactly the
+ * K-major operand tile the tensor core reads), so the intermediate never makes an HBM round trip and one launch
+ * boundary disappears.  Covers the pointwise chains of the reference's C3 / Bottleneck blocks
+ * (yolort/v5/models/common.py:94-116,149-173):
+ *   cv1||cv2 -> m.0.cv1          (own_C = c of the 2c output channels feed the tail; the first output is stored)
+ *   m.i.cv2 (3x3 + shortcut) -> m.(i+1).cv1
+ *   m.last.cv2 (3x3 + shortcut) -> cv3 over cat(m_out, cv2(x)): `extra` is the cv2 half, first output not stored
+ * tail(x) = act(W2 . [first_out[0:own_C] | extra] + bias2).  Supported when yb_conv_chain_supported() says so. */
+typedef struct {
+  const void* weight;           /* [Cout_pad][K_pad] K-major, K = own_C + extra_C (own channels first)          */
+  const float* bias;            /* [Cout_pad] fp32                                                                */
+  int32_t Cout, Cout_pad, K_pad;
+  int32_t act;
+  void* out;                    /* NHWC view at the first convolution's OUTPUT resolution                         */
+  int32_t out_cstride;
+  int32_t own_C;                /* channels [0, own_C) of the first convolution's output feed the tail           */
+  const void* extra;            /* optional second operand block (NHWC view, output resolution), may be NULL      */
+  int32_t extra_C, extra_cstride;
+  int32_t store_first;          /* 0: the first convolution's output stays on chip (nothing is written to `out`
+                                   of the op itself); 1: it is stored as usual                                    */
+} yb_conv_chain;
+
 /* All activation tensors are NHWC views: element (n,y,x,c) at base[((n*H+y)*W+x)*cstride + c].
  * `cstride` >= channels lets a producer write straight into a slice of a concat buffer. */
 typedef struct {
@@ -132,9 +155,15 @@ typedef struct {
   int32_t res_cstride;
   int32_t reserved;             /* bit 0: keep a 3x3 conv on the generic im2col kernel; bit 1: `weight` is the banded
                                    super-pixel stem matrix [Cout_pad][3][128] (engine.stem_band); bit 2: take the
-                                   halo-patch kernel's stride-2 parity-plane variant whatever the channel counts (tests) */
+                                   halo-patch kernel's stride-2 parity-plane variant whatever the channel counts (tests);
+                                   bit 3: do not split N over CTAs with resident weights (A/B timing, tests) */
   const yb_head_decode* decode; /* optional (host pointer, copied at plan creation): fused decode epilogue */
+  const yb_conv_chain* chain;   /* optional (host pointer, copied at plan creation): chained pointwise tail  */
 } yb_op_desc;
+
+/* 1 if `op` (a YB_OP_CONV with op->chain set) can run as one fused launch on this build, else 0 (the caller then
+ * emits the two convolutions separately).  Pure host logic: no GPU needed. */
+int yb_conv_chain_supported(const yb_op_desc* op);
 
 typedef struct yb_plan yb_plan;
 

@@ -1,0 +1,11 @@
+#!/bin/bash
+# Re-entry validation of HEAD: driver's test command, smoke, bench line, per-layer times, ncu launch list.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
+timeout -s KILL 1200 python -m pytest tests/ -x -q -m gpu -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$? $(tail -1 gpurun_out/pytest_gpu.log)"
+timeout -s KILL 200 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$? $(tail -1 gpurun_out/smoke.log | cut -c1-200)"
+timeout -s KILL 400 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.log 2>&1; tail -1 gpurun_out/bench.log > gpurun_out/bench.json; cut -c1-400 gpurun_out/bench.json
+timeout -s KILL 200 python scripts/layer_times.py > gpurun_out/layer_times.txt 2>&1; tail -2 gpurun_out/layer_times.txt
+timeout -s KILL 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 240 --csv \
+  --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --precondition 0 > gpurun_out/ncu_launches.log 2>&1
+ls -la gpurun_out | grep -E "bench.json|launches|layer"

@@ -35,14 +35,26 @@ def check_plan_stagewise(model_yolo, plan, verbose=True):
     L = plan._low.L
     tol = TOL[plan.dtype]
     out = []
-    for i, op in enumerate(L.ops):
+    # A launch covers one op, or two when a 1x1 convolution rides as the chained tail of its predecessor
+    # (PlanInstance.launch_ops).  keep_intermediates plans store the first output of a fused launch too, so the tail is
+    # checked against fp32 applied to exactly the fp16 tile it consumed on chip.
+    for li, grp in enumerate(plan.launch_ops):
+        snaps = {}
+        for i in grp:
+            op = L.ops[i]
+            if op.residual is not None:
+                snaps[i] = plan.buffers[op.residual.buf.name][..., op.residual.ch0: op.residual.ch0 + op.residual.C].clone()
+        plan.run(li, 1)
+        torch.cuda.synchronize()
+        for i in grp:
+            _check_op(model_yolo, plan, L.ops[i], snaps.get(i), tol, verbose, out, fused=len(grp) > 1)
+    return out
+
+
+def _check_op(model_yolo, plan, op, res_snapshot, tol, verbose, out, fused=False):
+    if True:
         src = plan.buffers[op.src.buf.name][..., op.src.ch0: op.src.ch0 + op.src.C]
         dst = plan.buffers[op.dst.buf.name][..., op.dst.ch0: op.dst.ch0 + op.dst.C]
-        res_snapshot = None
-        if op.residual is not None:
-            res_snapshot = plan.buffers[op.residual.buf.name][..., op.residual.ch0: op.residual.ch0 + op.residual.C].clone()
-        plan.run(i, 1)
-        torch.cuda.synchronize()
         got = _nchw(dst)
         if op.kind == _C.YB_OP_SPP_POOL:
             x = _nchw(src)
@@ -71,6 +83,5 @@ def check_plan_stagewise(model_yolo, plan, verbose=True):
         mx = float(err.max().item())
         if verbose and (bad or mx > 0.05):
             print(f"  stage {op.name}: violations {bad}/{err.numel()} max_abs_err {mx:.3e} ref_absmax {float(ref.abs().max()):.2f}")
-        out.append((op.name, bad, mx))
+        out.append((op.name + (" [fused launch]" if fused else ""), bad, mx))
         del ref, err, got
-    return out

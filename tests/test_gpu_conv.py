@@ -112,6 +112,16 @@ def test_large_m_many_tiles():
     run_conv(8, 80, 80, 64, 64, 3, 1, 1)     # 51 200 pixels -> 400 CTAs
 
 
+def test_silu_strongly_negative_preactivations():
+    """Pre-activations below -8: h + h tanh(h) evaluated with the fp16 tanh approximation cancels there (error up to
+    |v| 2^-12 on a result of a few 1e-3); the kernels switch such batches to v / (1 + e^-v) in fp32
+    (conv_epilogue.cuh: epilogue_batch_exact).  Large biases put ~10 % of the outputs in that range."""
+    run_conv(2, 20, 20, 64, 64, 1, 1, 0, bias_scale=6.0, seed=21)
+    run_conv(2, 24, 24, 64, 64, 3, 1, 1, bias_scale=6.0, seed=22, residual=True)
+    run_conv(2, 20, 20, 64, 128, 1, 1, 0, bias_scale=6.0, seed=23, dtype=torch.bfloat16)
+    run_conv(2, 24, 40, 32, 64, 3, 2, 1, bias_scale=6.0, seed=24)
+
+
 def test_rejects_unsupported():
     d = _C.OpDesc()
     d.kind = 99
@@ -195,3 +205,119 @@ def test_r31_activations(act):
     run_conv(2, 24, 40, 64, 64, 1, 1, 0, act=act, bias_scale=2.0)
     run_conv(2, 32, 32, 32, 64, 3, 1, 1, act=act, residual=(act == "hardswish"), bias_scale=2.0)
     run_conv(1, 20, 28, 48, 96, 3, 2, 1, act=act, dtype=torch.bfloat16)
+
+
+# ---- chained pointwise tails (yb_conv_chain: conv -> 1x1 conv inside one launch) ---------------------------
+def run_chain(N, H, W, Cin, C1, k, c_own, C2, extra=False, residual=False, dtype=torch.float16, seed=0, store_first=True,
+              act2=True):
+    """First convolution (k x k, stride 1, C1 outputs, optional shortcut) with a chained 1x1 tail over
+    [first_out[:c_own] | extra(c_own channels)] -> C2 channels.  Checks: the library accepts the fusion; the first
+    output (when stored) against fp32 on the rounded inputs; the tail against fp32 applied to the STORED first output
+    (= exactly the fp16 tile the tail consumed on chip); and, with store_first=False, bit equality of the tail with
+    the store_first=True run (the flag only gates the TMA store)."""
+    import ctypes
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(seed)
+    p = k // 2
+    x = torch.randn(N, H, W, Cin, generator=g).to(dtype).to(DEV)
+    w1 = (torch.randn(C1, Cin, k, k, generator=g) * (2.0 / (Cin * k * k)) ** 0.5).to(dtype)
+    b1 = torch.randn(C1, generator=g) * 0.5
+    K2 = c_own * (2 if extra else 1)
+    w2 = (torch.randn(C2, K2, 1, 1, generator=g) * (2.0 / K2) ** 0.5).to(dtype)
+    b2 = torch.randn(C2, generator=g) * 0.5
+    wp1, ci_pad, co_pad = pack_weight(w1.double(), dtype, DEV)
+    bp1 = pack_bias(b1.double(), co_pad, DEV)
+    wp2, k2_pad, co2_pad = pack_weight(w2.double(), dtype, DEV)
+    bp2 = pack_bias(b2.double(), co2_pad, DEV)
+    # the first output lives in the left window of a concat buffer whose right window is the extra operand (C3 layout)
+    cat_cs = C1 + (c_own if extra else 0)
+    cat = torch.randn(N, H, W, cat_cs, generator=g).to(dtype).to(DEV)
+    cat0 = cat.clone()
+    res = torch.randn(N, H, W, C1, generator=g).to(dtype).to(DEV) if residual else None
+    out2 = torch.full((N, H, W, C2 + 16), 7.0, dtype=dtype, device=DEV)      # tail output into a channel window too
+
+    def launch(store):
+        cat.copy_(cat0)
+        out2.fill_(7.0)
+        d = _C.OpDesc()
+        d.kind, d.dtype = _C.YB_OP_CONV, _C.dtype_code(dtype)
+        d.N, d.H, d.W, d.Cin, d.in_cstride, d.in_ = N, H, W, Cin, Cin, x.data_ptr()
+        d.Ho, d.Wo, d.Cout, d.out_cstride, d.out = H, W, C1, cat_cs, cat.data_ptr()
+        d.ksize, d.stride, d.pad, d.act = k, 1, p, _C.YB_ACT_SILU
+        d.weight, d.Cin_pad, d.Cout_pad, d.bias = wp1.data_ptr(), ci_pad, co_pad, bp1.data_ptr()
+        if residual:
+            d.residual, d.res_cstride = res.data_ptr(), C1
+        c = _C.ConvChain()
+        c.weight, c.bias, c.Cout, c.Cout_pad, c.K_pad = wp2.data_ptr(), bp2.data_ptr(), C2, co2_pad, k2_pad
+        c.act = _C.YB_ACT_SILU if act2 else _C.YB_ACT_NONE
+        c.out, c.out_cstride, c.own_C = out2.data_ptr(), C2 + 16, c_own
+        if extra:
+            c.extra, c.extra_C, c.extra_cstride = cat.data_ptr() + C1 * 2, c_own, cat_cs
+        c.store_first = 1 if store else 0
+        d.chain = ctypes.addressof(c)
+        assert _C.conv_chain_supported(d), _C.lib().yb_last_error().decode()
+        plan = _C.Plan([d], DEV)
+        plan.run()
+        torch.cuda.synchronize()
+        return out2[..., :C2].clone()
+
+    tol = 2.0 ** -9 if dtype == torch.float16 else 2.0 ** -6
+    got2 = launch(True)
+    ref1 = F.silu(F.conv2d(x.float().permute(0, 3, 1, 2), w1.float().to(DEV), b1.to(DEV), 1, p))
+    if residual:
+        ref1 = ref1 + res.float().permute(0, 3, 1, 2)
+    got1 = cat[..., :C1].float().permute(0, 3, 1, 2)
+    e1 = (got1 - ref1).abs()
+    bad1 = int((e1 > tol * (1 + ref1.abs())).sum())
+    if extra:
+        assert torch.equal(cat[..., C1:], cat0[..., C1:])                    # the extra window is only read
+    a2 = torch.cat([cat[..., :c_own], cat[..., C1:C1 + c_own]], -1) if extra else cat[..., :c_own]
+    ref2 = F.conv2d(a2.float().permute(0, 3, 1, 2), w2.float().to(DEV), b2.to(DEV))
+    if act2:
+        ref2 = F.silu(ref2)
+    e2 = (got2.float().permute(0, 3, 1, 2) - ref2).abs()
+    bad2 = int((e2 > tol * (1 + ref2.abs())).sum())
+    print(f"chain N{N} {H}x{W} {Cin}->{C1} k{k} -> [{c_own}{'+' + str(c_own) if extra else ''}]->{C2} {dtype}: "
+          f"first max_err {e1.max().item():.3e} viol {bad1}; tail max_err {e2.max().item():.3e} viol {bad2}")
+    if bad2:
+        idx = (e2 > tol * (1 + ref2.abs())).nonzero()[:8]
+        print("tail violations (n,c,y,x):", idx.tolist(), "got/ref/err:",
+              [(round(float(got2.float().permute(0, 3, 1, 2)[tuple(i)]), 5), round(float(ref2[tuple(i)]), 5), round(float(e2[tuple(i)]), 5))
+               for i in idx])
+    if bad1:
+        idx = (e1 > tol * (1 + ref1.abs())).nonzero()[:8]
+        print("first-output violations (n,c,y,x):", idx.tolist(), "got/ref:", [(float(got1[tuple(i)]), float(ref1[tuple(i)])) for i in idx])
+    assert torch.all(out2[..., C2:] == 7.0)
+    assert bad1 == 0 and bad2 == 0
+    if not store_first:
+        got2b = launch(False)
+        assert torch.equal(got2b, got2)
+        assert torch.equal(cat, cat0)            # nothing of the first output was written
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_chain_1x1_into_bottleneck_cv1(dtype):
+    """C3: cv1||cv2 (one 1x1 GEMM, 2c outputs) -> m.0.cv1 over its first c channels (common.py:168-172)."""
+    run_chain(2, 40, 44, 64, 64, 1, 32, 32, dtype=dtype, seed=1)        # c = 32: half a 64-column box feeds the tail
+    run_chain(3, 24, 40, 128, 128, 1, 64, 64, dtype=dtype, seed=2)      # c = 64: box 0 of two
+    run_chain(1, 17, 19, 256, 128, 1, 64, 64, dtype=dtype, seed=3)      # ragged M (323 pixels), 256 input channels
+    run_chain(2, 16, 16, 64, 64, 1, 32, 32, dtype=dtype, seed=4, act2=False)
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+def test_chain_3x3_into_next_cv1_and_cv3(dtype):
+    """Bottleneck 3x3 (+ shortcut) -> the next bottleneck's cv1 (common.py:111-116), and the last bottleneck -> cv3
+    over cat(m_out, cv2(x)) with the cv2 half fetched per tile (common.py:173); first output stored / not stored."""
+    run_chain(2, 40, 44, 64, 64, 3, 64, 64, residual=True, dtype=dtype, seed=5)                       # m.i.cv2 -> m.(i+1).cv1
+    run_chain(2, 40, 44, 64, 64, 3, 64, 128, extra=True, residual=True, dtype=dtype, seed=6, store_first=False)
+    run_chain(2, 48, 40, 32, 32, 3, 32, 64, extra=True, residual=True, dtype=dtype, seed=7, store_first=False)
+    run_chain(1, 20, 20, 64, 64, 3, 64, 128, extra=True, residual=False, dtype=dtype, seed=8, store_first=False)   # wrap tiles
+
+
+def test_chain_many_tiles_per_cta():
+    """Bench-like extents: tens of tiles per persistent CTA (mbarrier phases of the tail hand-off wrap many times)."""
+    run_chain(8, 160, 160, 64, 64, 1, 32, 32, seed=9)
+    run_chain(8, 160, 160, 32, 32, 3, 32, 64, extra=True, residual=True, seed=10, store_first=False)
+    run_chain(16, 80, 80, 64, 64, 3, 64, 128, extra=True, residual=True, seed=11, store_first=False)

@@ -152,7 +152,7 @@ def test_pipelined_host_predict_equals_device_forward():
     assert m._predict_pipelined(pinned) is not None          # the chunked path is the one predict() takes here
     Hb, Wb = m.transform.geometry(ims)[1]
     plan = m.model.get_plan(20, Hb, Wb, chunked=True)
-    assert plan.front_chunks == 4 and plan.front_ops == 13
+    assert plan.front_chunks == 4 and plan._front_op_count == 13 and plan.front_ops <= 13   # 13 ops, fewer launches when tails are chained
     for _ in range(2):                                        # twice: staging / arena reuse across calls
         got = m.predict(pinned)
         assert len(got) == len(ref) == 20

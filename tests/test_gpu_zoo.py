@@ -85,7 +85,9 @@ def test_yolov5m_bf16_heads():
 def test_yolov5m_detections():
     m, sd = _build(yolov5m, "m", _STABLE["m"], size=(160, 160), score_thresh=0.2)
     ims = [util.synth_image_u8(120, 160, 1), util.synth_image_u8(160, 96, 2)]
-    _check_dets(m, sd, ims, 0.93, score_thresh=0.2, size=(160, 160))      # measured 0.95 / 0.99
+    # measured 0.95 / 0.99 with the packed-half2 epilogue on shortcut layers, 0.917 / 0.99 with the (more accurate) fp32
+    # epilogue they run now: on this random-weight fixture the match count moves with ANY rounding change, in either direction
+    _check_dets(m, sd, ims, 0.90, score_thresh=0.2, size=(160, 160))
 
 
 def test_yolov5l_detections_mixed_sizes():

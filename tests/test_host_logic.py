@@ -36,13 +36,13 @@ def test_ctypes_structs_match_header_sizes(tmp_path):
     src = tmp_path / "sz.c"
     src.write_text(
         '#include <stdio.h>\n#include "yolort_b200.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu\\n", sizeof(yb_letterbox_geom), sizeof(yb_op_desc), '
-        'sizeof(yb_head_level), sizeof(yb_nms_params));return 0;}\n')
+        'int main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(yb_letterbox_geom), sizeof(yb_op_desc), '
+        'sizeof(yb_head_level), sizeof(yb_nms_params), sizeof(yb_conv_chain));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
     assert sizes == [ctypes.sizeof(_C.LetterboxGeom), ctypes.sizeof(_C.OpDesc), ctypes.sizeof(_C.HeadLevel),
-                     ctypes.sizeof(_C.NmsParams)]
+                     ctypes.sizeof(_C.NmsParams), ctypes.sizeof(_C.ConvChain)]
 
 
 def test_letterbox_geometry_matches_reference(golden_dir):

@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = (
     "yb_letterbox",
     "yb_letterbox_strided",
     "yb_scale_coords_params",
+    "yb_conv_chain_supported",
     "yb_plan_create",
     "yb_plan_run",
     "yb_plan_run_range",
@@ -73,6 +74,20 @@ class OpDesc(ctypes.Structure):
         ("residual", ctypes.c_void_p),
         ("res_cstride", ctypes.c_int32), ("reserved", ctypes.c_int32),
         ("decode", ctypes.c_void_p),
+        ("chain", ctypes.c_void_p),
+    ]
+
+
+class ConvChain(ctypes.Structure):
+    """yb_conv_chain: the pointwise tail fused onto a convolution (include/yolort_b200.h)."""
+    _fields_ = [
+        ("weight", ctypes.c_void_p), ("bias", ctypes.c_void_p),
+        ("Cout", ctypes.c_int32), ("Cout_pad", ctypes.c_int32), ("K_pad", ctypes.c_int32),
+        ("act", ctypes.c_int32),
+        ("out", ctypes.c_void_p), ("out_cstride", ctypes.c_int32),
+        ("own_C", ctypes.c_int32),
+        ("extra", ctypes.c_void_p), ("extra_C", ctypes.c_int32), ("extra_cstride", ctypes.c_int32),
+        ("store_first", ctypes.c_int32),
     ]
 
 
@@ -152,6 +167,7 @@ def lib() -> ctypes.CDLL:
     L.yb_scale_coords_params.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                          ctypes.POINTER(ctypes.c_float)]
     L.yb_plan_create.argtypes = [ctypes.POINTER(OpDesc), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    L.yb_conv_chain_supported.argtypes = [ctypes.POINTER(OpDesc)]
     L.yb_plan_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     L.yb_plan_run_range.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     L.yb_plan_num_launches.argtypes = [ctypes.c_void_p]
@@ -315,6 +331,11 @@ def letterbox(images: List[torch.Tensor], geoms, Hb: int, Wb: int, fill: float, 
 # ---------------------------------------------------------------------------------------------------
 # execution plan
 # ---------------------------------------------------------------------------------------------------
+def conv_chain_supported(op: "OpDesc") -> bool:
+    """Whether the native library can run `op` (with op.chain set) as one fused launch (pure host logic)."""
+    return bool(lib().yb_conv_chain_supported(ctypes.byref(op)))
+
+
 class Plan:
     """Owns a native yb_plan handle (list of prepared launches)."""
 

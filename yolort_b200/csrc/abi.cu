@@ -35,6 +35,12 @@ struct yb_plan {
 extern "C" const char* yb_last_error(void) { return g_err; }
 extern "C" int yb_abi_version(void) { return 1; }
 
+extern "C" int yb_conv_chain_supported(const yb_op_desc* op) {
+  if (op == nullptr || op->kind != YB_OP_CONV || op->chain == nullptr) return 0;
+  const int rc = patch_conv_eligible(*op) ? patch_conv_configure_check(*op) : conv_configure_check(*op);
+  return rc == YB_OK ? 1 : 0;
+}
+
 extern "C" int yb_plan_create(const yb_op_desc* ops, int n_ops, yb_plan** plan_out) {
   YB_REQUIRE(ops && n_ops > 0 && plan_out, "plan_create: null/empty arguments");
   yb_plan* plan = new yb_plan();

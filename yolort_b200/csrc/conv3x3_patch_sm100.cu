@@ -30,6 +30,7 @@
 
 #include "common.cuh"
 #include "conv_epilogue.cuh"
+#include "conv_chain.cuh"
 #include "conv_sm100.h"
 
 namespace yb {
@@ -70,12 +71,16 @@ struct PatchParams {
   int s2;                 // 1: stride-2 convolution over two column-parity planes (H, W are the OUTPUT extent)
   int band;               // 1: banded super-pixel weights (stem), see the kBand MMA loop
   int store_cols, store_bufs, bias_len;
+  int stage_buf_bytes;    // bytes between the staging buffers of an epilogue group (16 KB; 8 KB for the N-split variant)
   int kk_last;            // K=16 steps of the last channel chunk (TMA zero-fills past Cin, the MMA skips)
   int dbg;                // ablation knobs, -DYB_ABLATION builds only (common.cuh)
   TileGeom tg;
   uint32_t a_bytes, a_stride, b_sub_bytes, b_res_bytes, tmem_cols, idesc;   // a_stride: bytes reserved per patch
+  int acc_stride;         // TMEM columns per accumulator slot (= block_n)
+  int acc2_base;          // chain: first TMEM column of the tail's two accumulators (n2 columns each)
   const float* bias;
   EpilogueParams ep;
+  ChainParams ch;         // chained pointwise tail (kStore2 != 0 kernels; single-tile tasks with resident weights only)
 };
 
 __device__ __forceinline__ void tma_load_tiled_4d(const void* desc, uint64_t* bar, void* smem_dst, int c, int w,
@@ -197,22 +202,34 @@ __device__ __forceinline__ void issue_chunk_streaming_kk(int kc, bool first_chun
     issue_chunk_streaming<1, kMode>(first_chunk, no_mma, tmem_d0, block_n, a_lo0, a_lo1, tap_off16, a_hi, b_ring_lo0, b_step16, b_hi, idesc, b_full, b_empty, b_stages, kb);
 }
 
-template <bool kBf16, int kStoreCols, bool kRareAct, bool kBand = false>
+// kRes: the layer adds a shortcut (fp32 epilogue tail, conv_epilogue.cuh).  kStore2 != 0: a pointwise tail is chained onto
+// every tile (conv_chain.cuh): tmap_w2 = its weights, tmap_x = its optional second operand block (C3: the cv2 half of the
+// concat, fetched per tile with the output tile's box), tmap_out2 = its output.
+template <bool kBf16, int kStoreCols, bool kRareAct, bool kBand = false, bool kRes = true, int kStore2 = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const __grid_constant__ CUtensorMap tmap_out, const PatchParams p) {
+                     const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_w2,
+                     const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_out2,
+                     const PatchParams p) {
+  constexpr bool kChain = kStore2 != 0;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kMaxA], a_empty[kMaxA];
   __shared__ __align__(8) uint64_t b_full[kMaxB], b_empty[kMaxB];
   __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_bias[kEpiGroups][kMaxBlockN];
+  __shared__ __align__(8) uint64_t a2_full[kEpiGroups];     // chain: the tile's output box(es) are in shared memory
+  __shared__ __align__(8) uint64_t x_full[kEpiGroups];      // chain: the extra operand block has landed
+  __shared__ __align__(8) uint64_t acc2_full[kEpiGroups];   // chain: the tail's accumulator is complete
+  __shared__ __align__(8) uint64_t w2_full;
+  __shared__ __align__(16) float s_bias2[kChain ? kEpiGroups : 1][kChain ? kMaxBlockN : 4];
 
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* a_buf = base;                                                      // [a_slots][a_stride]
   uint8_t* b_buf = a_buf + static_cast<size_t>(p.a_slots) * p.a_stride;        // resident [9*chunks] or ring [b_stages]
   const size_t b_region = p.b_resident ? p.b_res_bytes : static_cast<size_t>(p.b_stages) * p.b_sub_bytes;
   uint8_t* staging = b_buf + b_region;                                        // [kEpiGroups][store_bufs][16 KB]
+  uint8_t* w2_res = staging + static_cast<size_t>(kEpiGroups) * p.store_bufs * kStageBufBytes;   // chain: tail weights (16 KB staging buffers there)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int taps_total = 9 * p.chunks;
@@ -232,7 +249,11 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     for (int g = 0; g < 2; ++g) {
       mbar_init(&acc_full[g], 1);
       mbar_init(&acc_empty[g], 4 * p.pair);   // pair tasks are drained by both epilogue groups (8 warps)
+      mbar_init(&a2_full[g], 1);
+      mbar_init(&x_full[g], 1);
+      mbar_init(&acc2_full[g], 1);
     }
+    mbar_init(&w2_full, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -299,11 +320,24 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             tma_load_2d(&tmap_b, &b_full[0], b_buf + static_cast<size_t>(i) * p.b_sub_bytes, i * p.block_k, 0);
         }
       } else if (p.b_resident) {
+        // With several N tiles the grid is a multiple of their count (host), so task % n_tiles -- the N tile -- is the
+        // same for every task of this CTA: its slice of the weights stays resident.
+        const int n0_res = (blockIdx.x % p.n_tiles) * p.block_n;
+        if constexpr (kChain) {
+          if (lane == 0) {   // tail weights: [n2][kc] chunks, resident for the CTA's lifetime
+            tma_prefetch_desc(&tmap_w2);
+            tma_prefetch_desc(&tmap_out2);
+            if (p.ch.extra_on) tma_prefetch_desc(&tmap_x);
+            mbar_expect_tx(&w2_full, p.ch.w2_chunks * p.ch.n2 * p.ch.w2_row_bytes);
+            for (int j = 0; j < p.ch.w2_chunks; ++j)
+              tma_load_2d(&tmap_w2, &w2_full, w2_res + j * p.ch.w2_sub_bytes, j * (p.ch.w2_row_bytes >> 1), 0);
+          }
+        }
         if (lane == 0) {
           mbar_expect_tx(&b_full[0], taps_total * b_bytes);
           for (int i = 0; i < taps_total; ++i)   // i = chunk*9 + tap ; weight column block = tap*chunks + chunk
             tma_load_2d(&tmap_b, &b_full[0], b_buf + static_cast<size_t>(i) * p.b_sub_bytes,
-                        ((i % 9) * p.chunks + i / 9) * p.block_k, 0);
+                        ((i % 9) * p.chunks + i / 9) * p.block_k, n0_res);
         }
       } else {
         int kb = 0;
@@ -348,6 +382,34 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       const uint32_t b_step16 = p.b_sub_bytes >> 4;
       const int mode = p.s2 ? 2 : (p.pair == 2 ? 1 : 0);
       int ka = 0, kb = 0, lt = 0;
+      // chain (single-tile tasks): the tail GEMM of task t is issued after the MMAs of task t + 1; its operands are the
+      // staging buffers of the epilogue group that drained task t (own box(es) first, then the extra block); it
+      // accumulates into columns of its own, one accumulator per epilogue group (see conv_sm100.cu: aliasing the
+      // drained first accumulator serialises the two groups through this in-order thread).
+      int pend = -1;
+      uint32_t ph2 = 0;
+      const uint32_t a2_hi = static_cast<uint32_t>(make_kmajor_desc(0, p.ch.own_row_bytes) >> 32);
+      const uint32_t x_hi = static_cast<uint32_t>(make_kmajor_desc(0, p.ch.extra_row_bytes) >> 32);
+      const uint32_t w2_hi = static_cast<uint32_t>(make_kmajor_desc(0, p.ch.w2_row_bytes) >> 32);
+      const uint32_t w2_lo0 = (smem_u32(w2_res) & 0x3FFFFu) >> 4;
+      auto issue_tail = [&](int gsel) {
+        mbar_wait(&a2_full[gsel], (ph2 >> gsel) & 1u);
+        if (p.ch.extra_on) mbar_wait(&x_full[gsel], (ph2 >> gsel) & 1u);
+        ph2 ^= 1u << gsel;
+        tc_fence_after();
+        const uint32_t d2 = tmem_base + p.acc2_base + gsel * p.ch.n2;
+        const uint32_t stag_lo = (smem_u32(staging + static_cast<size_t>(gsel) * p.store_bufs * kStageBufBytes) & 0x3FFFFu) >> 4;
+        if (YB_ELECT()) {
+          for (int j = 0; j < p.ch.w2_chunks; ++j)
+            umma_ksteps_rt(p.ch.ksteps, d2, stag_lo + j * (kStageBufBytes >> 4), j < p.ch.own_chunks ? a2_hi : x_hi,
+                           w2_lo0 + j * (p.ch.w2_sub_bytes >> 4), w2_hi, p.ch.idesc2, j == 0);
+          umma_commit(&acc2_full[gsel]);
+        }
+      };
+      if constexpr (kChain) {
+        mbar_wait(&w2_full, 0);
+        tc_fence_after();
+      }
       for (int task = blockIdx.x; task < p.num_tasks; task += gridDim.x, ++lt) {
         const int as = lt & 1;
         const uint32_t aph = (lt >> 1) & 1;
@@ -356,7 +418,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         mbar_wait(&acc_empty[as], aph ^ 1);
         tc_fence_after();
         // accumulator columns: single tasks alternate between two stages; pair tasks own two accumulators per stage
-        const uint32_t tmem_d0 = tmem_base + (p.pair == 2 ? 2 * as : as) * p.block_n;
+        const uint32_t tmem_d0 = tmem_base + (p.pair == 2 ? 2 * as : as) * p.acc_stride;
         for (int c = 0; c < p.chunks; ++c) {
           const int sa0 = ka % p.a_slots, sa1 = (ka + 1) % p.a_slots;
           mbar_wait(&a_full[sa0], (ka / p.a_slots) & 1);
@@ -420,6 +482,13 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           ka += cnt;
         }
         if (YB_ELECT()) umma_commit(&acc_full[as]);
+        if constexpr (kChain) {
+          if (pend >= 0) issue_tail(pend);
+          pend = as;
+        }
+      }
+      if constexpr (kChain) {
+        if (pend >= 0) issue_tail(pend);
       }
     }
   } else if (warp >= kFirstEpiWarp) {
@@ -432,13 +501,29 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const uint32_t bar_id = 1 + g;
     const int store_cols = kStoreCols != 0 ? kStoreCols : p.store_cols;
     const int row_bytes = store_cols * 2;
-    uint8_t* my_staging = staging + static_cast<size_t>(g) * p.store_bufs * kStageBufBytes;
+    uint8_t* my_staging = staging + static_cast<size_t>(g) * p.store_bufs * p.stage_buf_bytes;
     float* bias_s = s_bias[g];
     // position of this thread's accumulator row inside a tile
     const int grp = row_in_tile >> 3;
     const int yy = grp / p.tg.gpr;
     const int xx = (grp - yy * p.tg.gpr) * 8 + (row_in_tile & 7);
     int lt = 0, store_idx = 0;
+    uint32_t ph2 = 0;
+    if constexpr (kChain) {   // the tail has a single N tile: one bias vector for every task (visible after the first barrier)
+      for (int i = gtid; i < p.ch.n2; i += 128) s_bias2[g][i] = (i < p.ch.bias2_len) ? __ldg(p.ch.bias2 + i) : 0.f;
+    }
+    // Every task of this CTA has the same N tile when the grid is a multiple of the N-tile count (always with one N
+    // tile): the bias is then loaded ONCE instead of per task (a global-load latency plus a barrier per tile).
+#ifdef YB_NO_BIAS_HOIST       // A/B build (scripts/ab_step.sh)
+    const bool fixed_n = false;
+#else
+    const bool fixed_n = (gridDim.x % p.n_tiles) == 0;
+#endif
+    if (fixed_n) {
+      const int n0f = (blockIdx.x % p.n_tiles) * p.block_n;
+      for (int i = gtid; i < p.block_n; i += 128) bias_s[i] = (n0f + i < p.bias_len) ? __ldg(p.bias + n0f + i) : 0.f;
+      named_bar_sync(bar_id, 128);
+    }
     for (int task = blockIdx.x; task < p.num_tasks; task += gridDim.x, ++lt) {
       int as, slot;          // accumulator stage (barrier pair) and TMEM slot of the accumulator this group drains
       bool work = true;
@@ -469,22 +554,35 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         if (lane == 0) mbar_arrive(&acc_empty[as]);
         continue;
       }
-      for (int i = gtid; i < p.block_n; i += 128) bias_s[i] = (n0 + i < p.bias_len) ? __ldg(p.bias + n0 + i) : 0.f;
-      named_bar_sync(bar_id, 128);
+      if (!fixed_n) {
+        for (int i = gtid; i < p.block_n; i += 128) bias_s[i] = (n0 + i < p.bias_len) ? __ldg(p.bias + n0 + i) : 0.f;
+      }
+      if constexpr (kChain) {
+        // chain tasks index the staging buffers by box (own box(es) first, then the extra operand block; they stay put
+        // until the tail GEMM has read them), so the previous task's stores must have drained the buffers first
+        if (issuer) {
+          tma_store_wait_read<0>();
+          if (p.ch.extra_on) {   // the cv2 half of the concat for this tile's pixels: same box as the output tile
+            mbar_expect_tx(&x_full[g], p.ch.extra_bytes);
+            tma_load_tiled_4d(&tmap_x, &x_full[g], my_staging + p.ch.own_chunks * kStageBufBytes, 0, x0, y0, n_img);
+          }
+        }
+      }
+      if (kChain || !fixed_n) named_bar_sync(bar_id, 128);
       mbar_wait(&acc_full[as], aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * p.block_n;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + slot * p.acc_stride;
       for (int c0 = 0; c0 < p.block_n; c0 += store_cols, ++store_idx) {
         // Two staging buffers, one barrier per box: before the barrier below the issuer waits until the PREVIOUS
         // store has finished reading its buffer, which is the one the next box will overwrite.
-        uint8_t* buf = my_staging + (p.store_bufs == 2 ? (store_idx & 1) * kStageBufBytes : 0);
+        uint8_t* buf = my_staging + (kChain ? (c0 / store_cols) * kStageBufBytes : (p.store_bufs == 2 ? (store_idx & 1) * p.stage_buf_bytes : 0));
         uint8_t* my_row = buf + row_in_tile * row_bytes;
-        if (p.store_bufs == 1) {   // one staging buffer (stride-2 variant: the planes need the room): drain it first
+        if (!kChain && p.store_bufs == 1) {   // one staging buffer (stride-2 variant: the planes need the room): drain it first
           if (issuer) tma_store_wait_read<0>();
           named_bar_sync(bar_id, 128);
         }
         if (!YB_DBG(p, 1)) {
-          epilogue_box_select<kBf16, kStoreCols, kRareAct>(p.ep, store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
+          epilogue_box_select<kBf16, kStoreCols, kRareAct, kRes>(p.ep, store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
         }
         if (c0 + store_cols >= p.block_n) {
           tc_fence_before();
@@ -492,11 +590,39 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
         fence_proxy_async_smem();
-        if (issuer && p.store_bufs == 2) tma_store_wait_read<0>();
+        if constexpr (!kChain) {
+          if (issuer && p.store_bufs == 2) tma_store_wait_read<0>();
+        }
         named_bar_sync(bar_id, 128);
         if (issuer) {
-          if (n0 + c0 < p.ep.Cout && !YB_DBG(p, 5)) tma_store_4d(&tmap_out, buf, n0 + c0, x0, y0, n_img);
+          if ((!kChain || p.ch.store_first) && n0 + c0 < p.ep.Cout && !YB_DBG(p, 5)) tma_store_4d(&tmap_out, buf, n0 + c0, x0, y0, n_img);
           tma_store_commit();
+        }
+      }
+      if constexpr (kChain) {
+        // the tile's box(es) are in shared memory, visible to the async proxy, and every TMEM read of the group has
+        // retired: the MMA warp may run the tail GEMM into the columns this group has just drained
+        if (issuer) mbar_arrive(&a2_full[g]);
+        mbar_wait(&acc2_full[g], ph2);
+        ph2 ^= 1u;
+        tc_fence_after();
+        const uint32_t taddr2 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + p.acc2_base + g * p.ch.n2;
+        constexpr int kRow2 = kStore2 * 2;
+        // the tail's boxes reuse the staging buffers: the operand blocks are dead (the tail GEMM has completed), but the
+        // stores of the first output may still be reading them
+        if (issuer) tma_store_wait_read<0>();
+        named_bar_sync(bar_id, 128);
+        for (int c0 = 0; c0 < p.ch.n2; c0 += kStore2) {
+          uint8_t* buf = my_staging + ((c0 / kStore2) & 1) * kStageBufBytes;
+          epilogue_box<kBf16, kStore2, false, kBf16>(p.ch.ep2, taddr2 + c0, s_bias2[g] + c0, row, row_ok, c0, buf + row_in_tile * kRow2, row_in_tile);
+          if (c0 + kStore2 >= p.ch.n2) tc_fence_before();   // ordered before this group's next a2_full arrival
+          fence_proxy_async_smem();
+          if (issuer) tma_store_wait_read<0>();   // box k + 1 overwrites the buffer of box k - 1
+          named_bar_sync(bar_id, 128);
+          if (issuer) {
+            if (c0 < p.ch.ep2.Cout) tma_store_4d(&tmap_out2, buf, c0, x0, y0, n_img);
+            tma_store_commit();
+          }
         }
       }
     }
@@ -513,16 +639,32 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
 }  // namespace
 
-using PatchKernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const PatchParams);
+using PatchKernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                               const CUtensorMap, const PatchParams);
 
+// fp16 layers without a shortcut take the packed half2 epilogue tail (kRes = false); bf16 always runs the fp32 tail.
+// Chained tails (conv_chain.cuh): first output in one 32- or 64-column box, tail stored in 64-column boxes.
 template <bool kBf16>
 PatchKernelFn select_patch_kernel_t(const PatchParams& kp) {
-  if (kp.band) return conv3x3_patch_kernel<kBf16, 64, false, true>;    // banded super-pixel stem
+  constexpr bool kResAlways = kBf16;
+  if (kp.band) return conv3x3_patch_kernel<kBf16, 64, false, true, kResAlways>;    // banded super-pixel stem (no shortcut)
   if (kp.ep.act >= YB_ACT_HARDSWISH) return conv3x3_patch_kernel<kBf16, 0, true>;
+  const bool res = kResAlways || kp.ep.residual != nullptr;
+  if (kp.ch.on) {   // patch_conv_configure admits exactly these shapes
+    if (res) return kp.store_cols == 64 ? conv3x3_patch_kernel<kBf16, 64, false, false, true, 64> : conv3x3_patch_kernel<kBf16, 32, false, false, true, 64>;
+    return kp.store_cols == 64 ? conv3x3_patch_kernel<kBf16, 64, false, false, kResAlways, 64> : conv3x3_patch_kernel<kBf16, 32, false, false, kResAlways, 64>;
+  }
+  if (res) {
+    switch (kp.store_cols) {
+      case 64: return conv3x3_patch_kernel<kBf16, 64, false, false, true>;
+      case 32: return conv3x3_patch_kernel<kBf16, 32, false, false, true>;
+      default: return conv3x3_patch_kernel<kBf16, 16, false, false, true>;
+    }
+  }
   switch (kp.store_cols) {
-    case 64: return conv3x3_patch_kernel<kBf16, 64, false>;
-    case 32: return conv3x3_patch_kernel<kBf16, 32, false>;
-    default: return conv3x3_patch_kernel<kBf16, 16, false>;
+    case 64: return conv3x3_patch_kernel<kBf16, 64, false, false, kResAlways>;
+    case 32: return conv3x3_patch_kernel<kBf16, 32, false, false, kResAlways>;
+    default: return conv3x3_patch_kernel<kBf16, 16, false, false, kResAlways>;
   }
 }
 PatchKernelFn select_patch_kernel(const PatchParams& kp) {
@@ -530,7 +672,7 @@ PatchKernelFn select_patch_kernel(const PatchParams& kp) {
 }
 
 struct PatchConvOp {
-  CUtensorMap tmap_a, tmap_b, tmap_out;
+  CUtensorMap tmap_a, tmap_b, tmap_out, tmap_w2, tmap_x, tmap_out2;
   PatchParams kp;
   PatchKernelFn fn = nullptr;
   dim3 grid;
@@ -579,9 +721,9 @@ bool patch_conv_eligible(const yb_op_desc& d) {
   return eff >= 0.7;
 }
 
-int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConvOp** out) {
-  PatchConvOp* op = new PatchConvOp();
-  PatchParams& kp = op->kp;
+// Pure host logic: tiling, shared-memory layout and launch shape (no driver calls).
+static int patch_conv_configure(const yb_op_desc& d, PatchParams& kp, dim3& grid, size_t& smem_bytes) {
+  kp = PatchParams();
   kp.N = d.N;
   kp.s2 = d.stride == 2 ? 1 : 0;
   kp.H = d.Ho;     // the kernel tiles the OUTPUT map (equal to the input extent at stride 1)
@@ -614,10 +756,56 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
   if (const char* e = getenv("YB_CONV_DBG")) kp.dbg = atoi(e);
 #endif
   const size_t staging = static_cast<size_t>(kEpiGroups) * kp.store_bufs * kStageBufBytes;
-  const size_t avail = kSmemBudget - staging - 1024;
+  // chained tail: its resident weights come out of the same budget (chain_setup validates the rest below, once the
+  // first convolution's tiling is known; the byte count only depends on the descriptor)
+  size_t chain_bytes = 0;
+  if (d.chain != nullptr) {
+    const int kc = d.chain->own_C >= 64 ? 64 : d.chain->own_C;
+    const int chunks2 = kc > 0 ? d.chain->K_pad / kc : 0;
+    chain_bytes = static_cast<size_t>(chunks2) * ((static_cast<size_t>(d.chain->Cout_pad) * kc * 2 + 1023) & ~static_cast<size_t>(1023));
+    YB_REQUIRE(chain_bytes + staging + 1024 + 64 * 1024 < kSmemBudget, "patch conv: chained tail weights (%zu bytes) do not fit", chain_bytes);
+  }
+  const size_t avail = kSmemBudget - staging - 1024 - chain_bytes;
   uint32_t b_sub = (static_cast<uint32_t>(block_n * kp.block_k * 2) + 1023u) & ~1023u;
   size_t b_total = static_cast<size_t>(kp.band ? 6 : 9 * kp.chunks) * b_sub;
   kp.b_resident = (n_tiles == 1 && b_total + 2 * kp.a_stride <= avail) ? 1 : 0;
+  kp.stage_buf_bytes = kStageBufBytes;
+  // N-split with resident weights: when the whole filter bank does not fit in shared memory but half (a quarter) of it
+  // does, every CTA keeps ONE N tile for all its tasks (grid % n_tiles == 0 makes task % n_tiles constant per CTA) and
+  // loads that slice once.  The patch is then fetched by n_tiles CTAs, but nothing is streamed per task any more:
+  // 128 -> 128 at 40 x 40 moved 295 KB of weights + 92 KB of patches per pair of tiles through a 5-slab ring
+  // (tensor pipe 38 % active); with two 64-column halves it is 46 KB of patch per half tile and 144 KB of weights per CTA,
+  // once.  Shared memory: 144 KB weights + two 23 KB patches leave 16 KB of staging -> 32-column store boxes, one
+  // buffer per epilogue group.
+  int forced_store_cols = 0;
+  size_t staging_ns = staging;
+  if (!kp.b_resident && !kp.band && !kp.s2 && d.chain == nullptr && !(d.reserved & 8)) {
+    for (int ns = 2; ns <= 4 && !kp.b_resident; ns *= 2) {
+      if (d.Cout % (16 * ns) || sms % ns) continue;
+      const int bn = d.Cout / ns;
+      if (bn < 64) break;                      // narrower MMAs / more patch re-reads than the weight stream costs
+      const uint32_t bs = (static_cast<uint32_t>(bn * kp.block_k * 2) + 1023u) & ~1023u;
+      const size_t bt = static_cast<size_t>(9 * kp.chunks) * bs;
+      const int opt_cols[3] = {64, 64, 32}, opt_bufs[3] = {2, 1, 1};
+      for (int o = 0; o < 3; ++o) {
+        if (bn % opt_cols[o]) continue;
+        const size_t buf_bytes = static_cast<size_t>(128) * opt_cols[o] * 2;
+        const size_t stg = static_cast<size_t>(kEpiGroups) * opt_bufs[o] * buf_bytes;
+        if (bt + 2 * kp.a_stride + stg + 1024 > kSmemBudget) continue;
+        n_tiles = ns;
+        block_n = bn;
+        b_sub = bs;
+        b_total = bt;
+        kp.b_resident = 1;
+        kp.store_bufs = opt_bufs[o];
+        kp.stage_buf_bytes = static_cast<int>(buf_bytes);
+        forced_store_cols = opt_cols[o];
+        staging_ns = stg;
+        break;
+      }
+    }
+  }
+  const size_t avail_ns = kSmemBudget - staging_ns - 1024 - chain_bytes;
   // Weights that do not fit in shared memory are streamed from L2 for every task; two M tiles per weight pass halve
   // that stream (the bound of the deep layers: 128 -> 128 at 40 x 40 re-reads 295 KB per 128 output pixels).  Pair
   // tasks hold four accumulators (two stages x two tiles), so their N tile is at most 128 columns.
@@ -631,22 +819,38 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
   kp.block_n = block_n;
   kp.n_tiles = n_tiles;
   kp.b_sub_bytes = b_sub;
-  kp.store_cols = (block_n % 64 == 0) ? 64 : ((block_n % 32 == 0) ? 32 : 16);
+  kp.store_cols = forced_store_cols ? forced_store_cols : ((block_n % 64 == 0) ? 64 : ((block_n % 32 == 0) ? 32 : 16));
   kp.num_tasks = ((kp.m_tiles + kp.pair - 1) / kp.pair) * n_tiles;
   if (kp.band && !(d.Cin_pad == 64 && n_tiles == 1 && kp.store_cols == 64 && d.act < YB_ACT_HARDSWISH &&
                    d.residual == nullptr)) {
     set_error("patch conv: banded stem weights need Cin_pad 64, one N tile with 64-column store boxes, SiLU/linear epilogue");
-    delete op;
     return YB_ERR_INVALID;
   }
   if (kp.band && !kp.b_resident) {
     set_error("patch conv: banded stem weights do not fit in shared memory (block_n=%d)", block_n);
-    delete op;
     return YB_ERR_INVALID;
+  }
+  kp.acc_stride = block_n;
+  kp.ch.on = 0;
+  if (d.chain != nullptr) {
+    YB_REQUIRE(kp.b_resident && kp.pair == 1 && !kp.s2 && !kp.band,
+               "patch conv: a chained tail needs resident weights and single-tile stride-1 tasks (block_n=%d resident=%d pair=%d)",
+               block_n, kp.b_resident, kp.pair);
+    YB_REQUIRE(kp.store_cols == block_n && (block_n == 64 || block_n == 32),
+               "patch conv: a chained tail needs the first output in one 32- or 64-column box, got block_n=%d", block_n);
+    const char* why = chain_setup(d, block_n, n_tiles, kp.store_cols, /*allow_extra=*/true, &kp.ch);
+    YB_REQUIRE(why == nullptr, "patch conv: chained tail not supported here: %s", why);
+    YB_REQUIRE(chain_store2_cols(kp.ch.n2) == 64, "patch conv: the tail's Cout_pad must be a multiple of 64, got %d", kp.ch.n2);
+    YB_REQUIRE(static_cast<size_t>(kp.ch.w2_chunks) * kp.ch.w2_sub_bytes == chain_bytes, "patch conv: tail weight layout mismatch");
+    kp.acc2_base = 2 * kp.acc_stride;
+    YB_REQUIRE(kp.acc2_base + 2 * kp.ch.n2 <= 512, "patch conv: accumulators of the convolution and its tail exceed TMEM");
+    // the extra block arrives as the output tile's box: tile_w x tile_h pixel-rows (120 for the wrap tiling; the rows
+    // beyond are never stored)
+    kp.ch.extra_bytes = static_cast<uint32_t>(tg.tile_w * tg.tile_h) * static_cast<uint32_t>(kp.ch.extra_row_bytes);
   }
   kp.b_res_bytes = kp.b_resident ? static_cast<uint32_t>(b_total) : 0u;
   if (kp.b_resident) {
-    int a_st = static_cast<int>((avail - b_total) / kp.a_stride);
+    int a_st = static_cast<int>((avail_ns - b_total) / kp.a_stride);
     kp.a_slots = a_st > kMaxA ? kMaxA : a_st;
     kp.b_stages = 1;
   } else {
@@ -662,15 +866,14 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
     kp.b_stages = b_st > kMaxB ? kMaxB : b_st;
     if (kp.b_stages < 2) {
       set_error("patch conv: not enough shared memory for the weight ring (block_n=%d)", block_n);
-      delete op;
       return YB_ERR_INVALID;
     }
   }
+  YB_REQUIRE(kp.a_slots >= 2, "patch conv: fewer than two patch slots fit in shared memory (block_n=%d)", block_n);
   uint32_t cols = 32;
-  while (static_cast<int>(cols) < 2 * kp.pair * block_n) cols <<= 1;
+  while (static_cast<int>(cols) < 2 * kp.pair * kp.acc_stride + (kp.ch.on ? 2 * kp.ch.n2 : 0)) cols <<= 1;
   if (cols > 512) {
-    set_error("patch conv: %d accumulator columns exceed TMEM (pair=%d block_n=%d)", 2 * kp.pair * block_n, kp.pair, block_n);
-    delete op;
+    set_error("patch conv: %d accumulator columns exceed TMEM (pair=%d block_n=%d)", 2 * kp.pair * kp.acc_stride, kp.pair, block_n);
     return YB_ERR_INVALID;
   }
   kp.tmem_cols = cols;
@@ -682,11 +885,33 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
   kp.bias = d.bias;
   const uint32_t fmt = kp.ep.is_bf16 ? 1u : 0u;
   kp.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(block_n >> 3) << 17) | (8u << 24);
-  op->grid = dim3(kp.num_tasks < sms ? kp.num_tasks : sms, 1, 1);
+  grid = dim3(kp.num_tasks < sms ? kp.num_tasks : sms, 1, 1);
+  YB_REQUIRE(!(kp.b_resident && n_tiles > 1) || grid.x % n_tiles == 0, "patch conv: N-split grid %u not a multiple of %d", grid.x, n_tiles);
   const size_t b_region = kp.b_resident ? kp.b_res_bytes : static_cast<size_t>(kp.b_stages) * kp.b_sub_bytes;
-  size_t smem = static_cast<size_t>(kp.a_slots) * kp.a_stride + b_region + staging + 1024;
+  size_t smem = static_cast<size_t>(kp.a_slots) * kp.a_stride + b_region + staging_ns + chain_bytes + 1024;
+  YB_REQUIRE(smem <= kSmemBudget, "patch conv: %zu bytes of shared memory needed, %zu available", smem, kSmemBudget);
   if (smem < 120 * 1024) smem = 120 * 1024;
-  op->smem_bytes = smem;
+  smem_bytes = smem;
+  return YB_OK;
+}
+
+int patch_conv_configure_check(const yb_op_desc& d) {
+  PatchParams kp;
+  dim3 grid;
+  size_t smem = 0;
+  return patch_conv_configure(d, kp, grid, smem);
+}
+
+int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConvOp** out) {
+  PatchConvOp* op = new PatchConvOp();
+  PatchParams& kp = op->kp;
+  int rc = patch_conv_configure(d, kp, op->grid, op->smem_bytes);
+  if (rc != YB_OK) {
+    delete op;
+    return rc;
+  }
+  const TileGeom& tg = kp.tg;
+  const int block_n = kp.block_n;
 
   const CUtensorMapDataType dt = kp.ep.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const int rb = kp.block_k * 2;
@@ -753,6 +978,44 @@ int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConv
       return YB_ERR_CUDA;
     }
   }
+  op->tmap_w2 = op->tmap_b;      // placeholders when nothing is chained (never dereferenced)
+  op->tmap_x = op->tmap_a;
+  op->tmap_out2 = op->tmap_out;
+  if (kp.ch.on) {
+    const yb_conv_chain& c = *d.chain;
+    const int kc = kp.ch.w2_row_bytes / 2;
+    const CUtensorMapSwizzle swk = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    cuuint64_t wdims[2] = {static_cast<cuuint64_t>(c.K_pad), static_cast<cuuint64_t>(c.Cout_pad)};
+    cuuint64_t wstrides[1] = {static_cast<cuuint64_t>(c.K_pad) * 2};
+    cuuint32_t wbox[2] = {static_cast<cuuint32_t>(kc), static_cast<cuuint32_t>(kp.ch.n2)};
+    cuuint32_t estr2[2] = {1, 1};
+    cr = encode_tiled(&op->tmap_w2, dt, 2, const_cast<void*>(c.weight), wdims, wstrides, wbox, estr2, CU_TENSOR_MAP_INTERLEAVE_NONE, swk,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cuuint32_t estr4[4] = {1, 1, 1, 1};
+    if (cr == CUDA_SUCCESS && kp.ch.extra_on) {   // the tile's pixels of the extra operand: the output tile's box
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(c.extra_C), static_cast<cuuint64_t>(d.Wo), static_cast<cuuint64_t>(d.Ho),
+                            static_cast<cuuint64_t>(d.N)};
+      cuuint64_t strides[3] = {static_cast<cuuint64_t>(c.extra_cstride) * 2, static_cast<cuuint64_t>(c.extra_cstride) * 2 * d.Wo,
+                               static_cast<cuuint64_t>(c.extra_cstride) * 2 * d.Wo * d.Ho};
+      cuuint32_t box[4] = {static_cast<cuuint32_t>(kc), static_cast<cuuint32_t>(tg.tile_w), static_cast<cuuint32_t>(tg.tile_h), 1};
+      cr = encode_tiled(&op->tmap_x, dt, 4, const_cast<void*>(c.extra), dims, strides, box, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE, swk,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (cr == CUDA_SUCCESS) {
+      cuuint64_t dims[4] = {static_cast<cuuint64_t>(c.Cout), static_cast<cuuint64_t>(d.Wo), static_cast<cuuint64_t>(d.Ho),
+                            static_cast<cuuint64_t>(d.N)};
+      cuuint64_t strides[3] = {static_cast<cuuint64_t>(c.out_cstride) * 2, static_cast<cuuint64_t>(c.out_cstride) * 2 * d.Wo,
+                               static_cast<cuuint64_t>(c.out_cstride) * 2 * d.Wo * d.Ho};
+      cuuint32_t box[4] = {64, static_cast<cuuint32_t>(tg.tile_w), static_cast<cuuint32_t>(tg.tile_h), 1};
+      cr = encode_tiled(&op->tmap_out2, dt, 4, c.out, dims, strides, box, estr4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (cr != CUDA_SUCCESS) {
+      set_error("patch conv: cuTensorMapEncodeTiled (chained tail) failed with CUresult %d", static_cast<int>(cr));
+      delete op;
+      return YB_ERR_CUDA;
+    }
+  }
   op->fn = select_patch_kernel(kp);
   cudaError_t e = cudaFuncSetAttribute(op->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget));
   if (e != cudaSuccess) {
@@ -775,7 +1038,7 @@ int patch_conv_launch(const PatchConvOp* op, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, op->fn, op->tmap_a, op->tmap_b, op->tmap_out, op->kp));
+  YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, op->fn, op->tmap_a, op->tmap_b, op->tmap_out, op->tmap_w2, op->tmap_x, op->tmap_out2, op->kp));
   return YB_OK;
 }
 

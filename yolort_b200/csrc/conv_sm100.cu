@@ -29,6 +29,7 @@
 #include "common.cuh"
 #include "conv_sm100.h"
 #include "conv_epilogue.cuh"
+#include "conv_chain.cuh"
 #include "decode_common.cuh"
 
 namespace yb {
@@ -59,8 +60,11 @@ struct ConvKernelParams {
   int kk_last;     // K=16 steps of the LAST channel chunk (Cin need not fill it: TMA zero-fills, the MMA skips)
   int dbg;         // ablation knobs, -DYB_ABLATION builds only (common.cuh)
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, idesc;
+  int acc_stride;  // TMEM columns between the two accumulator stages (= block_n)
+  int acc2_base;   // chain: first TMEM column of the tail's two accumulators (n2 columns each), after the first conv's
   const float* bias;
   EpilogueParams ep;
+  ChainParams ch;  // chained pointwise tail (kStore2 != 0 kernels)
   int decode_on;        // detection head with the fused decode epilogue (no logits are stored)
   int dec_H, dec_W;     // level extent (output pixels)
   yb_head_decode dec;   // copied from the op descriptor
@@ -75,10 +79,14 @@ __device__ __forceinline__ void issue_group(int cnt, bool first_group, uint32_t 
   for (int j = 1; j < cnt; ++j) umma_ksteps<KK>(tmem_d, a_lo0 + j * a_step16, desc_hi, b_lo0 + j * b_step16, desc_hi, idesc, false);
 }
 
-template <bool kBf16, int kStoreCols, bool kRareAct, bool kDecode>
+// kRes: the layer adds a shortcut (fp32 epilogue tail, conv_epilogue.cuh).  kStore2 != 0: a pointwise tail is chained
+// onto every tile (conv_chain.cuh), its output stored in boxes of kStore2 columns.
+template <bool kBf16, int kStoreCols, bool kRareAct, bool kDecode, bool kRes = true, int kStore2 = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_out, const ConvKernelParams p) {
+                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_w2,
+                 const __grid_constant__ CUtensorMap tmap_out2, const ConvKernelParams p) {
+  constexpr bool kChain = kStore2 != 0;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -87,6 +95,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __shared__ __align__(8) uint64_t b_full;
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_bias[kEpiGroups][kMaxBlockN];
+  __shared__ __align__(8) uint64_t a2_full[kEpiGroups];     // chain: the tile's output boxes are in shared memory
+  __shared__ __align__(8) uint64_t acc2_full[kEpiGroups];   // chain: the tail's accumulator is complete
+  __shared__ __align__(8) uint64_t w2_full;
+  __shared__ __align__(16) float s_bias2[kChain ? kEpiGroups : 1][kChain ? kMaxBlockN : 4];
 
   // Swizzled tiles need 1024-byte alignment.
   uint8_t* tiles = reinterpret_cast<uint8_t*>(
@@ -95,6 +107,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t stage_bytes = p.kpg * (p.a_stage_bytes + (p.b_resident ? 0u : p.b_stage_bytes));
   uint8_t* b_res = tiles + static_cast<size_t>(p.stages) * stage_bytes;   // resident weights (optional)
   uint8_t* staging = b_res + p.b_res_bytes;                                // [kEpiGroups][2][kStageBufBytes]
+  uint8_t* w2_res = staging + kEpiGroups * 2 * kStageBufBytes;             // chain: resident tail weights
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -111,7 +124,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int g = 0; g < kEpiGroups; ++g) {
       mbar_init(&acc_full[g], 1);
       mbar_init(&acc_empty[g], 4);  // one arrival per epilogue warp of the group
+      mbar_init(&a2_full[g], 1);
+      mbar_init(&acc2_full[g], 1);
     }
+    mbar_init(&w2_full, 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -135,6 +151,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tma_load_2d(&tmap_b, &b_full, b_res + it * p.b_stage_bytes, it * p.block_k, 0);
   }
 #endif
+  if constexpr (kChain) {
+    if (warp == 0 && lane == 0) {   // tail weights: [n2][kc] chunks, resident for the CTA's lifetime
+      tma_prefetch_desc(&tmap_w2);
+      tma_prefetch_desc(&tmap_out2);
+      mbar_expect_tx(&w2_full, p.ch.w2_chunks * p.ch.n2 * p.ch.w2_row_bytes);
+      for (int j = 0; j < p.ch.w2_chunks; ++j)
+        tma_load_2d(&tmap_w2, &w2_full, w2_res + j * p.ch.w2_sub_bytes, j * (p.ch.w2_row_bytes >> 1), 0);
+    }
+  }
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #ifdef YB_NO_WEIGHT_PREFETCH      // A/B build: weights fetched after the wait (scripts/ab_step.sh)
@@ -214,13 +239,42 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t desc_hi = static_cast<uint32_t>(make_kmajor_desc(0, row_bytes) >> 32);
       const uint32_t a_step16 = p.a_stage_bytes >> 4, b_step16 = p.b_stage_bytes >> 4;
       int kit = 0, lt = 0;
+      // chain: the tail GEMM of tile t is issued after the MMAs of tile t + 1 (its operand is what the epilogue of
+      // tile t writes, which takes about as long as the next tile's MMAs).  The tail has its own accumulator columns
+      // (one per epilogue group): with D2 aliased onto the drained first accumulator, the next-but-one tile's MMAs had
+      // to wait for the tail's epilogue and -- this thread issuing in order -- the two epilogue groups ran in lock step
+      // (measured: 64->64 + 32->32 at 160x160 74 us fused vs 82 us as two launches).  No "tail accumulator empty"
+      // barrier is needed: group g drains tail t - 2 before it writes the boxes of tile t, whose a2_full arrival
+      // this thread waits for.
+      int pend = -1;
+      uint32_t ph2 = 0;
+      const uint32_t a2_hi = static_cast<uint32_t>(make_kmajor_desc(0, p.ch.own_row_bytes) >> 32);
+      const uint32_t w2_hi = static_cast<uint32_t>(make_kmajor_desc(0, p.ch.w2_row_bytes) >> 32);
+      const uint32_t w2_lo0 = (smem_u32(w2_res) & 0x3FFFFu) >> 4;
+      auto issue_tail = [&](int gsel) {
+        mbar_wait(&a2_full[gsel], (ph2 >> gsel) & 1u);
+        ph2 ^= 1u << gsel;
+        tc_fence_after();
+        const uint32_t d2 = tmem_base + p.acc2_base + gsel * p.ch.n2;
+        const uint32_t stag_lo = (smem_u32(staging + static_cast<size_t>(gsel) * 2 * kStageBufBytes) & 0x3FFFFu) >> 4;
+        if (YB_ELECT()) {
+          for (int j = 0; j < p.ch.own_chunks; ++j)
+            umma_ksteps_rt(p.ch.ksteps, d2, stag_lo + j * (kStageBufBytes >> 4), a2_hi, w2_lo0 + j * (p.ch.w2_sub_bytes >> 4), w2_hi,
+                           p.ch.idesc2, j == 0);
+          umma_commit(&acc2_full[gsel]);
+        }
+      };
+      if constexpr (kChain) {
+        mbar_wait(&w2_full, 0);
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
         const int as = lt & 1;
 
         const uint32_t aph = (lt >> 1) & 1;
         mbar_wait(&acc_empty[as], aph ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * p.block_n;
+        const uint32_t tmem_d = tmem_base + as * p.acc_stride;
         int chunk = 0;   // channel chunk of the running k-iteration (it = tap * chunks + chunk)
         for (int it0 = 0; it0 < p.num_k_iters; it0 += p.kpg, ++kit) {
           const int cnt = min(p.kpg, p.num_k_iters - it0);
@@ -256,9 +310,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           chunk = (chunk + cnt) % p.chunks;
         }
         if (YB_ELECT()) umma_commit(&acc_full[as]);  // accumulator of this tile complete
+        if constexpr (kChain) {
+          if (pend >= 0) issue_tail(pend);
+          pend = as;
+        }
+      }
+      if constexpr (kChain) {
+        if (pend >= 0) issue_tail(pend);
       }
     }
-  } else {
+  } else if (warp >= kFirstEpiWarp) {   // (warp 2 has no role: it must not touch the groups' bias rows / named barriers)
     // ===================== epilogue groups =====================
     const int g = (warp - kFirstEpiWarp) >> 2;   // group == accumulator stage it drains
     const int q = warp & 3;          // TMEM lane quarter this warp may access
@@ -271,6 +332,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* my_staging = staging + static_cast<size_t>(g) * 2 * kStageBufBytes;
     float* bias_s = s_bias[g];
     int lt = 0, store_idx = 0;
+    uint32_t ph2 = 0;
+    if constexpr (kChain) {   // the tail has a single N tile: its bias is the same for every tile (visible after the first barrier)
+      for (int i = gtid; i < p.ch.n2; i += 128) s_bias2[g][i] = (i < p.ch.bias2_len) ? __ldg(p.ch.bias2 + i) : 0.f;
+    }
+    // Every tile of this CTA has the same N tile when the grid is a multiple of the N-tile count (always with one N
+    // tile): the bias is then loaded ONCE instead of per tile (a global-load latency plus a barrier per tile).
+#ifdef YB_NO_BIAS_HOIST       // A/B build (scripts/ab_step.sh)
+    const bool fixed_n = false;
+#else
+    const bool fixed_n = (gridDim.x % p.n_tiles) == 0;
+#endif
+    if (fixed_n) {
+      const int n0f = (blockIdx.x % p.n_tiles) * p.block_n;
+      for (int i = gtid; i < p.block_n; i += 128) bias_s[i] = (n0f + i < p.bias_len) ? __ldg(p.bias + n0f + i) : 0.f;
+      named_bar_sync(bar_id, 128);
+    }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
       if ((lt & 1) != g) continue;
       const uint32_t aph = (lt >> 1) & 1;
@@ -287,11 +364,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (lane == 0) mbar_arrive(&acc_empty[g]);
         continue;
       }
-      for (int i = gtid; i < p.block_n; i += 128) bias_s[i] = (n0 + i < p.bias_len) ? __ldg(p.bias + n0 + i) : 0.f;
-      named_bar_sync(bar_id, 128);
+      if (!fixed_n) {
+        for (int i = gtid; i < p.block_n; i += 128) bias_s[i] = (n0 + i < p.bias_len) ? __ldg(p.bias + n0 + i) : 0.f;
+      }
+      if constexpr (kChain) {
+        // chain tiles index the staging buffers by box (box b of the tile stays in buffer b until the tail GEMM has
+        // read it), so the previous tile's stores must have drained both buffers before this tile writes them
+        if (issuer) tma_store_wait_read<0>();
+      }
+      if (kChain || !fixed_n) named_bar_sync(bar_id, 128);
       mbar_wait(&acc_full[g], aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * p.block_n;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * p.acc_stride;
       if constexpr (kDecode) {
         // ---- fused post-processing front end (yolort/models/box_head.py:328-360,418) ----
         // This thread owns one output pixel: all A*(nc+5) logits of its anchors sit in its TMEM lane.  Per anchor:
@@ -398,10 +482,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int c0 = 0; c0 < p.block_n; c0 += store_cols, ++store_idx) {
         // Two staging buffers, one barrier per box: before the barrier below the issuer waits until the PREVIOUS
         // store has finished reading its buffer, which is the one the next box will overwrite.
-        uint8_t* buf = my_staging + (store_idx & 1) * kStageBufBytes;
+        uint8_t* buf = my_staging + (kChain ? ((c0 / store_cols) & 1) : (store_idx & 1)) * kStageBufBytes;
         uint8_t* my_row = buf + row_in_tile * row_bytes;
         if (!YB_DBG(p, 1)) {
-          epilogue_box_select<kBf16, kStoreCols, kRareAct>(p.ep, store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
+          epilogue_box_select<kBf16, kStoreCols, kRareAct, kRes>(p.ep, store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
         }
         if (c0 + store_cols >= p.block_n) {
           // all TMEM reads of this tile are done: hand the accumulator stage back to the MMA warp
@@ -410,11 +494,39 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (lane == 0) mbar_arrive(&acc_empty[g]);
         }
         fence_proxy_async_smem();
-        if (issuer) tma_store_wait_read<0>();
+        if constexpr (!kChain) {
+          if (issuer) tma_store_wait_read<0>();
+        }
         named_bar_sync(bar_id, 128);
         if (issuer) {
-          if (n0 + c0 < p.ep.Cout && !YB_DBG(p, 5)) tma_store_2d(&tmap_out, buf, n0 + c0, m0);
+          if ((!kChain || p.ch.store_first) && n0 + c0 < p.ep.Cout && !YB_DBG(p, 5)) tma_store_2d(&tmap_out, buf, n0 + c0, m0);
           tma_store_commit();
+        }
+      }
+      if constexpr (kChain) {
+        // every box of the tile is in shared memory, visible to the async proxy (fence + barrier above), and every
+        // TMEM read of the group has retired: the MMA warp may run the tail GEMM
+        if (issuer) mbar_arrive(&a2_full[g]);
+        mbar_wait(&acc2_full[g], ph2);
+        ph2 ^= 1u;
+        tc_fence_after();
+        const uint32_t taddr2 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + p.acc2_base + g * p.ch.n2;
+        constexpr int kRow2 = kStore2 * 2;
+        // the tail's boxes reuse the staging buffers: the operand boxes are dead (the tail GEMM has completed), but the
+        // stores of the first output may still be reading them
+        if (issuer) tma_store_wait_read<0>();
+        named_bar_sync(bar_id, 128);
+        for (int c0 = 0; c0 < p.ch.n2; c0 += kStore2) {
+          uint8_t* buf = my_staging + ((c0 / kStore2) & 1) * kStageBufBytes;
+          epilogue_box<kBf16, kStore2, false, kBf16>(p.ch.ep2, taddr2 + c0, s_bias2[g] + c0, row, row_ok, c0, buf + row_in_tile * kRow2, row_in_tile);
+          if (c0 + kStore2 >= p.ch.n2) tc_fence_before();   // ordered before this group's next a2_full arrival
+          fence_proxy_async_smem();
+          if (issuer) tma_store_wait_read<0>();   // box k + 1 overwrites the buffer of box k - 1
+          named_bar_sync(bar_id, 128);
+          if (issuer) {
+            if (c0 < p.ch.ep2.Cout) tma_store_2d(&tmap_out2, buf, c0, m0);
+            tma_store_commit();
+          }
         }
       }
     }
@@ -468,18 +580,35 @@ uint32_t pow2_cols(int n) {
 
 }  // namespace
 
-using ConvKernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKernelParams);
+using ConvKernelFn = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                              const ConvKernelParams);
 
-// One kernel per (dtype, store-box width) for the SiLU / linear epilogue; the r3.1 activations and the fused decode
-// epilogue are separate kernels that pick the store width at run time (see conv_epilogue.cuh).
+// One kernel per (dtype, store-box width, shortcut) for the SiLU / linear epilogue; the r3.1 activations and the fused
+// decode epilogue are separate kernels that pick the store width at run time (see conv_epilogue.cuh).  fp16 layers
+// without a shortcut take the packed half2 epilogue tail (kRes = false); bf16 always runs the fp32 tail, so it has one
+// variant.  Chained tails (conv_chain.cuh): 64-column boxes for the first output, 64 / 32 for the tail.
 template <bool kBf16>
 ConvKernelFn select_conv_kernel_t(const ConvKernelParams& kp) {
   if (kp.decode_on) return conv_umma_kernel<kBf16, 0, false, true>;
   if (kp.ep.act >= YB_ACT_HARDSWISH) return conv_umma_kernel<kBf16, 0, true, false>;
+  constexpr bool kResAlways = kBf16;
+  const bool res = kResAlways || kp.ep.residual != nullptr;
+  if (kp.ch.on) {   // conv_configure admits exactly these shapes
+    const int s2 = chain_store2_cols(kp.ch.n2);
+    if (res) return s2 == 64 ? conv_umma_kernel<kBf16, 64, false, false, true, 64> : conv_umma_kernel<kBf16, 64, false, false, true, 32>;
+    return s2 == 64 ? conv_umma_kernel<kBf16, 64, false, false, kResAlways, 64> : conv_umma_kernel<kBf16, 64, false, false, kResAlways, 32>;
+  }
+  if (res) {
+    switch (kp.store_cols) {
+      case 64: return conv_umma_kernel<kBf16, 64, false, false, true>;
+      case 32: return conv_umma_kernel<kBf16, 32, false, false, true>;
+      default: return conv_umma_kernel<kBf16, 16, false, false, true>;
+    }
+  }
   switch (kp.store_cols) {
-    case 64: return conv_umma_kernel<kBf16, 64, false, false>;
-    case 32: return conv_umma_kernel<kBf16, 32, false, false>;
-    default: return conv_umma_kernel<kBf16, 16, false, false>;
+    case 64: return conv_umma_kernel<kBf16, 64, false, false, kResAlways>;
+    case 32: return conv_umma_kernel<kBf16, 32, false, false, kResAlways>;
+    default: return conv_umma_kernel<kBf16, 16, false, false, kResAlways>;
   }
 }
 ConvKernelFn select_conv_kernel(const ConvKernelParams& kp) {
@@ -488,16 +617,16 @@ ConvKernelFn select_conv_kernel(const ConvKernelParams& kp) {
 
 struct ConvOp {
   PatchConvOp* patch = nullptr;  // non-null: this conv runs on the halo-patch kernel
-  CUtensorMap tmap_a, tmap_b, tmap_out;
+  CUtensorMap tmap_a, tmap_b, tmap_out, tmap_w2, tmap_out2;
   ConvKernelParams kp;
   ConvKernelFn fn = nullptr;
   dim3 grid;
   size_t smem_bytes;
 };
 
-int conv_op_create(const yb_op_desc& d, ConvOp** out) {
-  int rc = load_driver_entry_points();
-  if (rc != YB_OK) return rc;
+// Pure host logic: validates the op and derives tiling, pipeline depth, shared-memory layout and launch shape
+// (no driver calls: yb_conv_chain_supported runs this without a GPU).
+static int conv_configure(const yb_op_desc& d, ConvKernelParams& kp, dim3& grid, size_t& smem_bytes) {
   YB_REQUIRE(d.dtype == YB_F16 || d.dtype == YB_BF16, "conv: dtype must be f16 or bf16");
   YB_REQUIRE(d.ksize >= 1 && d.ksize <= 7 && d.stride >= 1 && d.stride <= 2, "conv: ksize/stride");
   YB_REQUIRE(d.act >= YB_ACT_NONE && d.act <= YB_ACT_LEAKY01, "conv: unknown activation %d", d.act);
@@ -524,17 +653,8 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
   YB_REQUIRE(!(d.reserved & 2) || patch_conv_eligible(d),
              "conv: banded stem weights (reserved bit 1) need the halo-patch kernel, which this %dx%d map does not qualify for",
              d.H, d.W);
-  ConvOp* op = new ConvOp();
-  if (patch_conv_eligible(d)) {
-    rc = patch_conv_create(d, g_encode_tiled, &op->patch);
-    if (rc != YB_OK) {
-      delete op;
-      return rc;
-    }
-    *out = op;
-    return YB_OK;
-  }
-  ConvKernelParams& kp = op->kp;
+  if (patch_conv_eligible(d)) return YB_OK;   // configured by patch_conv_configure
+  kp = ConvKernelParams();
   kp.M = static_cast<int>(M_ll);
   kp.ep.Cout = d.Cout;
   const int m_tiles = (kp.M + kBlockM - 1) / kBlockM;
@@ -543,7 +663,7 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
   // than two tiles per SM so the persistent grid balances better.
   int n_tiles = (d.Cout + kMaxBlockN - 1) / kMaxBlockN;
   int block_n = (((d.Cout + n_tiles - 1) / n_tiles) + 15) / 16 * 16;
-  if (m_tiles * n_tiles < 2 * sms && block_n > 128 && block_n % 32 == 0) {
+  if (m_tiles * n_tiles < 2 * sms && block_n > 128 && block_n % 32 == 0 && d.chain == nullptr) {
     block_n /= 2;
     n_tiles = (d.Cout + block_n - 1) / block_n;
   }
@@ -566,7 +686,6 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
     if (!(dd.n_anchors > 0 && dd.n_anchors <= 4 && width <= kMaxBlockN && width <= d.Cout_pad && d.ksize == 1 &&
           dd.keys && dd.boxes && dd.img_count && dd.img_maxc)) {
       set_error("conv: fused decode needs a 1x1 head with n_anchors*(n_classes+5) <= %d and a candidate arena", kMaxBlockN);
-      delete op;
       return YB_ERR_INVALID;
     }
     // all anchors of a pixel must sit in one accumulator row: one N tile covering the whole head
@@ -591,7 +710,21 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
   if (kp.kk_last > (kp.block_k >> 4)) kp.kk_last = kp.block_k >> 4;
   kp.a_stage_bytes = kBlockM * kp.block_k * 2;
   kp.b_stage_bytes = (static_cast<uint32_t>(kp.block_n * kp.block_k * 2) + 1023u) & ~1023u;
-  const size_t fixed = static_cast<size_t>(kEpiGroups) * 2 * kStageBufBytes + 1024;
+  kp.acc_stride = kp.block_n;
+  kp.ch.on = 0;
+  size_t chain_bytes = 0;
+  if (d.chain != nullptr) {
+    YB_REQUIRE(kp.store_cols == 64, "conv: a chained tail needs 64-column output boxes (Cout %% 64 == 0), got Cout=%d", d.Cout);
+    const char* why = chain_setup(d, kp.block_n, kp.n_tiles, kp.store_cols, /*allow_extra=*/false, &kp.ch);
+    YB_REQUIRE(why == nullptr, "conv: chained tail not supported here: %s", why);
+    const int s2 = chain_store2_cols(kp.ch.n2);
+    YB_REQUIRE(s2 == 64 || s2 == 32, "conv: the tail's Cout_pad must be a multiple of 32, got %d", kp.ch.n2);
+    kp.acc2_base = 2 * kp.acc_stride;
+    YB_REQUIRE(kp.acc2_base + 2 * kp.ch.n2 <= 512, "conv: accumulators of the convolution and its tail exceed TMEM (%d + %d columns)",
+               kp.acc2_base, 2 * kp.ch.n2);
+    chain_bytes = static_cast<size_t>(kp.ch.w2_chunks) * kp.ch.w2_sub_bytes;
+  }
+  const size_t fixed = static_cast<size_t>(kEpiGroups) * 2 * kStageBufBytes + 1024 + chain_bytes;
   // Weights stay resident in shared memory when the layer has a single N tile and they are small:
   // the persistent CTA then streams only activations (halves the L2->SM traffic of the shallow layers).
   const size_t b_total = static_cast<size_t>(kp.num_k_iters) * kp.b_stage_bytes;
@@ -612,7 +745,7 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   kp.stages = stages;
-  kp.tmem_cols = pow2_cols(2 * kp.block_n);
+  kp.tmem_cols = pow2_cols(2 * kp.acc_stride + (kp.ch.on ? 2 * kp.ch.n2 : 0));
   kp.ep.is_bf16 = d.dtype == YB_BF16;
   const uint32_t fmt = kp.ep.is_bf16 ? 1u : 0u;
   kp.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(kp.block_n >> 3) << 17) |
@@ -621,11 +754,43 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
   kp.bias = d.bias;
   kp.ep.residual = d.residual;
   kp.ep.res_cstride = d.res_cstride;
-  op->grid = dim3(kp.num_tiles < sms ? kp.num_tiles : sms, 1, 1);
+  grid = dim3(kp.num_tiles < sms ? kp.num_tiles : sms, 1, 1);
   // >= 120 KB so that two CTAs can never share an SM (each owns up to all 512 TMEM columns)
   size_t smem = static_cast<size_t>(stages) * stage_bytes + kp.b_res_bytes + fixed;
+  YB_REQUIRE(smem <= kSmemBudget, "conv: %zu bytes of shared memory needed, %zu available", smem, kSmemBudget);
   if (smem < 120 * 1024) smem = 120 * 1024;
-  op->smem_bytes = smem;
+  smem_bytes = smem;
+  return YB_OK;
+}
+
+int conv_configure_check(const yb_op_desc& d) {
+  ConvKernelParams kp;
+  dim3 grid;
+  size_t smem = 0;
+  return conv_configure(d, kp, grid, smem);
+}
+
+int conv_op_create(const yb_op_desc& d, ConvOp** out) {
+  int rc = load_driver_entry_points();
+  if (rc != YB_OK) return rc;
+  ConvOp* op = new ConvOp();
+  rc = conv_configure(d, op->kp, op->grid, op->smem_bytes);
+  if (rc != YB_OK) {
+    delete op;
+    return rc;
+  }
+  if (patch_conv_eligible(d)) {
+    rc = patch_conv_create(d, g_encode_tiled, &op->patch);
+    if (rc != YB_OK) {
+      delete op;
+      return rc;
+    }
+    *out = op;
+    return YB_OK;
+  }
+  ConvKernelParams& kp = op->kp;
+  const int Ho = d.Ho, Wo = d.Wo;
+  (void)Ho; (void)Wo;
 
   const CUtensorMapDataType dt =
       kp.ep.is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -698,6 +863,31 @@ int conv_op_create(const yb_op_desc& d, ConvOp** out) {
       return YB_ERR_CUDA;
     }
   }
+  op->tmap_w2 = op->tmap_b;      // placeholders when nothing is chained (never dereferenced)
+  op->tmap_out2 = op->tmap_out;
+  if (kp.ch.on) {
+    const yb_conv_chain& c = *d.chain;
+    const int kc = kp.ch.w2_row_bytes / 2;
+    cuuint64_t wdims[2] = {static_cast<cuuint64_t>(c.K_pad), static_cast<cuuint64_t>(c.Cout_pad)};
+    cuuint64_t wstrides[1] = {static_cast<cuuint64_t>(c.K_pad) * 2};
+    cuuint32_t wbox[2] = {static_cast<cuuint32_t>(kc), static_cast<cuuint32_t>(kp.ch.n2)};
+    cuuint32_t estr[2] = {1, 1};
+    cr = g_encode_tiled(&op->tmap_w2, dt, 2, const_cast<void*>(c.weight), wdims, wstrides, wbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle_for_row_bytes(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr == CUDA_SUCCESS) {
+      const int s2 = chain_store2_cols(kp.ch.n2);
+      cuuint64_t odims[2] = {static_cast<cuuint64_t>(c.Cout), static_cast<cuuint64_t>(kp.M)};
+      cuuint64_t ostrides[1] = {static_cast<cuuint64_t>(c.out_cstride) * 2};
+      cuuint32_t obox[2] = {static_cast<cuuint32_t>(s2), kBlockM};
+      cr = g_encode_tiled(&op->tmap_out2, dt, 2, c.out, odims, ostrides, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swizzle_for_row_bytes(s2 * 2), CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (cr != CUDA_SUCCESS) {
+      set_error("conv: cuTensorMapEncodeTiled (chained tail) failed with CUresult %d", static_cast<int>(cr));
+      delete op;
+      return YB_ERR_CUDA;
+    }
+  }
   op->fn = select_conv_kernel(kp);
   cudaError_t e = cudaFuncSetAttribute(op->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBudget));
   if (e != cudaSuccess) {
@@ -721,7 +911,7 @@ int conv_op_launch(const ConvOp* op, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, op->fn, op->tmap_a, op->tmap_b, op->tmap_out, op->kp));
+  YB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, op->fn, op->tmap_a, op->tmap_b, op->tmap_out, op->tmap_w2, op->tmap_out2, op->kp));
   return YB_OK;
 }
 

@@ -175,7 +175,8 @@ constexpr int kRowPixels = 32;       // pixels per warp
 constexpr int kRowWarps = 4;         // warps per block
 constexpr int kRowMaxBytes = 512;    // longest row handled (A*K 16-bit logits padded to a multiple of 8)
 constexpr int kRowPitch = kRowMaxBytes + 16;   // shared-memory row pitch: 132 words -> lanes spread over 8 banks
-constexpr int kRowList = 1024;       // block-local candidate list (entries beyond it fall back to global atomics)
+constexpr int kRowList = 512;        // block-local candidate list (entries beyond it fall back to global atomics)
+constexpr int kRowPairs = kRowPixels * YB_MAX_ANCHORS;   // per-warp list of (pixel, anchor) pairs that passed objectness
 
 template <typename T>
 __device__ __forceinline__ float row_elem(const uint8_t* row, int e) {
@@ -188,11 +189,12 @@ __device__ __forceinline__ float row_elem(const uint8_t* row, int e) {
 template <typename T>
 __global__ void __launch_bounds__(kRowWarps * 32)
 decode_rows_kernel(const __grid_constant__ DecodeParams p, Workspace ws, int blocks_per_image) {
-  extern __shared__ __align__(16) uint8_t s_rows_raw[];     // [kRowWarps][kRowPixels][kRowPitch] | list[kRowList] u64
+  extern __shared__ __align__(16) uint8_t s_rows_raw[];     // [kRowWarps][kRowPixels][kRowPitch] | list[kRowList] u64 | pairs[kRowWarps][kRowPairs] uint2
   __shared__ int s_count, s_base, s_maxc;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* s_rows = s_rows_raw + static_cast<size_t>(warp) * kRowPixels * kRowPitch;
   uint64_t* s_list = reinterpret_cast<uint64_t*>(s_rows_raw + static_cast<size_t>(kRowWarps) * kRowPixels * kRowPitch);
+  uint2* s_pairs = reinterpret_cast<uint2*>(s_list + kRowList) + warp * kRowPairs;
   const int P = p.pix_start[p.n_levels];                       // pixels per image over all levels
   const int img = blockIdx.x / blocks_per_image;
   const int r0 = (blockIdx.x - img * blocks_per_image) * (kRowWarps * kRowPixels) + warp * kRowPixels;
@@ -246,26 +248,43 @@ decode_rows_kernel(const __grid_constant__ DecodeParams p, Workspace ws, int blo
     }
   }
   float lane_maxc = -INFINITY;
-  // Class scan: every lane walks the classes of ITS OWN pixel's passing anchors (no cross-lane traffic; with ~20 % of
-  // the anchors passing objectness nearly every warp has work for every anchor, so lane-parallel beats the
-  // warp-serial "one (pixel, anchor) pair at a time" scan: 228 warp-instructions per pair, 38 M per yolov5s batch).
+  // Class scan.  The (pixel, anchor) pairs that passed objectness are first COMPACTED across the warp (ballot + prefix
+  // popcount into a per-warp list), then lane q takes pair q: with ~20 % of the anchors passing, the lane-owns-pixel
+  // scan ran every anchor's loop with ~6 of 32 lanes active (ncu: 18.6 active threads per instruction, the kernel
+  // issue-bound at 19.4 M warp instructions); compacted, one pass covers what took three.
   // A raw-logit pre-test spares the exact sigmoid for almost every class: sigmoid(x) * obj > thr  <=>  x > logit(thr/obj);
   // the exact expression (the reference's arithmetic) decides for the few that clear it.  The 1e-2 logit margin dwarfs
   // any rounding; for r -> 1 (obj barely above thr) every x > 15 is tested exactly.
-  const yb_head_level& L = p.lvl[lv];
+  const uint32_t lt_lanes = (1u << lane) - 1u;
+  int n_pairs = 0;
 #pragma unroll
   for (int a = 0; a < YB_MAX_ANCHORS; ++a) {
     if (a >= p.n_anchors) break;
-    if (!((pass_bits >> a) & 1u)) continue;
+    const bool pass = (pass_bits >> a) & 1u;
+    const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+    if (pass)   // px, py: 10 bits each (maps up to 1023 wide), level 2, anchor 2, source lane 5
+      s_pairs[n_pairs + __popc(bal & lt_lanes)] =
+          make_uint2(static_cast<uint32_t>(px) | static_cast<uint32_t>(py) << 10 | static_cast<uint32_t>(lv) << 20 |
+                         static_cast<uint32_t>(a) << 22 | static_cast<uint32_t>(lane) << 24,
+                     __float_as_uint(obj[a]));
+    n_pairs += __popc(bal);
+  }
+  __syncwarp();
+  for (int q = lane; q < n_pairs; q += 32) {
+    const uint2 ent = s_pairs[q];
+    const int qx = ent.x & 1023, qy = (ent.x >> 10) & 1023, ql = (ent.x >> 20) & 3, a = (ent.x >> 22) & 3;
+    const uint8_t* q_row = s_rows + ((ent.x >> 24) & 31) * kRowPitch;
+    const float q_obj = __uint_as_float(ent.y);
+    const yb_head_level& L = p.lvl[ql];
     float lt = -INFINITY;
     if (p.score_thresh > 0.f) {
-      const float rr = p.score_thresh / obj[a];                // < 1: the anchor passed obj > thr
+      const float rr = p.score_thresh / q_obj;                 // < 1: the anchor passed obj > thr
       lt = fminf(__logf(rr / (1.0f - rr)) - 1e-2f, 15.0f);
     }
-    const int anchor = p.lvl_start[lv] + (a * L.H + py) * L.W + px;
+    const int anchor = p.lvl_start[ql] + (a * L.H + qy) * L.W + qx;
     // The class logits of this anchor are elements [e0, e1) of the row; they are walked in aligned 16-byte chunks
-    // (8 logits per LDS.128: with the 528-byte row pitch the 32 lanes of a warp cover all 32 banks, where 2-byte loads
-    // hit 8 banks 4-way) and pre-tested two at a time in half2 / bfloat162 arithmetic against the threshold rounded DOWN.
+    // (8 logits per LDS.128) and pre-tested two at a time in half2 / bfloat162 arithmetic against the threshold
+    // rounded DOWN.
     const int e0 = a * K + 5, e1 = a * K + K;
     using T2 = typename std::conditional<std::is_same<T, __half>::value, __half2, __nv_bfloat162>::type;
     T2 lt2;
@@ -275,8 +294,8 @@ decode_rows_kernel(const __grid_constant__ DecodeParams p, Workspace ws, int blo
       lt2 = __bfloat162bfloat162(__float2bfloat16_rd(lt));
     bool any = false;
     for (int c = e0 >> 3; c <= (e1 - 1) >> 3; ++c) {
-      const uint4 q = *reinterpret_cast<const uint4*>(my_row + c * 16);
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      const uint4 qv = *reinterpret_cast<const uint4*>(q_row + c * 16);
+      const uint32_t w[4] = {qv.x, qv.y, qv.z, qv.w};
       uint32_t hit = 0;                                        // bit j: element 8c + j cleared the pre-test
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -293,8 +312,8 @@ decode_rows_kernel(const __grid_constant__ DecodeParams p, Workspace ws, int blo
         const int j = __ffs(hit) - 1;
         hit &= hit - 1;
         const int k = 8 * c + j - e0;
-        const float x = row_elem<T>(my_row, 8 * c + j);
-        const float score = __fmul_rn(sigmoidf_ref(x), obj[a]);
+        const float x = row_elem<T>(q_row, 8 * c + j);
+        const float score = __fmul_rn(sigmoidf_ref(x), q_obj);
         if (score > p.score_thresh) {
           any = true;
           const uint64_t key = (static_cast<uint64_t>(orderable_desc(score)) << 32) |
@@ -310,9 +329,9 @@ decode_rows_kernel(const __grid_constant__ DecodeParams p, Workspace ws, int blo
       }
     }
     if (any) {
-      const float4 b = decode_box(sigmoidf_ref(row_elem<T>(my_row, a * K + 0)), sigmoidf_ref(row_elem<T>(my_row, a * K + 1)),
-                                  sigmoidf_ref(row_elem<T>(my_row, a * K + 2)), sigmoidf_ref(row_elem<T>(my_row, a * K + 3)),
-                                  px, py, L.stride_px, L.anchors_px[2 * a], L.anchors_px[2 * a + 1]);
+      const float4 b = decode_box(sigmoidf_ref(row_elem<T>(q_row, a * K + 0)), sigmoidf_ref(row_elem<T>(q_row, a * K + 1)),
+                                  sigmoidf_ref(row_elem<T>(q_row, a * K + 2)), sigmoidf_ref(row_elem<T>(q_row, a * K + 3)),
+                                  qx, qy, L.stride_px, L.anchors_px[2 * a], L.anchors_px[2 * a + 1]);
       ws.boxes[static_cast<long long>(img) * p.anchors_per_image + anchor] = b;
       lane_maxc = fmaxf(lane_maxc, fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
     }
@@ -427,6 +446,75 @@ __device__ void bitonic_sort_smem(uint64_t* keys, int n) {
       __syncthreads();
     }
   }
+}
+
+// Bitonic sort of R * blockDim.x keys (blockDim.x = kNmsThreads) with the keys in REGISTERS: thread t owns elements
+// t*R .. t*R+R-1.  Of the log2(n)(log2(n)+1)/2 compare-exchange stages only those whose partner distance reaches into
+// another warp (j >= 32 R) go through shared memory with a barrier; distances inside a warp use shuffles and distances
+// below R stay inside the thread.  2048 keys: 10 barrier stages instead of 66 (measured: 50 k -> see profiles/ cycles for the
+// per-image sort of the bench's ~1100 candidates).  Same network as bitonic_sort_smem, so the same (total) order.
+template <int R>
+__device__ void bitonic_sort_regs(uint64_t* s) {
+  const int tid = threadIdx.x;
+  const int n = R * blockDim.x;
+  uint64_t v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = s[tid * R + r];
+  for (int k = 2; k <= n; k <<= 1) {
+    int j = k >> 1;
+    if (j >= 32 * R) {
+      // partners live in other warps: these stages run on the shared-memory copy
+      __syncthreads();   // everybody has finished reading the previous contents
+#pragma unroll
+      for (int r = 0; r < R; ++r) s[tid * R + r] = v[r];
+      __syncthreads();
+      for (; j >= 32 * R; j >>= 1) {
+        for (int pidx = tid; pidx < (n >> 1); pidx += blockDim.x) {
+          const int e = ((pidx & ~(j - 1)) << 1) | (pidx & (j - 1));   // element with bit j clear
+          const uint64_t a = s[e], b = s[e | j];
+          const bool up = (e & k) == 0;
+          if ((a > b) == up) {
+            s[e] = b;
+            s[e | j] = a;
+          }
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) v[r] = s[tid * R + r];
+    }
+    for (; j >= R; j >>= 1) {          // partner thread in the same warp
+      const int m = j / R;
+      const bool lower = (tid & m) == 0;
+      const bool up = ((tid * R) & k) == 0;
+      const bool keep_min = lower == up;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const uint64_t o = __shfl_xor_sync(0xffffffffu, v[r], m);
+        const bool take = keep_min ? (o < v[r]) : (o > v[r]);
+        v[r] = take ? o : v[r];
+      }
+    }
+#pragma unroll
+    for (int jj = R >> 1; jj >= 1; jj >>= 1) {   // partner register in the same thread (compile-time distances)
+      if (2 * jj <= k) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if ((r & jj) == 0) {
+            const bool up = ((tid * R + r) & k) == 0;
+            const uint64_t a = v[r], b = v[r | jj];
+            const bool sw = (a > b) == up;
+            v[r] = sw ? b : a;
+            v[r | jj] = sw ? a : b;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < R; ++r) s[tid * R + r] = v[r];
+  __syncthreads();
 }
 
 // In-CTA stable LSD radix sort (8-bit digits) of `count` keys living in global memory.
@@ -563,11 +651,14 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
   uint64_t* keys_g = ws.keys_a + static_cast<long long>(img) * p.cap_per_image;
   const uint64_t* sorted;
   if (count <= kSmallSort) {
-    int n2 = 32;
-    while (n2 < count) n2 <<= 1;
+    // padded to 4 (8) keys per thread with keys that sort last
+    const int n2 = count <= 4 * kNmsThreads ? 4 * kNmsThreads : 8 * kNmsThreads;
     for (int i = tid; i < n2; i += blockDim.x) s_keys[i] = i < count ? keys_g[i] : ~0ull;
     __syncthreads();
-    bitonic_sort_smem(s_keys, n2);
+    if (n2 == 4 * kNmsThreads)
+      bitonic_sort_regs<4>(s_keys);
+    else
+      bitonic_sort_regs<8>(s_keys);
     sorted = s_keys;
   } else {
     __syncthreads();
@@ -654,40 +745,52 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
     __syncthreads();
     const int S = s_nsurv;
     const int nwords = (S + 31) >> 5;
-    if (use_labmask) {   // bit i of s_labmask[label] <=> survivor i carries that label
-      if (tid < S) atomicOr(&s_labmask[sv_label[tid] * (kSweep / 32) + (tid >> 5)], 1u << (tid & 31));
+    if (use_labmask) {   // bit i of s_labmask[word][label] <=> survivor i carries that label (label-minor: lanes with
+                         // different labels hit different banks)
+      if (tid < S) atomicOr(&s_labmask[(tid >> 5) * p.n_classes + sv_label[tid]], 1u << (tid & 31));
       __syncthreads();
     }
     if (base == 0) YB_NMS_TICK();  // slot 6: compaction
-    // suppression bit-matrix: bit j of row i set iff survivor i (if kept) suppresses survivor j > i
-    if (tid < S) {
-      const float4 bi = sv_box[tid];
-      const float ai = sv_area[tid];
-      const int li = sv_label[tid];
-      for (int w = 0; w < kSweep / 32; ++w) {
+    // suppression bit-matrix: bit j of row i set iff survivor i (if kept) suppresses survivor j > i.  Only the words
+    // w >= i / 32 of a row are ever read; those (row, word) pairs are enumerated word-major (word w has
+    // min(S, 32 (w + 1)) rows) and dealt out round-robin, so every thread gets the same number of pairs -- with one
+    // thread per ROW the first warp walked 16 words per thread while the last walked one (70 k of the kernel's 185 k
+    // cycles were this triangle's critical path).
+    {
+      int w = 0, acc = 0;                         // pairs [acc, acc + rows(w)) belong to word w
+      for (int q = tid;; q += blockDim.x) {
+        while (w < nwords && q >= acc + min(S, 32 * (w + 1))) {
+          acc += min(S, 32 * (w + 1));
+          ++w;
+        }
+        if (w >= nwords) break;
+        const int i = q - acc;
+        const float4 bi = sv_box[i];
+        const float ai = sv_area[i];
+        const int li = sv_label[i];
         uint32_t bits = 0;
         const int j0 = w << 5;
-        if (w < nwords && j0 + 31 > tid) {
+        if (j0 + 31 > i) {
           // step 1: which later survivors can this one suppress at all (same class, or any in offset-trick mode)
           uint32_t cand;
           const int jend = min(32, S - j0);
           if (trick) {
             cand = jend == 32 ? 0xffffffffu : ((1u << jend) - 1u);
           } else if (use_labmask) {
-            cand = s_labmask[li * (kSweep / 32) + w];
+            cand = s_labmask[w * p.n_classes + li];
           } else {
             cand = 0;
             for (int b = 0; b < jend; ++b) cand |= (sv_label[j0 + b] == li ? 1u : 0u) << b;
           }
-          if (j0 <= tid) cand &= ~((2u << (tid - j0)) - 1u);   // only j > i
-          // step 2: IoU only for those (a warp now iterates max-popcount times instead of 32)
+          if (j0 <= i) cand &= ~((2u << (i - j0)) - 1u);   // only j > i
+          // step 2: IoU only for those (a warp iterates max-popcount times instead of 32)
           while (cand) {
             const int b = __ffs(cand) - 1;
             cand &= cand - 1;
             if (iou_over(bi, ai, sv_box[j0 + b], sv_area[j0 + b], p.iou_thresh)) bits |= 1u << b;
           }
         }
-        s_mask[tid * (kSweep / 32) + w] = bits;
+        s_mask[i * (kSweep / 32) + w] = bits;
       }
     }
     __syncthreads();
@@ -697,15 +800,37 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
     // only memory traffic is 16 independent shared-memory loads per KEPT survivor (no cross-lane exchange on
     // the critical path).
     if (warp == 0) {
+      // Survivors are resolved 32 at a time.  Inside a chunk the decision chain runs on registers only: every lane holds
+      // the chunk's 32 x 32 diagonal block (32 broadcast loads, issued up front) and walks the 32 survivors with a
+      // 4-instruction dependent chain each; the rows of the survivors that were kept are then OR-ed into the removed
+      // words of the LATER chunks by the lanes that own them (independent loads).  The one-survivor-at-a-time loop cost
+      // ~90 cycles per survivor (a shared-memory load and a vote on the critical path): 45 k of the kernel's 185 k cycles.
       uint32_t removed = 0, keep = 0;   // lane l owns word l of both sets (S <= 512 -> 16 words)
       int kc = s_kcount;
       const int kc0 = kc;
-      for (int i = 0; i < S; ++i) {
-        const bool mine = lane == (i >> 5);
-        if (__any_sync(0xffffffffu, mine && ((removed >> (i & 31)) & 1u))) continue;
-        if (mine) keep |= 1u << (i & 31);
-        if (lane < nwords) removed |= s_mask[i * (kSweep / 32) + lane];
-        if (++kc >= p.max_det) break;
+      for (int c = 0; c < nwords && kc < p.max_det; ++c) {
+        uint32_t diag[32];
+#pragma unroll
+        for (int b = 0; b < 32; ++b) diag[b] = (32 * c + b < S) ? s_mask[(32 * c + b) * (kSweep / 32) + c] : 0xffffffffu;
+        uint32_t rem_c = __shfl_sync(0xffffffffu, removed, c);
+        if (S - 32 * c < 32) rem_c |= ~((1u << (S - 32 * c)) - 1u);   // positions past the last survivor
+        uint32_t keep_c = 0;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) {
+          const bool take = !((rem_c >> b) & 1u) && kc < p.max_det;
+          kc += take ? 1 : 0;
+          keep_c |= (take ? 1u : 0u) << b;
+          rem_c |= take ? diag[b] : 0u;
+        }
+        if (lane == c) keep = keep_c;
+        if (lane > c && lane < nwords) {
+          uint32_t kk = keep_c;
+          while (kk) {
+            const int b = __ffs(kk) - 1;
+            kk &= kk - 1;
+            removed |= s_mask[(32 * c + b) * (kSweep / 32) + lane];
+          }
+        }
       }
       if (lane < kSweep / 32) s_keep[lane] = keep;
       if (lane == 0) s_newkept = kc - kc0;
@@ -1030,7 +1155,7 @@ extern "C" int yb_decode_candidates(const yb_nms_params* p, const yb_head_level*
   if (rows) {
     const int bpi = (dp.pix_start[p->n_levels] + kRowWarps * kRowPixels - 1) / (kRowWarps * kRowPixels);   // blocks per image
     const unsigned rblocks = static_cast<unsigned>(p->n_images) * static_cast<unsigned>(bpi);
-    constexpr int kRowSmem = kRowWarps * kRowPixels * kRowPitch + kRowList * 8;   // 66 KB rows + 8 KB candidate list
+    constexpr int kRowSmem = kRowWarps * kRowPixels * kRowPitch + kRowList * 8 + kRowWarps * kRowPairs * 8;   // 66 KB rows + 4 KB candidate list + 4 KB pair lists
     static bool configured = false;
     if (!configured) {
       YB_CHECK_CUDA(cudaFuncSetAttribute(decode_rows_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRowSmem));

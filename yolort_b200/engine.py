@@ -16,6 +16,8 @@ path_aggregation_network.py:199-239, box_head.py:68-82).  Here the module tree i
 
 Host code only prepares descriptors; all arithmetic happens in csrc/*.cu.
 """
+import ctypes
+import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
 
@@ -62,6 +64,12 @@ class _Op:
     pack: int = 1                          # horizontally adjacent pixels treated as ONE pixel with pack x channels
     force_im2col: bool = False             # keep this 3x3/s1 conv on the generic im2col kernel
     band: bool = False                     # weight is the banded super-pixel stem matrix (stem_band), Cin_pad 64
+    # The NEXT op of the list is a 1x1 convolution over this op's output (channels [0, chain_own) of it, followed by the
+    # channels of `chain_extra` if set) and may run as this op's chained tail in the same launch (yb_conv_chain);
+    # `chain_store`: this op's output is still read by somebody else and has to be written to memory.
+    chain_own: int = 0
+    chain_extra: Optional[_View] = None
+    chain_store: bool = True
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -259,11 +267,21 @@ class _Lowering:
                   _View(cat, 0, 2 * c_), 1, 1, 0, _C.YB_ACT_SILU)
         y = _View(cat, 0, c_)
         n = len(m.m)
+        # Pointwise chains (common.py:94-116,149-173): every 1x1 convolution of the block consumes the tile its
+        # predecessor has just produced -- cv1||cv2 -> m.0.cv1, m.i.cv2 -> m.(i+1).cv1, m.last.cv2 -> cv3 (whose other
+        # half, cv2(x), is fetched per tile).  Marked here, fused per shape where the kernels support it
+        # (PlanInstance); the last bottleneck's output is then never written (only cv3 reads it).
+        if n > 0:
+            self.ops[-1].chain_own = c_
         for i, blk in enumerate(m.m):
             t = self.buf(f"{name}.m{i}.t", div, c_)
             self.conv_module(f"{name}.m.{i}.cv1", blk.cv1, y, _View(t, 0, c_))
             out = _View(cat, 0, c_) if i == n - 1 else _View(self.buf(f"{name}.m{i}.y", div, c_), 0, c_)
             self.conv_module(f"{name}.m.{i}.cv2", blk.cv2, _View(t, 0, c_), out, residual=y if blk.add else None)
+            self.ops[-1].chain_own = c_
+            if i == n - 1:
+                self.ops[-1].chain_extra = _View(cat, c_, c_)
+                self.ops[-1].chain_store = False
             y = out
         self.conv_module(f"{name}.cv3", m.cv3, _View(cat, 0, 2 * c_), dst)
 
@@ -425,34 +443,41 @@ def front_op_count(L: _Lowering) -> int:
 
 
 def assign_offsets(L: _Lowering, x0: _Buf, keep: List[_Buf], N: int, H: int, W: int, reuse: bool, esz: int = 2,
-                   front_ops: int = 0):
-    """Arena layout for one (N, H, W): byte offset per buffer and the arena size.
+                   front_ops: int = 0, launches: Optional[List[Tuple[int, ...]]] = None):
+    """Arena layout for one (N, H, W): byte offset per buffer and the arena size.  `launches` groups the ops that run
+    as ONE kernel (chained tails): liveness is tracked per launch, since everything a fused launch touches is live at
+    the same time.
 
     With `reuse`, a buffer occupies its bytes only from its first writer to its last reader (launch order is the op
     order and every launch waits for the previous one, programmatic dependent launch included), so the arena is the
     peak of the live set instead of the sum of all activations (yolov5x batch 64 1280x1280: 56 GB -> a few GB).
     Buffers in `keep` (head logits, the PAN results) stay live to the end."""
-    n_ops = len(L.ops)
+    if launches is None:
+        launches = [(i,) for i in range(len(L.ops))]
+    step_of = {i: t for t, grp in enumerate(launches) for i in grp}
+    n_ops = len(launches)          # time is counted in launches
     size = {id(b): _round_up(N * (H // b.div) * (W // b.div) * b.C * esz, 1024) for b in L.bufs}
     first = {id(b): n_ops for b in L.bufs}
     last = {id(b): -1 for b in L.bufs}
     first[id(x0)] = -1
     for i, op in enumerate(L.ops):
-        first[id(op.dst.buf)] = min(first[id(op.dst.buf)], i)
-        last[id(op.dst.buf)] = max(last[id(op.dst.buf)], i)
+        t = step_of[i]
+        first[id(op.dst.buf)] = min(first[id(op.dst.buf)], t)
+        last[id(op.dst.buf)] = max(last[id(op.dst.buf)], t)
         for v in (op.src, op.residual):
             if v is not None:
-                last[id(v.buf)] = max(last[id(v.buf)], i)
-                first[id(v.buf)] = min(first[id(v.buf)], i)
+                last[id(v.buf)] = max(last[id(v.buf)], t)
+                first[id(v.buf)] = min(first[id(v.buf)], t)
     for b in keep:
         last[id(b)] = n_ops
     # chunked front (PlanInstance.run_front_chunk): the first `front_ops` ops run once per image chunk, so every buffer
     # they touch must keep its bytes until the last chunk has passed through all of them
+    front_steps = step_of[front_ops - 1] + 1 if front_ops else 0
     for i, op in enumerate(L.ops[:front_ops]):
         for v in (op.dst, op.src, op.residual):
             if v is not None:
                 first[id(v.buf)] = -1
-                last[id(v.buf)] = max(last[id(v.buf)], front_ops - 1)
+                last[id(v.buf)] = max(last[id(v.buf)], front_steps - 1)
     offsets: Dict[int, int] = {}
     if not reuse:
         off = 0
@@ -512,7 +537,7 @@ class PlanInstance:
     """Arena + native plan for one (N, H, W); weights come from the Engine's shared `Lowered`."""
 
     def __init__(self, low: Lowered, N: int, H: int, W: int, post: Optional[dict] = None, keep_intermediates: bool = False,
-                 chunked: bool = False):
+                 chunked: bool = False, fuse_chains: bool = True):
         L, x0, head_bufs, feats = low.L, low.x0, low.head_bufs, low.feats
         grain = max(b.div for b in L.bufs)
         if H % grain or W % grain:
@@ -524,23 +549,13 @@ class PlanInstance:
         # the input canvas stays live too, so that a plan can be re-run (timing loops, tests) without re-letterboxing
         keep = [x0] + list(head_bufs) + [v.buf for v in feats.values()]
         # chunked front: 4 chunks when the batch divides (>= 4 images per chunk)
-        self.front_ops = front_op_count(L) if (chunked and N % 4 == 0 and N >= 16 and not keep_intermediates) else 0
-        self.front_chunks = 4 if self.front_ops else 0
-        offsets, total = assign_offsets(L, x0, keep, N, H, W, reuse=not keep_intermediates, esz=esz,
-                                        front_ops=self.front_ops)
-        self.arena = torch.zeros((max(total, 1024),), dtype=torch.uint8, device=L.device)
-        self.arena_bytes = total
-        self.unshared_bytes = sum(_round_up(N * (H // b.div) * (W // b.div) * b.C * esz, 1024) for b in L.bufs)
-        base = self.arena.data_ptr()
+        front_ops = front_op_count(L) if (chunked and N % 4 == 0 and N >= 16 and not keep_intermediates) else 0
+        self.front_chunks = 4 if front_ops else 0
         code = _C.dtype_code(L.dtype)
+        self._chains: List[_C.ConvChain] = []    # yb_conv_chain blocks the descriptors point at (kept alive)
+        no_nsplit = os.environ.get("YB_NO_NSPLIT", "0") == "1"    # A/B timing: keep streamed weights + tile pairs
 
-        def ptr(v: _View) -> int:
-            return base + offsets[id(v.buf)] + v.ch0 * esz
-
-        descs = []
-        self.op_names = []
-        self.op_flops = []
-        for op in L.ops:
+        def make_desc(op: _Op, ptr) -> "_C.OpDesc":
             d = _C.OpDesc()
             hi, wi = H // op.src.buf.div, W // op.src.buf.div
             ho, wo = H // op.dst.buf.div, W // op.dst.buf.div
@@ -554,18 +569,84 @@ class PlanInstance:
             d.Ho, d.Wo = ho, wo
             d.Cout, d.out_cstride, d.out = op.dst.C * k, op.dst.buf.C * k, ptr(op.dst)
             d.ksize, d.stride, d.pad, d.act = op.ksize, op.stride, op.pad, op.act
-            flops = 0
             if op.kind == _C.YB_OP_CONV:
                 d.weight, d.bias = op.weight.data_ptr(), op.bias.data_ptr()
                 d.Cout_pad, _, d.Cin_pad = op.weight.shape
                 if op.band:
                     d.Cin_pad = 64     # [Cout_pad, 3, 2 x 64] banded stem matrix: one 64-channel chunk of super-pixels
-                flops = N * ho * wo * op.flops_per_pixel
-            d.reserved = (1 if op.force_im2col else 0) | (2 if op.band else 0)
+            d.reserved = (1 if op.force_im2col else 0) | (2 if op.band else 0) | (8 if no_nsplit else 0)
             if op.residual is not None:
                 d.residual, d.res_cstride = ptr(op.residual), op.residual.buf.C
+            return d
+
+        def make_chain(op: _Op, tail: _Op, ptr) -> "_C.ConvChain":
+            """yb_conv_chain for `tail` (the 1x1 convolution after `op`) riding on `op`'s launch."""
+            c = _C.ConvChain()
+            c.weight, c.bias = tail.weight.data_ptr(), tail.bias.data_ptr()
+            c.Cout_pad, _, c.K_pad = tail.weight.shape
+            c.Cout, c.act = tail.dst.C, tail.act
+            c.out, c.out_cstride = ptr(tail.dst), tail.dst.buf.C
+            c.own_C = op.chain_own
+            if op.chain_extra is not None:
+                c.extra, c.extra_C, c.extra_cstride = ptr(op.chain_extra), op.chain_extra.C, op.chain_extra.buf.C
+            # stage-wise inspection wants every activation in memory, also the one only the tail reads
+            c.store_first = 1 if (op.chain_store or keep_intermediates) else 0
+            return c
+
+        def chainable(i: int) -> bool:
+            op = L.ops[i]
+            if not (fuse_chains and op.chain_own > 0 and i + 1 < len(L.ops) and i + 1 != front_ops):
+                return False
+            tail = L.ops[i + 1]
+            if not (tail.kind == _C.YB_OP_CONV and tail.ksize == 1 and tail.stride == 1 and tail.residual is None
+                    and tail.pack == 1 and op.pack == 1 and op.kind == _C.YB_OP_CONV):
+                return False
+            d = make_desc(op, lambda v: 4096)           # support depends on shapes / alignment only
+            c = make_chain(op, tail, lambda v: 4096)
+            d.chain = ctypes.addressof(c)
+            return _C.conv_chain_supported(d)
+
+        # launch list: groups of op indices that run as one kernel
+        launches: List[Tuple[int, ...]] = []
+        i = 0
+        while i < len(L.ops):
+            if chainable(i):
+                launches.append((i, i + 1))
+                i += 2
+            else:
+                launches.append((i,))
+                i += 1
+        self.launch_ops = launches
+        step_of = {j: t for t, grp in enumerate(launches) for j in grp}
+        self.front_ops = step_of[front_ops - 1] + 1 if front_ops else 0     # in launches (what the run_* methods count)
+        self._front_op_count = front_ops                                       # in ops of the lowering
+        offsets, total = assign_offsets(L, x0, keep, N, H, W, reuse=not keep_intermediates, esz=esz,
+                                        front_ops=front_ops, launches=launches)
+        self.arena = torch.zeros((max(total, 1024),), dtype=torch.uint8, device=L.device)
+        self.arena_bytes = total
+        self.unshared_bytes = sum(_round_up(N * (H // b.div) * (W // b.div) * b.C * esz, 1024) for b in L.bufs)
+        base = self.arena.data_ptr()
+
+        def ptr(v: _View) -> int:
+            return base + offsets[id(v.buf)] + v.ch0 * esz
+
+        descs = []
+        self.op_names = []
+        self.op_flops = []
+        for grp in launches:
+            op = L.ops[grp[0]]
+            d = make_desc(op, ptr)
+            name = op.name
+            flops = N * (H // op.dst.buf.div) * (W // op.dst.buf.div // op.pack) * op.flops_per_pixel if op.kind == _C.YB_OP_CONV else 0
+            if len(grp) == 2:
+                tail = L.ops[grp[1]]
+                c = make_chain(op, tail, ptr)
+                self._chains.append(c)
+                d.chain = ctypes.addressof(c)
+                name = f"{op.name} -> {tail.name}"
+                flops += N * (H // tail.dst.buf.div) * (W // tail.dst.buf.div) * tail.flops_per_pixel
             descs.append(d)
-            self.op_names.append(op.name)
+            self.op_names.append(name)
             self.op_flops.append(flops)
         self._low = low                     # keeps the shared weights alive
         self.n_heads = low.n_heads
@@ -635,15 +716,15 @@ class PlanInstance:
     def _build_front_plans(self) -> None:
         """Launch lists of ops [0, front_ops) restricted to the images of one chunk: same descriptors, N = chunk and
         every tensor pointer advanced by the chunk's images (activations are NHWC, image-major)."""
-        import ctypes as _ct
-
         L = self._low.L
         c = self.N // self.front_chunks
         esz = 2
         plans = []
         for k in range(self.front_chunks):
             ds = []
-            for op, d in zip(L.ops[: self.front_ops], self._descs[: self.front_ops]):
+            chains = []
+            for grp, d in zip(self.launch_ops[: self.front_ops], self._descs[: self.front_ops]):
+                op = L.ops[grp[0]]
                 d2 = _C.OpDesc.from_buffer_copy(d)
                 d2.N = c
 
@@ -654,8 +735,16 @@ class PlanInstance:
                 d2.out = d.out + adv(op.dst)
                 if op.residual is not None:
                     d2.residual = d.residual + adv(op.residual)
+                if len(grp) == 2:      # chained tail: its own block of pointers
+                    tail = L.ops[grp[1]]
+                    c2 = _C.ConvChain.from_buffer_copy(_C.ConvChain.from_address(d.chain))
+                    c2.out = c2.out + adv(tail.dst)
+                    if op.chain_extra is not None:
+                        c2.extra = c2.extra + adv(op.chain_extra)
+                    chains.append(c2)
+                    d2.chain = ctypes.addressof(c2)
                 ds.append(d2)
-            plans.append(_C.Plan(ds, self.device))
+            plans.append(_C.Plan(ds, self.device))      # the native plan copies what it needs at creation
         self._front_plans = plans
 
     def run_front_chunk(self, k: int) -> None:
@@ -707,6 +796,8 @@ class Engine:
         self.lowerings = 0       # how many times the weights were folded/packed (tests: stays 1 across shapes)
         self.stem_variant = "auto"
         self.graphs = False      # replay plans as CUDA graphs (PlanInstance.run_graph)
+        # chained pointwise tails (yb_conv_chain); YB_NO_CHAIN=1 keeps every convolution its own launch (A/B timing)
+        self.fuse_chains = os.environ.get("YB_NO_CHAIN", "0") != "1"
 
     # -- weights -------------------------------------------------------------------------------------------------
     def _fingerprint(self) -> Tuple[int, ...]:
@@ -746,13 +837,13 @@ class Engine:
         pkey = None if post is None else (post["score_thresh"], post["nms_thresh"], post["detections_per_img"],
                                           post["semantics"], post["num_classes"])
         chunked = bool(chunked and N % 4 == 0 and N >= 16 and not keep_intermediates)
-        key = (N, H, W, pkey, bool(keep_intermediates), chunked)
+        key = (N, H, W, pkey, bool(keep_intermediates), chunked, bool(self.fuse_chains))
         inst = self._plans.get(key)
         if inst is not None:
             self._plans.move_to_end(key)
             return inst
         with _C.device_guard(self.device):
-            inst = PlanInstance(low, N, H, W, post, keep_intermediates, chunked)
+            inst = PlanInstance(low, N, H, W, post, keep_intermediates, chunked, self.fuse_chains)
         inst.use_graph = bool(self.graphs)
         self._plans[key] = inst
         budget = self._budget()
