@@ -81,3 +81,37 @@ def test_candidate_arena_grows_instead_of_truncating():
     out = PostProcess([8, 16, 32], 0.3, 0.45, 300, anchors_px=[[float(v) for v in a] for a in ANCH])(
         [h.to(DEV) for h in heads])[0]
     util.assert_dets_close(util.to_np(out), ref, box_atol=5e-4, score_atol=2e-6, allow_tie_swaps=True)
+
+
+_ANCH4 = [[float(v) for v in a] for a in ANCH] + [[436.0, 615.0, 739.0, 380.0, 925.0, 792.0]]
+
+
+@pytest.mark.parametrize("levels", [
+    [(16, 24), (8, 12), (4, 6)],
+    [(16, 24), (8, 12), (4, 6), (2, 3)],          # the P6 fixture's extents: 510 pixels, warps straddle level borders
+    [(20, 20), (10, 10), (5, 5), (3, 3)],
+])
+@pytest.mark.parametrize("obj_shift", [-4.0, -1.0])   # ~2 % / ~25 % of the anchors pass objectness
+def test_nhwc_row_decode_multi_level_vs_oracle(levels, obj_shift):
+    """The plan's NHWC-256 head layout through the coalesced row kernel (lane-owns-pixel load, compacted class scan)
+    + NMS against the oracle's decode + batched_nms on the same fp16 logits, for 3 and 4 detection levels."""
+    g = torch.Generator().manual_seed(31 * len(levels) + levels[0][0] + int(obj_shift))
+    n, a, nc = 2, 3, 80
+    k = nc + 5
+    strides = [8, 16, 32, 64][: len(levels)]
+    anchors = _ANCH4[: len(levels)]
+    nhwc, ref_heads = [], []
+    for (h, w) in levels:
+        t = torch.randn(n, h, w, a, k, generator=g) * 1.5
+        t[..., 4] += obj_shift
+        t[..., 5:] -= 1.0
+        th = t.half()
+        buf = torch.zeros(n, h, w, 256, dtype=torch.float16)
+        buf[..., : a * k] = th.view(n, h, w, a * k)
+        nhwc.append(buf.to(DEV))
+        ref_heads.append(th.float().permute(0, 3, 1, 2, 4).contiguous())
+    ref = R.postprocess(ref_heads, 0.25, 0.45, 300, R.TV_AUTO, strides, anchors)
+    got = _C.decode_nms(nhwc, "nhwc", strides, anchors, 0.25, 0.45, 300, num_classes=nc)
+    for gd, rd in zip(got, ref):
+        print(levels, obj_shift, "candidates", rd["n_candidates"], "dets", len(rd["scores"]))
+        util.assert_dets_close(util.to_np(gd), rd, box_atol=2e-4, score_atol=2e-6, allow_tie_swaps=True)

@@ -281,3 +281,52 @@ def test_u8_scaling_by_reciprocal_equals_division_after_16bit_rounding():
     mul = v.float() * torch.tensor(1.0 / 255.0, dtype=torch.float32)
     assert torch.equal(div.half(), mul.half()) and torch.equal(div.bfloat16(), mul.bfloat16())
     assert not torch.equal(div, mul)
+
+
+def _conv_desc(N, H, W, Cin, Cout, k, s, p, res=False):
+    import torch
+
+    d = _C.OpDesc()
+    d.kind, d.dtype = _C.YB_OP_CONV, _C.dtype_code(torch.float16)
+    d.N, d.H, d.W, d.Cin, d.in_cstride, d.in_ = N, H, W, Cin, Cin, 4096
+    d.Ho, d.Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    d.Cout, d.out_cstride, d.out = Cout, Cout, 4096
+    d.ksize, d.stride, d.pad, d.act = k, s, p, _C.YB_ACT_SILU
+    d.weight, d.bias = 4096, 4096
+    d.Cin_pad = (Cin + 63) // 64 * 64 if Cin > 32 else (Cin + 15) // 16 * 16
+    d.Cout_pad = (Cout + 15) // 16 * 16
+    if res:
+        d.residual, d.res_cstride = 4096, Cout
+    return d
+
+
+def test_conv_config_and_chain_support_are_host_logic():
+    """Launch configuration and chained-tail eligibility are decided without a GPU (yb_conv_config,
+    yb_conv_chain_supported): the yolov5s batch-32 640x640 layers land where DESIGN.md says."""
+    c = _C.conv_config(_conv_desc(32, 80, 80, 64, 64, 3, 1, 1))
+    assert c["patch_kernel"] == 1 and c["weights_resident"] == 1 and c["n_tiles"] == 1
+    c = _C.conv_config(_conv_desc(32, 40, 40, 128, 128, 3, 1, 1))           # 295 KB of weights: streamed, two tiles per pass
+    assert c["patch_kernel"] == 1 and c["weights_resident"] == 0 and c["tiles_per_pass"] == 2 and c["slots"] >= 3
+    c = _C.conv_config(_conv_desc(32, 160, 160, 64, 64, 1, 1, 0))
+    assert c["patch_kernel"] == 0 and c["weights_resident"] == 1 and c["smem_bytes"] <= 222 * 1024
+
+    def chain(d, cout, k, own, extra=0):
+        ch = _C.ConvChain()
+        ch.weight, ch.bias, ch.out = 4096, 4096, 4096
+        ch.Cout, ch.Cout_pad, ch.K_pad, ch.act, ch.out_cstride, ch.own_C = cout, (cout + 15) // 16 * 16, k, _C.YB_ACT_SILU, cout, own
+        if extra:
+            ch.extra, ch.extra_C, ch.extra_cstride = 4096, extra, 2 * extra
+        ch.store_first = 0 if extra else 1
+        d.chain = ctypes.addressof(ch)
+        ok = _C.conv_chain_supported(d)
+        cfg = _C.conv_config(d) if ok else None
+        return ok, cfg
+
+    ok, cfg = chain(_conv_desc(32, 160, 160, 64, 64, 1, 1, 0), 32, 32, 32)                 # cv1||cv2 -> m.0.cv1, c = 32
+    assert ok and cfg["chained"] == 1
+    ok, cfg = chain(_conv_desc(32, 80, 80, 64, 64, 3, 1, 1, res=True), 128, 128, 64, extra=64)   # m.cv2 -> cv3, c = 64
+    assert ok and cfg["chained"] == 1 and cfg["slots"] >= 2
+    ok, _ = chain(_conv_desc(32, 40, 40, 128, 128, 3, 1, 1, res=True), 256, 256, 128, extra=128)  # 128 KB of tail weights
+    assert not ok
+    ok, _ = chain(_conv_desc(32, 20, 20, 512, 512, 1, 1, 0), 256, 256, 256)                # several N tiles
+    assert not ok

@@ -119,10 +119,31 @@ def test_gpu_end_to_end_vs_reference_fixture_p6():
     m = _model()
     ims = [torch.from_numpy(z["img0"]).to(DEV), torch.from_numpy(z["img1"]).to(DEV)]
     out = m(ims)
+    # (1) against the reference fixture.  This random net sits at the edge of chaos (see the heads test above) and its
+    # boxes reach +-1300 px on a 192-px canvas ((2 sigmoid)^2 x 900-px anchors): a 1e-3 change of a head logit moves such a
+    # box by pixels, so the coordinate tolerance of the matched pairs is relative to the BOX here, and loose; the strict
+    # 1e-3-of-canvas check of the 4-level path is (2).  Measured on B200: matched 0.977 / 0.997, coordinates within
+    # 1.2e-2 of the box extent.
     for got, ref in zip(out, util.dets_from_npz(z, 2)):
+        frac = util.match_fraction(util.to_np(got), ref, iou_thr=0.9)
+        st = util.pair_stats(util.to_np(got), ref, 192.0)
+        print("p6 e2e matched:", frac, len(got["scores"]), len(ref["scores"]), st)
+        assert frac >= 0.95
+        extent = float(np.abs(ref["boxes"]).max())
+        assert st["max_box_rel"] * 192.0 <= 2e-2 * max(extent, 192.0)
+    # (2) post-processing of the 4-level path, strictly: the oracle's decode + batched_nms + scale_coords applied to the
+    # GPU's OWN head logits must reproduce the model's detections (labels exact, boxes within 1e-3 x canvas).
+    geoms, (Hb, Wb) = m.transform.geometry(ims)
+    plan = m.model.get_plan(2, Hb, Wb)
+    heads = []
+    for h in plan.heads:
+        hh = h[..., :255].float().cpu()
+        heads.append(hh.view(*hh.shape[:3], 3, 85).permute(0, 3, 1, 2, 4).contiguous())
+    own = R.postprocess(heads, 0.15, 0.45, 300, R.TV_AUTO, util.P6_STRIDES, util.P6_ANCHORS)
+    for got, ref, im in zip(out, own, ims):
+        ref["boxes"] = R.scale_coords(ref["boxes"], Hb, Wb, int(im.shape[-2]), int(im.shape[-1]))
         frac = util.match_fraction(util.to_np(got), ref, iou_thr=0.9, side=192)
-        print("p6 e2e matched:", frac, len(got["scores"]), len(ref["scores"]))
-        assert frac >= 0.95      # measured 0.973 / 0.997; matched boxes within 1e-3 x canvas
+        assert frac >= 0.999 and len(got["scores"]) == len(ref["scores"])
 
 
 @pytest.mark.gpu

@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "yb_letterbox_strided",
     "yb_scale_coords_params",
     "yb_conv_chain_supported",
+    "yb_conv_config",
     "yb_plan_create",
     "yb_plan_run",
     "yb_plan_run_range",
@@ -168,6 +169,7 @@ def lib() -> ctypes.CDLL:
                                          ctypes.POINTER(ctypes.c_float)]
     L.yb_plan_create.argtypes = [ctypes.POINTER(OpDesc), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
     L.yb_conv_chain_supported.argtypes = [ctypes.POINTER(OpDesc)]
+    L.yb_conv_config.argtypes = [ctypes.POINTER(OpDesc), ctypes.POINTER(ctypes.c_int32)]
     L.yb_plan_run.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     L.yb_plan_run_range.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     L.yb_plan_num_launches.argtypes = [ctypes.c_void_p]
@@ -334,6 +336,15 @@ def letterbox(images: List[torch.Tensor], geoms, Hb: int, Wb: int, fill: float, 
 def conv_chain_supported(op: "OpDesc") -> bool:
     """Whether the native library can run `op` (with op.chain set) as one fused launch (pure host logic)."""
     return bool(lib().yb_conv_chain_supported(ctypes.byref(op)))
+
+
+def conv_config(op: "OpDesc") -> dict:
+    """How the library would launch this convolution (host-only): kernel, tiling, residency, shared memory."""
+    info = (ctypes.c_int32 * 12)()
+    check(lib().yb_conv_config(ctypes.byref(op), info), "yb_conv_config")
+    keys = ("patch_kernel", "block_n", "n_tiles", "weights_resident", "tiles_per_pass", "slots", "ring", "store_cols",
+            "store_bufs", "smem_bytes", "grid", "chained")
+    return dict(zip(keys, [int(v) for v in info]))
 
 
 class Plan:

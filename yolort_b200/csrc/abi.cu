@@ -41,6 +41,12 @@ extern "C" int yb_conv_chain_supported(const yb_op_desc* op) {
   return rc == YB_OK ? 1 : 0;
 }
 
+extern "C" int yb_conv_config(const yb_op_desc* op, int32_t* info12) {
+  YB_REQUIRE(op != nullptr && info12 != nullptr && op->kind == YB_OP_CONV, "conv_config: needs a convolution op and an output array");
+  for (int i = 0; i < 12; ++i) info12[i] = 0;
+  return patch_conv_eligible(*op) ? patch_conv_configure_check(*op, info12) : conv_configure_check(*op, info12);
+}
+
 extern "C" int yb_plan_create(const yb_op_desc* ops, int n_ops, yb_plan** plan_out) {
   YB_REQUIRE(ops && n_ops > 0 && plan_out, "plan_create: null/empty arguments");
   yb_plan* plan = new yb_plan();

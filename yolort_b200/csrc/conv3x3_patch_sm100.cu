@@ -772,11 +772,9 @@ static int patch_conv_configure(const yb_op_desc& d, PatchParams& kp, dim3& grid
   kp.stage_buf_bytes = kStageBufBytes;
   // N-split with resident weights: when the whole filter bank does not fit in shared memory but half (a quarter) of it
   // does, every CTA keeps ONE N tile for all its tasks (grid % n_tiles == 0 makes task % n_tiles constant per CTA) and
-  // loads that slice once.  The patch is then fetched by n_tiles CTAs, but nothing is streamed per task any more:
-  // 128 -> 128 at 40 x 40 moved 295 KB of weights + 92 KB of patches per pair of tiles through a 5-slab ring
-  // (tensor pipe 38 % active); with two 64-column halves it is 46 KB of patch per half tile and 144 KB of weights per CTA,
-  // once.  Shared memory: 144 KB weights + two 23 KB patches leave 16 KB of staging -> 32-column store boxes, one
-  // buffer per epilogue group.
+  // loads that slice once; the patch is then fetched by n_tiles CTAs, but nothing is streamed per task any more.  Only
+  // taken when three patch slots still fit next to the slice (see below) -- which rules out the zoo's 128-channel
+  // layers (144 KB slice + 3 x 23 KB patches + staging > 222 KB): those keep the pair-of-tiles weight stream.
   int forced_store_cols = 0;
   size_t staging_ns = staging;
   if (!kp.b_resident && !kp.band && !kp.s2 && d.chain == nullptr && !(d.reserved & 8)) {
@@ -791,7 +789,10 @@ static int patch_conv_configure(const yb_op_desc& d, PatchParams& kp, dim3& grid
         if (bn % opt_cols[o]) continue;
         const size_t buf_bytes = static_cast<size_t>(128) * opt_cols[o] * 2;
         const size_t stg = static_cast<size_t>(kEpiGroups) * opt_bufs[o] * buf_bytes;
-        if (bt + 2 * kp.a_stride + stg + 1024 > kSmemBudget) continue;
+        // at least three patch slots: with two, a task that needs both (two channel chunks) cannot prefetch the next
+        // task's patch and every task pays the L2 latency -- measured on B200 (128 -> 128 at 40 x 40, batch 32): 30.8 us
+        // with 144 KB of resident weights and two slots vs 28.7 - 32.7 us streaming the weights for pairs of tiles
+        if (bt + 3 * kp.a_stride + stg + 1024 > kSmemBudget) continue;
         n_tiles = ns;
         block_n = bn;
         b_sub = bs;
@@ -895,11 +896,26 @@ static int patch_conv_configure(const yb_op_desc& d, PatchParams& kp, dim3& grid
   return YB_OK;
 }
 
-int patch_conv_configure_check(const yb_op_desc& d) {
+int patch_conv_configure_check(const yb_op_desc& d, int* info) {
   PatchParams kp;
   dim3 grid;
   size_t smem = 0;
-  return patch_conv_configure(d, kp, grid, smem);
+  const int rc = patch_conv_configure(d, kp, grid, smem);
+  if (rc == YB_OK && info) {   // yb_conv_config: see include/yolort_b200.h
+    info[0] = 1;
+    info[1] = kp.block_n;
+    info[2] = kp.n_tiles;
+    info[3] = kp.b_resident;
+    info[4] = kp.pair;
+    info[5] = kp.a_slots;
+    info[6] = kp.b_resident ? 0 : kp.b_stages;
+    info[7] = kp.store_cols;
+    info[8] = kp.store_bufs;
+    info[9] = static_cast<int>(smem);
+    info[10] = static_cast<int>(grid.x);
+    info[11] = kp.ch.on;
+  }
+  return rc;
 }
 
 int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConvOp** out) {

@@ -172,7 +172,9 @@ __device__ __forceinline__ void epilogue_box(const EpilogueParams& p, uint32_t t
           const __half2 r = __hfma2(h, *reinterpret_cast<__half2*>(&tp), h);
           o[j] = *reinterpret_cast<const uint32_t*>(&r);
         }
-        packed_ok = __hge(__hmin(__low2half(mn), __high2half(mn)), __float2half_rn(kSiluExactBelow));
+        // rows outside the output (ragged tiles, the junk rows of the wrap tiling) hold arbitrary data: they must not
+        // steer the warp's choice, or two launches on the same input could round their valid rows differently
+        packed_ok = !row_ok || __hge(__hmin(__low2half(mn), __high2half(mn)), __float2half_rn(kSiluExactBelow));
       }
 #ifdef YB_NO_SILU_GUARD      // A/B build without the guard (scripts/ab_step.sh)
       packed_ok = true;
@@ -218,7 +220,7 @@ __device__ __forceinline__ void epilogue_box(const EpilogueParams& p, uint32_t t
 #ifdef YB_NO_SILU_GUARD
       mn = 0.f;
 #endif
-      if (__any_sync(0xffffffffu, mn < kSiluExactBelow)) {   // see epilogue_batch_exact
+      if (__any_sync(0xffffffffu, row_ok && mn < kSiluExactBelow)) {   // see epilogue_batch_exact (valid rows only decide)
         epilogue_batch_exact<kBf16>(p.act, p.Cout, p.residual, p.res_cstride, taddr + b0, s_bias + b0, row, row_ok, col0 + b0, my_row, row_in_tile, b0 >> 3, kChunks, kRowBytes);
         continue;
       }

@@ -763,11 +763,26 @@ static int conv_configure(const yb_op_desc& d, ConvKernelParams& kp, dim3& grid,
   return YB_OK;
 }
 
-int conv_configure_check(const yb_op_desc& d) {
+int conv_configure_check(const yb_op_desc& d, int* info) {
   ConvKernelParams kp;
   dim3 grid;
   size_t smem = 0;
-  return conv_configure(d, kp, grid, smem);
+  const int rc = conv_configure(d, kp, grid, smem);
+  if (rc == YB_OK && info && !patch_conv_eligible(d)) {   // yb_conv_config: see include/yolort_b200.h
+    info[0] = 0;
+    info[1] = kp.block_n;
+    info[2] = kp.n_tiles;
+    info[3] = kp.b_resident;
+    info[4] = 1;
+    info[5] = kp.stages;
+    info[6] = kp.kpg;
+    info[7] = kp.store_cols;
+    info[8] = 2;
+    info[9] = static_cast<int>(smem);
+    info[10] = static_cast<int>(grid.x);
+    info[11] = kp.ch.on;
+  }
+  return rc;
 }
 
 int conv_op_create(const yb_op_desc& d, ConvOp** out) {

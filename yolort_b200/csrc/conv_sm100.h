@@ -15,13 +15,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 struct PatchConvOp;
 bool patch_conv_eligible(const yb_op_desc& d);
 int patch_conv_create(const yb_op_desc& d, EncodeTiledFn encode_tiled, PatchConvOp** out);
-int patch_conv_configure_check(const yb_op_desc& d);   // host-only validation + tiling (no driver calls)
+int patch_conv_configure_check(const yb_op_desc& d, int* info = nullptr);   // host-only validation + tiling (no driver calls)
 int patch_conv_launch(const PatchConvOp* op, cudaStream_t stream);
 void patch_conv_destroy(PatchConvOp* op);
 
 struct ConvOp;
 int conv_op_create(const yb_op_desc& d, ConvOp** out);
-int conv_configure_check(const yb_op_desc& d);         // host-only validation + tiling (no driver calls)
+int conv_configure_check(const yb_op_desc& d, int* info = nullptr);         // host-only validation + tiling (no driver calls)
 int conv_op_launch(const ConvOp* op, cudaStream_t stream);
 void conv_op_destroy(ConvOp* op);
 
