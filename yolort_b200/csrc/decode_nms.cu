@@ -783,11 +783,17 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
             for (int b = 0; b < jend; ++b) cand |= (sv_label[j0 + b] == li ? 1u : 0u) << b;
           }
           if (j0 <= i) cand &= ~((2u << (i - j0)) - 1u);   // only j > i
-          // step 2: IoU only for those (a warp iterates max-popcount times instead of 32)
+          // step 2: IoU only for those, two per iteration (independent chains: the loads and the division overlap)
           while (cand) {
-            const int b = __ffs(cand) - 1;
+            const int b0 = __ffs(cand) - 1;
             cand &= cand - 1;
-            if (iou_over(bi, ai, sv_box[j0 + b], sv_area[j0 + b], p.iou_thresh)) bits |= 1u << b;
+            const bool two = cand != 0;
+            const int b1 = two ? __ffs(cand) - 1 : b0;
+            cand &= cand - 1;          // no-op when cand is already 0
+            const bool o0 = iou_over(bi, ai, sv_box[j0 + b0], sv_area[j0 + b0], p.iou_thresh);
+            const bool o1 = iou_over(bi, ai, sv_box[j0 + b1], sv_area[j0 + b1], p.iou_thresh);
+            bits |= (o0 ? 1u : 0u) << b0;
+            bits |= (o1 ? 1u : 0u) << b1;   // b1 == b0 when there was only one: same bit
           }
         }
         s_mask[i * (kSweep / 32) + w] = bits;
@@ -823,13 +829,10 @@ nms_image_kernel(const NmsParams p, Workspace ws) {
           rem_c |= take ? diag[b] : 0u;
         }
         if (lane == c) keep = keep_c;
-        if (lane > c && lane < nwords) {
-          uint32_t kk = keep_c;
-          while (kk) {
-            const int b = __ffs(kk) - 1;
-            kk &= kk - 1;
-            removed |= s_mask[(32 * c + b) * (kSweep / 32) + lane];
-          }
+        if (lane > c && lane < nwords) {   // 32 predicated, independent loads (a data-dependent loop would serialise their latency)
+#pragma unroll
+          for (int b = 0; b < 32; ++b)
+            if ((keep_c >> b) & 1u) removed |= s_mask[(32 * c + b) * (kSweep / 32) + lane];
         }
       }
       if (lane < kSweep / 32) s_keep[lane] = keep;
