@@ -48,6 +48,36 @@ def test_float_inputs_and_s2d_layout_agree_with_nchw():
         assert (nchw.float().cpu() - ref).abs().max() <= (2e-3 if dt == torch.float16 else 8e-3)
 
 
+@pytest.mark.parametrize("hw", [(640, 640), (128, 192), (64, 72)])
+def test_identity_full_canvas_uint8_fast_kernel(hw):
+    """uint8 images that already have the canvas size (identity resize, no padding) take the dedicated copy kernel:
+    s2d[n, Y, X, (dy*2+dx)*4 + c] == half(byte / 255.0) bit for bit, the fourth channel of every quad zero; and a mixed
+    batch (one image smaller -> generic tile kernel) writes the same bits for the identity image."""
+    h, w = hw
+    g = torch.Generator().manual_seed(h + w)
+    ims = [torch.randint(0, 256, (3, h, w), dtype=torch.uint8, generator=g).to(DEV) for _ in range(3)]
+    tr = YOLOTransform(min(h, w), max(h, w), size_divisible=8)
+    geoms, (Hb, Wb) = tr.geometry(ims)
+    if (Hb, Wb) != (h, w):
+        pytest.skip("transform rounds this canvas up")
+    for dt in (torch.float16, torch.bfloat16):
+        s2d = torch.full((3, Hb // 2, Wb // 2, 16), 9.0, dtype=dt, device=DEV)
+        tr.letterbox_into(ims, geoms, Hb, Wb, s2d, _C.YB_LAYOUT_S2D16)
+        v = s2d.view(3, Hb // 2, Wb // 2, 2, 2, 4)
+        assert torch.all(v[..., 3] == 0)
+        back = v[..., :3].permute(0, 5, 1, 3, 2, 4).reshape(3, 3, Hb, Wb)
+        want = torch.stack([(im.float() / 255.0).to(dt) for im in ims])
+        assert torch.equal(back, want)
+        # same image next to a smaller one: the batch goes through the generic tile kernel
+        small = torch.randint(0, 256, (3, h - 8, w - 16), dtype=torch.uint8, generator=g).to(DEV)
+        mixed = [ims[0], small]
+        geoms2, (Hb2, Wb2) = tr.geometry(mixed)
+        if (Hb2, Wb2) == (Hb, Wb):
+            s2 = torch.full((2, Hb // 2, Wb // 2, 16), 9.0, dtype=dt, device=DEV)
+            tr.letterbox_into(mixed, geoms2, Hb, Wb, s2, _C.YB_LAYOUT_S2D16)
+            assert torch.equal(s2[0], s2d[0])
+
+
 def test_mixed_batch_geometry_639_trap():
     # sizes whose long side resizes to 639 (SURVEY.md appendix A.2) in one batch with a 640 one
     ims = [torch.randint(0, 256, (3, 800, 600), dtype=torch.uint8), torch.randint(0, 256, (3, 480, 640), dtype=torch.uint8)]

@@ -133,6 +133,26 @@ __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) {
   return __float2bfloat16_rn(v);
 }
 
+// byte -> float without a conversion instruction: 0x4B000000 | b is the float 2^23 + b, exactly; subtracting 2^23 leaves b.
+// (The conversion pipe, I2F / F2F, runs at a fraction of the ALU rate: the uint8 -> fp16 canvas was bound by it, ~48 us
+// for 39 M values whatever the memory access pattern -- measured on B200 with two different kernels.)
+__device__ __forceinline__ float byte_to_float(uint32_t word, int k) {   // byte k (0..3) of `word`
+  return __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | static_cast<uint32_t>(k))), 8388608.0f);
+}
+// two floats -> two 16-bit values with ONE packed conversion instruction
+template <typename DstT>
+__device__ __forceinline__ uint32_t cvt_pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t cvt_pack2<__half>(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+template <>
+__device__ __forceinline__ uint32_t cvt_pack2<__nv_bfloat16>(float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 // NCHW destination (reference layout): thread per (y, x), three planes.
 template <typename SrcT, typename DstT, bool kHwc>
 __global__ void letterbox_nchw_kernel(const __grid_constant__ BatchGeom bg, int img0, int Hb, int Wb,
@@ -311,63 +331,93 @@ letterbox_s2d_tile_kernel(const __grid_constant__ BatchGeom bg, int img0, int Hb
   }
   __syncthreads();
   StagedSrc<kHwc> S{s_src, s_mis, pitch, rows, y_lo, x_lo};
-  const int X = X0 + (tid & (kTileX - 1));
-  if (X >= W2) return;
-  if (s_rect[6]) {
-    // copy fast path: this thread's 2x2 canvas block = source pixels (2Y+dy - top, 2X+dx - left); per (row, channel)
-    // the two horizontally adjacent bytes sit side by side in the staged line
-    const int bx = 2 * (X - X0);                                   // x offset inside the staged rectangle
+  // Work item = HALF a space-to-depth pixel: canvas row 2Y + dy, columns 2X and 2X + 1, i.e. 16 contiguous output
+  // bytes.  Consecutive lanes take consecutive halves, so a warp's store instruction writes one contiguous 512-byte
+  // run (4 lines); with a whole pixel per thread the 16-byte pieces sat 32 bytes apart (8 lines per instruction) and the
+  // store wavefronts, not DRAM, bounded the kernel (see letterbox_s2d_identity_kernel below).
+  constexpr int kHalves = 2 * kTileY * kTileX;                      // 1024 per tile
+  const bool copy = s_rect[6] != 0;
 #pragma unroll
-    for (int k = 0; k < (kTileY * kTileX) / kTileThreads; ++k) {
-      const int Yl = (tid / kTileX) + k * (kTileThreads / kTileX);     // s2d row inside the tile
-      __align__(16) DstT v[16];
+  for (int k = 0; k < kHalves / kTileThreads; ++k) {
+    const int hp = tid + k * kTileThreads;
+    const int dy = hp & 1, xs = (hp >> 1) & (kTileX - 1), Yl = hp / (2 * kTileX);
+    const int X = X0 + xs, Y = Y0 + Yl;
+    if (X >= W2 || Y >= H2) continue;
+    float f[2][3];
+    if (copy) {
+      // copy fast path (identity resize, tile fully inside the image): the two horizontally adjacent bytes of a
+      // (row, channel) sit side by side in the staged line; bytes become floats without a conversion instruction and
+      // half(byte * (1/255)) equals half(torch's byte / 255.0) for all 256 byte values (tests/test_host_logic.py)
+      const int r = 2 * Yl + dy, bx = 2 * xs;
 #pragma unroll
-      for (int dy = 0; dy < 2; ++dy) {
-        const int r = 2 * Yl + dy;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const int line = kHwc ? r : c * rows + r;
-          const uint8_t* ln = s_src + line * pitch + s_mis[line] + (kHwc ? 3 * bx + c : bx);
-          // fp16 / bf16 of byte * (1/255) equals fp16 / bf16 of torch's byte / 255.0 for all 256 byte values
-          // (tests/test_host_logic.py checks the table), so the copy path needs no LUT round trip through shared memory
-          v[(dy * 2 + 0) * 4 + c] = cvt_out<DstT>(__fmul_rn(static_cast<float>(ln[0]), 1.0f / 255.0f));
-          v[(dy * 2 + 1) * 4 + c] = cvt_out<DstT>(__fmul_rn(static_cast<float>(ln[kHwc ? 3 : 1]), 1.0f / 255.0f));
-        }
-        v[(dy * 2 + 0) * 4 + 3] = cvt_out<DstT>(0.f);
-        v[(dy * 2 + 1) * 4 + 3] = cvt_out<DstT>(0.f);
+      for (int c = 0; c < 3; ++c) {
+        const int line = kHwc ? r : c * rows + r;
+        const uint8_t* ln = s_src + line * pitch + s_mis[line] + (kHwc ? 3 * bx + c : bx);
+        f[0][c] = __fmul_rn(byte_to_float(ln[0], 0), 1.0f / 255.0f);
+        f[1][c] = __fmul_rn(byte_to_float(ln[kHwc ? 3 : 1], 0), 1.0f / 255.0f);
       }
-      DstT* o = dst + ((static_cast<size_t>(img0 + li) * H2 + (Y0 + Yl)) * W2 + X) * 16;
-      reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(v)[0];
-      reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(v)[1];
-    }
-    return;
-  }
-#pragma unroll
-  for (int k = 0; k < (kTileY * kTileX) / kTileThreads; ++k) {
-    const int Y = Y0 + (tid / kTileX) + k * (kTileThreads / kTileX);
-    if (Y >= H2) break;
-    __align__(16) DstT v[16];
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
+    } else {
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
-        float rgb[3];
         if (staged)
-          sample_rgb_staged<kHwc>(g, S, s_lut, 2 * Y + dy, 2 * X + dx, fill, rgb);
+          sample_rgb_staged<kHwc>(g, S, s_lut, 2 * Y + dy, 2 * X + dx, fill, f[dx]);
         else if (any)
-          sample_rgb<uint8_t, kHwc>(g, s_lut, 2 * Y + dy, 2 * X + dx, fill, rgb);
+          sample_rgb<uint8_t, kHwc>(g, s_lut, 2 * Y + dy, 2 * X + dx, fill, f[dx]);
         else
-          rgb[0] = rgb[1] = rgb[2] = fill;
-        const int q = (dy * 2 + dx) * 4;
-        v[q + 0] = cvt_out<DstT>(rgb[0]);
-        v[q + 1] = cvt_out<DstT>(rgb[1]);
-        v[q + 2] = cvt_out<DstT>(rgb[2]);
-        v[q + 3] = cvt_out<DstT>(0.f);
+          f[dx][0] = f[dx][1] = f[dx][2] = fill;
       }
     }
-    DstT* o = dst + ((static_cast<size_t>(img0 + li) * H2 + Y) * W2 + X) * 16;
-    reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(v)[0];
-    reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(v)[1];
+    uint8_t* o = reinterpret_cast<uint8_t*>(dst + ((static_cast<size_t>(img0 + li) * H2 + Y) * W2 + X) * 16) + dy * 16;
+    *reinterpret_cast<uint4*>(o) = make_uint4(cvt_pack2<DstT>(f[0][0], f[0][1]), cvt_pack2<DstT>(f[0][2], 0.f),
+                                              cvt_pack2<DstT>(f[1][0], f[1][1]), cvt_pack2<DstT>(f[1][2], 0.f));
+  }
+}
+
+// Identity resize of planar uint8 images that cover the whole canvas (pre-sized inputs: the 640 x 640 headline case and
+// any serving front end that resizes on the host): nothing to interpolate, nothing to pad.  What bounds this copy is
+// the number of 128-byte lines a STORE instruction touches (one L1 wavefront per line), not arithmetic: with a thread
+// per space-to-depth pixel a warp's 16-byte stores sit 32 bytes apart (8 lines per instruction, the tile kernel's copy
+// path: 47 us), with a thread per 8 canvas pixels 128 bytes apart (32 lines: 60 - 66 us, measured).  Here LANE l WRITES
+// BYTES [16 l, 16 l + 16) of a 512-byte run: lane (x, dy) = (l / 2, l % 2) converts canvas row 2Y + dy, columns 2X,
+// 2X + 1 (three 2-byte loads; even / odd lanes read two source rows, 32 contiguous bytes each) into its half of
+// space-to-depth pixel X -- four lines per store instruction, four such runs per warp.
+// byte * (1/255) in fp32 then ONE packed conversion per value pair; half(byte * (1/255)) equals half(torch's byte / 255.0)
+// for all 256 byte values (tests/test_host_logic.py).
+constexpr int kIdRuns = 4;      // 512-byte runs (16 space-to-depth pixels each) per warp
+template <typename DstT>
+__global__ void __launch_bounds__(256)
+letterbox_s2d_identity_kernel(const __grid_constant__ BatchGeom bg, int img0, int Hb, int Wb, DstT* __restrict__ dst) {
+  const int li = blockIdx.z;
+  const int H2 = Hb >> 1, W2 = Wb >> 1;
+  const int xblocks = (W2 + 16 * kIdRuns - 1) / (16 * kIdRuns);
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= xblocks * H2) return;
+  const int Y = warp / xblocks, xb = warp - Y * xblocks;
+  const int dy = lane & 1, xo = lane >> 1;
+  const uint8_t* base = static_cast<const uint8_t*>(bg.img[li].src) + static_cast<size_t>(2 * Y + dy) * Wb;
+  const size_t plane = static_cast<size_t>(Hb) * Wb;
+  uint16_t in[kIdRuns][3];
+#pragma unroll
+  for (int r = 0; r < kIdRuns; ++r) {
+    const int X = xb * 16 * kIdRuns + r * 16 + xo;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      in[r][c] = X < W2 ? __ldg(reinterpret_cast<const uint16_t*>(base + c * plane + 2 * X)) : static_cast<uint16_t>(0);
+  }
+  uint8_t* orow = reinterpret_cast<uint8_t*>(dst + (static_cast<size_t>(img0 + li) * H2 + Y) * W2 * 16);
+#pragma unroll
+  for (int r = 0; r < kIdRuns; ++r) {
+    const int X = xb * 16 * kIdRuns + r * 16 + xo;
+    float f[2][3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      f[0][c] = __fmul_rn(byte_to_float(in[r][c], 0), 1.0f / 255.0f);
+      f[1][c] = __fmul_rn(byte_to_float(in[r][c], 1), 1.0f / 255.0f);
+    }
+    if (X < W2)
+      *reinterpret_cast<uint4*>(orow + static_cast<size_t>(X) * 32 + dy * 16) =
+          make_uint4(cvt_pack2<DstT>(f[0][0], f[0][1]), cvt_pack2<DstT>(f[0][2], 0.f), cvt_pack2<DstT>(f[1][0], f[1][1]),
+                     cvt_pack2<DstT>(f[1][2], 0.f));
   }
 }
 
@@ -380,6 +430,21 @@ int launch_typed(const BatchGeom& bg, int img0, int count, int Hb, int Wb, float
     letterbox_nchw_kernel<SrcT, DstT, kHwc><<<grid, threads, 0, stream>>>(bg, img0, Hb, Wb, fill, lut,
                                                                     static_cast<DstT*>(dst));
   } else if constexpr (std::is_same<SrcT, uint8_t>::value && sizeof(DstT) == 2) {
+    if constexpr (!kHwc) {
+      bool identity = (Wb % 2 == 0) && (Hb % 2 == 0);
+      for (int j = 0; j < count && identity; ++j) {
+        const ImgGeom& g = bg.img[j];
+        identity = g.src_h == Hb && g.src_w == Wb && g.new_h == Hb && g.new_w == Wb && g.top == 0 && g.left == 0 &&
+                   (reinterpret_cast<uintptr_t>(g.src) & 1) == 0;
+      }
+      if (identity) {
+        const int warps_total = ((Wb / 2 + 16 * kIdRuns - 1) / (16 * kIdRuns)) * (Hb / 2);
+        dim3 grid((warps_total * 32 + 255) / 256, 1, count);
+        letterbox_s2d_identity_kernel<DstT><<<grid, 256, 0, stream>>>(bg, img0, Hb, Wb, static_cast<DstT*>(dst));
+        YB_CHECK_CUDA(cudaGetLastError());
+        return YB_OK;
+      }
+    }
     dim3 grid((Wb / 2 + kTileX - 1) / kTileX, (Hb / 2 + kTileY - 1) / kTileY, count);
     // staging bytes for the largest source rectangle of a 16 x 128 output tile in this batch (identity resizes need
     // 8 KB, a 2x down-scale ~31 KB): small footprints let more CTAs share an SM and hide the load -> sample latency
