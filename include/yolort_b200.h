@@ -156,7 +156,9 @@ typedef struct {
   int32_t reserved;             /* bit 0: keep a 3x3 conv on the generic im2col kernel; bit 1: `weight` is the banded
                                    super-pixel stem matrix [Cout_pad][3][128] (engine.stem_band); bit 2: take the
                                    halo-patch kernel's stride-2 parity-plane variant whatever the channel counts (tests);
-                                   bit 3: do not split N over CTAs with resident weights (A/B timing, tests) */
+                                   bit 3: do not split N over CTAs with resident weights (A/B timing, tests);
+                                   bit 4: four TMEM accumulator stages instead of two where they fit (measured equal or slower on
+                                   B200: 1.315 vs 1.312 ms per yolov5s plan; opt-in for A/B timing) */
   const yb_head_decode* decode; /* optional (host pointer, copied at plan creation): fused decode epilogue */
   const yb_conv_chain* chain;   /* optional (host pointer, copied at plan creation): chained pointwise tail  */
 } yb_op_desc;

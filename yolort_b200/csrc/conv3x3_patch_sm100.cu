@@ -77,6 +77,8 @@ struct PatchParams {
   TileGeom tg;
   uint32_t a_bytes, a_stride, b_sub_bytes, b_res_bytes, tmem_cols, idesc;   // a_stride: bytes reserved per patch
   int acc_stride;         // TMEM columns per accumulator slot (= block_n)
+  int acc_stages;         // accumulator stages of single-tile tasks: 2, or 4 (each epilogue group owns two, so the MMAs of
+                          // its next task are done before it has stored the current one); pair tasks always use 2 x 2 slots
   int acc2_base;          // chain: first TMEM column of the tail's two accumulators (n2 columns each)
   const float* bias;
   EpilogueParams ep;
@@ -215,7 +217,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t a_full[kMaxA], a_empty[kMaxA];
   __shared__ __align__(8) uint64_t b_full[kMaxB], b_empty[kMaxB];
-  __shared__ __align__(8) uint64_t acc_full[2], acc_empty[2];
+  __shared__ __align__(8) uint64_t acc_full[4], acc_empty[4];
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_bias[kEpiGroups][kMaxBlockN];
   __shared__ __align__(8) uint64_t a2_full[kEpiGroups];     // chain: the tile's output box(es) are in shared memory
@@ -246,9 +248,11 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < 4; ++g) {
       mbar_init(&acc_full[g], 1);
       mbar_init(&acc_empty[g], 4 * p.pair);   // pair tasks are drained by both epilogue groups (8 warps)
+    }
+    for (int g = 0; g < 2; ++g) {
       mbar_init(&a2_full[g], 1);
       mbar_init(&x_full[g], 1);
       mbar_init(&acc2_full[g], 1);
@@ -411,8 +415,8 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         tc_fence_after();
       }
       for (int task = blockIdx.x; task < p.num_tasks; task += gridDim.x, ++lt) {
-        const int as = lt & 1;
-        const uint32_t aph = (lt >> 1) & 1;
+        const int as = lt % p.acc_stages;
+        const uint32_t aph = (lt / p.acc_stages) & 1;
         const int m_first = (task / p.n_tiles) * p.pair;
         const int cnt = p.s2 ? 2 : min(p.pair, p.m_tiles - m_first);
         mbar_wait(&acc_empty[as], aph ^ 1);
@@ -484,7 +488,7 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         if (YB_ELECT()) umma_commit(&acc_full[as]);
         if constexpr (kChain) {
           if (pend >= 0) issue_tail(pend);
-          pend = as;
+          pend = lt & 1;   // the epilogue group that drains this task
         }
       }
       if constexpr (kChain) {
@@ -536,10 +540,10 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         work = m_tile < p.m_tiles;
       } else {
         if ((lt & 1) != g) continue;
-        as = g;
-        slot = g;
+        as = lt % p.acc_stages;
+        slot = as;
       }
-      const uint32_t aph = (lt >> 1) & 1;
+      const uint32_t aph = (lt / p.acc_stages) & 1;
       const int n0 = (task % p.n_tiles) * p.block_n;
       int n_img = 0, y0 = 0, x0 = 0;
       if (work) tile_coords(p, m_tile, n_img, y0, x0);
@@ -832,6 +836,7 @@ static int patch_conv_configure(const yb_op_desc& d, PatchParams& kp, dim3& grid
     return YB_ERR_INVALID;
   }
   kp.acc_stride = block_n;
+  kp.acc_stages = 2;
   kp.ch.on = 0;
   if (d.chain != nullptr) {
     YB_REQUIRE(kp.b_resident && kp.pair == 1 && !kp.s2 && !kp.band,
@@ -843,7 +848,8 @@ static int patch_conv_configure(const yb_op_desc& d, PatchParams& kp, dim3& grid
     YB_REQUIRE(why == nullptr, "patch conv: chained tail not supported here: %s", why);
     YB_REQUIRE(chain_store2_cols(kp.ch.n2) == 64, "patch conv: the tail's Cout_pad must be a multiple of 64, got %d", kp.ch.n2);
     YB_REQUIRE(static_cast<size_t>(kp.ch.w2_chunks) * kp.ch.w2_sub_bytes == chain_bytes, "patch conv: tail weight layout mismatch");
-    kp.acc2_base = 2 * kp.acc_stride;
+    kp.acc_stages = ((d.reserved & 16) && 4 * kp.acc_stride + 2 * kp.ch.n2 <= 512) ? 4 : 2;
+    kp.acc2_base = kp.acc_stages * kp.acc_stride;
     YB_REQUIRE(kp.acc2_base + 2 * kp.ch.n2 <= 512, "patch conv: accumulators of the convolution and its tail exceed TMEM");
     // the extra block arrives as the output tile's box: tile_w x tile_h pixel-rows (120 for the wrap tiling; the rows
     // beyond are never stored)
@@ -871,8 +877,9 @@ static int patch_conv_configure(const yb_op_desc& d, PatchParams& kp, dim3& grid
     }
   }
   YB_REQUIRE(kp.a_slots >= 2, "patch conv: fewer than two patch slots fit in shared memory (block_n=%d)", block_n);
+  if (!kp.ch.on && kp.pair == 1 && 4 * kp.acc_stride <= 512 && (d.reserved & 16)) kp.acc_stages = 4;   // reserved bit 4: four stages (measured equal or slower: opt-in)
   uint32_t cols = 32;
-  while (static_cast<int>(cols) < 2 * kp.pair * kp.acc_stride + (kp.ch.on ? 2 * kp.ch.n2 : 0)) cols <<= 1;
+  while (static_cast<int>(cols) < (kp.pair == 2 ? 4 : kp.acc_stages) * kp.acc_stride + (kp.ch.on ? 2 * kp.ch.n2 : 0)) cols <<= 1;
   if (cols > 512) {
     set_error("patch conv: %d accumulator columns exceed TMEM (pair=%d block_n=%d)", 2 * kp.pair * kp.acc_stride, kp.pair, block_n);
     return YB_ERR_INVALID;

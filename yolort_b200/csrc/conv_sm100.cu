@@ -39,6 +39,7 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kMaxStages = 12;
 constexpr int kEpiGroups = 2;
+constexpr int kMaxAccStages = 4;
 constexpr int kFirstEpiWarp = 3;                     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warp 2: idle
 constexpr int kThreads = 32 * kFirstEpiWarp + kEpiGroups * 128;
 constexpr int kStageBufBytes = 128 * 128;  // 128 rows x (up to) 64 columns x 2 B
@@ -60,7 +61,10 @@ struct ConvKernelParams {
   int kk_last;     // K=16 steps of the LAST channel chunk (Cin need not fill it: TMA zero-fills, the MMA skips)
   int dbg;         // ablation knobs, -DYB_ABLATION builds only (common.cuh)
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, idesc;
-  int acc_stride;  // TMEM columns between the two accumulator stages (= block_n)
+  int acc_stride;  // TMEM columns between accumulator stages (= block_n)
+  int acc_stages;  // 2 or 4 accumulator stages: with 4, each epilogue group owns two and the MMAs of its next tile have
+                   // completed by the time it has stored the current one (with 2 the group waited out MMA + commit latency
+                   // at the start of every tile)
   int acc2_base;   // chain: first TMEM column of the tail's two accumulators (n2 columns each), after the first conv's
   const float* bias;
   EpilogueParams ep;
@@ -90,8 +94,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t acc_full[kEpiGroups];
-  __shared__ __align__(8) uint64_t acc_empty[kEpiGroups];
+  __shared__ __align__(8) uint64_t acc_full[kMaxAccStages];
+  __shared__ __align__(8) uint64_t acc_empty[kMaxAccStages];
   __shared__ __align__(8) uint64_t b_full;
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float s_bias[kEpiGroups][kMaxBlockN];
@@ -121,9 +125,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&b_full, 1);
-    for (int g = 0; g < kEpiGroups; ++g) {
+    for (int g = 0; g < kMaxAccStages; ++g) {
       mbar_init(&acc_full[g], 1);
-      mbar_init(&acc_empty[g], 4);  // one arrival per epilogue warp of the group
+      mbar_init(&acc_empty[g], 4);  // one arrival per epilogue warp of the group that drains the stage
+    }
+    for (int g = 0; g < kEpiGroups; ++g) {
       mbar_init(&a2_full[g], 1);
       mbar_init(&acc2_full[g], 1);
     }
@@ -269,9 +275,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tc_fence_after();
       }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
-        const int as = lt & 1;
+        const int as = lt % p.acc_stages;   // accumulator stage; the epilogue group is lt & 1 (stages are even / odd alike)
 
-        const uint32_t aph = (lt >> 1) & 1;
+        const uint32_t aph = (lt / p.acc_stages) & 1;
         mbar_wait(&acc_empty[as], aph ^ 1);  // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * p.acc_stride;
@@ -312,7 +318,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (YB_ELECT()) umma_commit(&acc_full[as]);  // accumulator of this tile complete
         if constexpr (kChain) {
           if (pend >= 0) issue_tail(pend);
-          pend = as;
+          pend = lt & 1;   // the group that drains this tile
         }
       }
       if constexpr (kChain) {
@@ -350,18 +356,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
       if ((lt & 1) != g) continue;
-      const uint32_t aph = (lt >> 1) & 1;
+      const int as = lt % p.acc_stages;
+      const uint32_t aph = (lt / p.acc_stages) & 1;
       const int m_tile = tile / p.n_tiles;
       const int n0 = (tile - m_tile * p.n_tiles) * p.block_n;
       const int m0 = m_tile * kBlockM;
       const long long row = static_cast<long long>(m0) + row_in_tile;
       const bool row_ok = row < p.M;
       if (YB_DBG(p, 16)) {   // ablation: accumulator handshake only
-        mbar_wait(&acc_full[g], aph);
+        mbar_wait(&acc_full[as], aph);
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[g]);
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
         continue;
       }
       if (!fixed_n) {
@@ -373,9 +380,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (issuer) tma_store_wait_read<0>();
       }
       if (kChain || !fixed_n) named_bar_sync(bar_id, 128);
-      mbar_wait(&acc_full[g], aph);
+      mbar_wait(&acc_full[as], aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * p.acc_stride;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.acc_stride;
       if constexpr (kDecode) {
         // ---- fused post-processing front end (yolort/models/box_head.py:328-360,418) ----
         // This thread owns one output pixel: all A*(nc+5) logits of its anchors sit in its TMEM lane.  Per anchor:
@@ -476,7 +483,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[g]);
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
         continue;
       }
       for (int c0 = 0; c0 < p.block_n; c0 += store_cols, ++store_idx) {
@@ -491,7 +498,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           // all TMEM reads of this tile are done: hand the accumulator stage back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty[g]);
+          if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
         fence_proxy_async_smem();
         if constexpr (!kChain) {
@@ -711,6 +718,7 @@ static int conv_configure(const yb_op_desc& d, ConvKernelParams& kp, dim3& grid,
   kp.a_stage_bytes = kBlockM * kp.block_k * 2;
   kp.b_stage_bytes = (static_cast<uint32_t>(kp.block_n * kp.block_k * 2) + 1023u) & ~1023u;
   kp.acc_stride = kp.block_n;
+  kp.acc_stages = 2;
   kp.ch.on = 0;
   size_t chain_bytes = 0;
   if (d.chain != nullptr) {
@@ -719,7 +727,8 @@ static int conv_configure(const yb_op_desc& d, ConvKernelParams& kp, dim3& grid,
     YB_REQUIRE(why == nullptr, "conv: chained tail not supported here: %s", why);
     const int s2 = chain_store2_cols(kp.ch.n2);
     YB_REQUIRE(s2 == 64 || s2 == 32, "conv: the tail's Cout_pad must be a multiple of 32, got %d", kp.ch.n2);
-    kp.acc2_base = 2 * kp.acc_stride;
+    kp.acc_stages = ((d.reserved & 16) && 4 * kp.acc_stride + 2 * kp.ch.n2 <= 512) ? 4 : 2;
+    kp.acc2_base = kp.acc_stages * kp.acc_stride;
     YB_REQUIRE(kp.acc2_base + 2 * kp.ch.n2 <= 512, "conv: accumulators of the convolution and its tail exceed TMEM (%d + %d columns)",
                kp.acc2_base, 2 * kp.ch.n2);
     chain_bytes = static_cast<size_t>(kp.ch.w2_chunks) * kp.ch.w2_sub_bytes;
@@ -745,7 +754,8 @@ static int conv_configure(const yb_op_desc& d, ConvKernelParams& kp, dim3& grid,
   if (stages > kMaxStages) stages = kMaxStages;
   if (stages < 2) stages = 2;
   kp.stages = stages;
-  kp.tmem_cols = pow2_cols(2 * kp.acc_stride + (kp.ch.on ? 2 * kp.ch.n2 : 0));
+  if (!kp.ch.on && 4 * kp.acc_stride <= 512 && (d.reserved & 16)) kp.acc_stages = 4;   // reserved bit 4: four stages (measured equal or slower: opt-in)
+  kp.tmem_cols = pow2_cols(kp.acc_stages * kp.acc_stride + (kp.ch.on ? 2 * kp.ch.n2 : 0));
   kp.ep.is_bf16 = d.dtype == YB_BF16;
   const uint32_t fmt = kp.ep.is_bf16 ? 1u : 0u;
   kp.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(kp.block_n >> 3) << 17) |

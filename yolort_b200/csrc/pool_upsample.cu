@@ -7,6 +7,8 @@
 //    produces all three (nested windows), 8 channels (16 bytes) per thread.
 //  * nearest-neighbour 2x upsample (nn.Upsample(scale_factor=2), path_aggregation_network.py:123,134),
 //    writing into a channel window of the next concat buffer.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "conv_sm100.h"
 
@@ -67,44 +69,51 @@ __global__ void spp_pool_kernel(const uint16_t* __restrict__ in, int in_cs, uint
 }
 
 // SPPF-style cascade in shared memory: mp9 = mp5(mp5(x)), mp13 = mp5(mp9) (exactly equal to the direct
-// windows with -inf padding, yolort/v5/models/common.py:196).  One CTA owns one (image, channel-octet)
-// plane: 3 planes of H*W 16-byte pixels in shared memory, separable 5-tap max (rows then columns).
+// windows with -inf padding, yolort/v5/models/common.py:196).  One CTA owns the H x W planes of G adjacent channel
+// octets of one image: 3 buffers of H*W*G 16-byte items [pixel][octet] in shared memory, separable 5-tap max (rows then
+// columns).  G octets = 16 G contiguous bytes per pixel in global memory: with G = 8 a warp's load / store instruction
+// covers four whole 128-byte lines, where the one-octet-per-CTA version touched 32 lines for 16 bytes each (the pixel
+// stride of the concat buffer is 2 KB) -- 20.6 us for 26 MB of traffic on B200, bound by those wavefronts.
 template <bool kBf16>
 __global__ void spp_pool_cascade_kernel(const uint16_t* __restrict__ in, int in_cs, uint16_t* __restrict__ out,
-                                        int out_cs, int H, int W, int C) {
+                                        int out_cs, int H, int W, int C, int G) {
   extern __shared__ __align__(16) uint8_t pool_smem[];
-  const int c8n = C >> 3;
-  const int n = blockIdx.x / c8n;
-  const int c8 = blockIdx.x - n * c8n;
-  const int HW = H * W;
+  const int groups = (C >> 3) / G;
+  const int n = blockIdx.x / groups;
+  const int c8 = (blockIdx.x - n * groups) * G;      // first octet of this CTA
+  const int HW = H * W, items = HW * G;
   uint4* cur = reinterpret_cast<uint4*>(pool_smem);
-  uint4* tmp = cur + HW;
-  uint4* nxt = tmp + HW;
+  uint4* tmp = cur + items;
+  uint4* nxt = tmp + items;
   const uint16_t* src = in + static_cast<long long>(n) * HW * in_cs + c8 * 8;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x)
-    cur[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(i) * in_cs));
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int pix = i / G, o = i - pix * G;
+    cur[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<long long>(pix) * in_cs + o * 8));
+  }
   __syncthreads();
   uint16_t* dst = out + static_cast<long long>(n) * HW * out_cs + c8 * 8;
   for (int level = 0; level < 3; ++level) {
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) {  // horizontal 5-tap
-      const int y = i / W, x = i - y * W;
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {  // horizontal 5-tap
+      const int pix = i / G;
+      const int y = pix / W, x = pix - y * W;
       uint4 m = cur[i];
       for (int dx = -2; dx <= 2; ++dx) {
         const int xx = x + dx;
-        if (dx != 0 && xx >= 0 && xx < W) max8<kBf16>(m, cur[y * W + xx]);
+        if (dx != 0 && xx >= 0 && xx < W) max8<kBf16>(m, cur[i + dx * G]);
       }
       tmp[i] = m;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) {  // vertical 5-tap
-      const int y = i / W, x = i - y * W;
+    for (int i = threadIdx.x; i < items; i += blockDim.x) {  // vertical 5-tap
+      const int pix = i / G, o = i - pix * G;
+      const int y = pix / W;
       uint4 m = tmp[i];
       for (int dy = -2; dy <= 2; ++dy) {
         const int yy = y + dy;
-        if (dy != 0 && yy >= 0 && yy < H) max8<kBf16>(m, tmp[yy * W + x]);
+        if (dy != 0 && yy >= 0 && yy < H) max8<kBf16>(m, tmp[i + dy * W * G]);
       }
       nxt[i] = m;
-      *reinterpret_cast<uint4*>(dst + static_cast<long long>(i) * out_cs + level * C) = m;
+      *reinterpret_cast<uint4*>(dst + static_cast<long long>(pix) * out_cs + level * C + o * 8) = m;
     }
     __syncthreads();
     uint4* t = cur;
@@ -148,7 +157,12 @@ int validate_pool_or_upsample(const yb_op_desc& d) {
 }
 
 int spp_pool_launch(const yb_op_desc& d, cudaStream_t stream) {
-  const size_t plane_smem = static_cast<size_t>(d.H) * d.W * 16 * 3;
+  // channel octets per CTA: as many (8, 4, 2, 1) as divide the octet count and fit 3 buffers in shared memory
+  static int g_max = 0;     // TEMPORARY A/B knob (removed once measured)
+  if (g_max == 0) { const char* e = getenv("YB_POOL_G"); g_max = e ? atoi(e) : 2; if (g_max < 1) g_max = 1; }
+  int G = g_max;
+  while (G > 1 && (((d.Cin >> 3) % G) != 0 || static_cast<size_t>(d.H) * d.W * 16 * 3 * G > 200 * 1024)) G >>= 1;
+  const size_t plane_smem = static_cast<size_t>(d.H) * d.W * 16 * 3 * G;
   if (plane_smem <= 200 * 1024) {
     static size_t configured[2] = {48 * 1024, 48 * 1024};
     const int bf = d.dtype == YB_BF16 ? 1 : 0;
@@ -161,13 +175,14 @@ int spp_pool_launch(const yb_op_desc& d, cudaStream_t stream) {
                                            static_cast<int>(plane_smem)));
       configured[bf] = plane_smem;
     }
-    const unsigned blocks = static_cast<unsigned>(d.N) * (d.Cin >> 3);
+    const unsigned blocks = static_cast<unsigned>(d.N) * ((d.Cin >> 3) / G);
+    const int threads = G >= 4 ? 512 : 256;
     if (bf)
-      spp_pool_cascade_kernel<true><<<blocks, 256, plane_smem, stream>>>(
-          static_cast<const uint16_t*>(d.in), d.in_cstride, static_cast<uint16_t*>(d.out), d.out_cstride, d.H, d.W, d.Cin);
+      spp_pool_cascade_kernel<true><<<blocks, threads, plane_smem, stream>>>(
+          static_cast<const uint16_t*>(d.in), d.in_cstride, static_cast<uint16_t*>(d.out), d.out_cstride, d.H, d.W, d.Cin, G);
     else
-      spp_pool_cascade_kernel<false><<<blocks, 256, plane_smem, stream>>>(
-          static_cast<const uint16_t*>(d.in), d.in_cstride, static_cast<uint16_t*>(d.out), d.out_cstride, d.H, d.W, d.Cin);
+      spp_pool_cascade_kernel<false><<<blocks, threads, plane_smem, stream>>>(
+          static_cast<const uint16_t*>(d.in), d.in_cstride, static_cast<uint16_t*>(d.out), d.out_cstride, d.H, d.W, d.Cin, G);
     YB_CHECK_CUDA(cudaGetLastError());
     return YB_OK;
   }
