@@ -34,6 +34,22 @@
 
 namespace yb {
 
+#ifdef YB_EPI_TIMING
+// Instrumented build (make variant EXTRA=-DYB_EPI_TIMING, scripts/epi_timing.py): clock64 totals of the epilogue phases of
+// CTA 0 / group 0 / thread 0, accumulated over the tiles of one launch.  Never part of the shipped library.
+__device__ unsigned long long g_epi_ticks[16];
+#define YB_EPI_TICK(slot)                                                     \
+  do {                                                                        \
+    if (blockIdx.x == 0 && gtid == 0 && g == 0) {                             \
+      const long long t_now_ = clock64();                                     \
+      g_epi_ticks[slot] += static_cast<unsigned long long>(t_now_ - t_prev_); \
+      t_prev_ = t_now_;                                                       \
+    }                                                                         \
+  } while (0)
+#else
+#define YB_EPI_TICK(slot) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kBlockM = 128;
@@ -91,6 +107,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_w2,
                  const __grid_constant__ CUtensorMap tmap_out2, const ConvKernelParams p) {
   constexpr bool kChain = kStore2 != 0;
+  // -DYB_STORE_WARP (A/B build only): stores issued by the otherwise idle warp 2 instead of a thread of the epilogue
+  // group, so that the group's threads neither meet at a named barrier per box nor wait for the issuing thread (clock64
+  // profile of the 1x1 layers, CTA 0 / group 0: store issue 11-17 %, barrier 7-10 %, store-read wait 5 % of the group's
+  // time).  Measured on B200: 1.317 ms per yolov5s plan against 1.311 ms with the in-group issue -- those slices were not
+  // on the kernels' critical path -- so the shipped kernels keep the in-group issue and carry none of this.
+#ifdef YB_STORE_WARP
+  constexpr bool kStoreWarp = !kChain && !kDecode;
+#else
+  constexpr bool kStoreWarp = false;
+#endif
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -102,6 +128,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __shared__ __align__(8) uint64_t a2_full[kEpiGroups];     // chain: the tile's output boxes are in shared memory
   __shared__ __align__(8) uint64_t acc2_full[kEpiGroups];   // chain: the tail's accumulator is complete
   __shared__ __align__(8) uint64_t w2_full;
+  // store warp (warp 2): box_ready[g][b] = the group's box in staging buffer b is written and fenced; buf_free[g][b] = the
+  // TMA store that read it has finished with the buffer
+  __shared__ __align__(8) uint64_t box_ready[kEpiGroups][2];
+  __shared__ __align__(8) uint64_t buf_free[kEpiGroups][2];
   __shared__ __align__(16) float s_bias2[kChain ? kEpiGroups : 1][kChain ? kMaxBlockN : 4];
 
   // Swizzled tiles need 1024-byte alignment.
@@ -134,6 +164,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&acc2_full[g], 1);
     }
     mbar_init(&w2_full, 1);
+    for (int g = 0; g < kEpiGroups; ++g)
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&box_ready[g][b], 4);   // one arrival per epilogue warp
+        mbar_init(&buf_free[g][b], 1);
+      }
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -325,7 +360,42 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (pend >= 0) issue_tail(pend);
       }
     }
-  } else if (warp >= kFirstEpiWarp) {   // (warp 2 has no role: it must not touch the groups' bias rows / named barriers)
+  } else if (warp == 2) {
+    // ===================== store warp =====================
+    if constexpr (kStoreWarp) {
+      if (YB_ROLE_LANES(lane)) {
+        const int store_cols = kStoreCols != 0 ? kStoreCols : p.store_cols;
+        int lt = 0;
+        int cnt[kEpiGroups] = {0, 0};          // boxes stored so far per group
+        int pend_g = -1, pend_b = 0;           // the store issued last: its buffer is released one store later
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
+          const int g = lt & 1;
+          const int m_tile = tile / p.n_tiles;
+          const int n0 = (tile - m_tile * p.n_tiles) * p.block_n;
+          const int m0 = m_tile * kBlockM;
+          for (int c0 = 0; c0 < p.block_n; c0 += store_cols) {
+            const int b = cnt[g] & 1;
+            mbar_wait(&box_ready[g][b], (cnt[g] >> 1) & 1);
+            if (lane == 0) {   // bulk async-groups are per thread: the same lane issues and waits
+              if (n0 + c0 < p.ep.Cout) tma_store_2d(&tmap_out, staging + (static_cast<size_t>(g) * 2 + b) * kStageBufBytes, n0 + c0, m0);
+              tma_store_commit();
+              if (pend_g >= 0) {               // every store but the one just issued has finished reading shared memory
+                tma_store_wait_read<1>();
+                mbar_arrive(&buf_free[pend_g][pend_b]);
+              }
+            }
+            pend_g = g;
+            pend_b = b;
+            ++cnt[g];
+          }
+        }
+        if (lane == 0) {
+          tma_store_wait_all<0>();             // the kernel must not end with stores in flight
+          if (pend_g >= 0) mbar_arrive(&buf_free[pend_g][pend_b]);
+        }
+      }
+    }
+  } else if (warp >= kFirstEpiWarp) {
     // ===================== epilogue groups =====================
     const int g = (warp - kFirstEpiWarp) >> 2;   // group == accumulator stage it drains
     const int q = warp & 3;          // TMEM lane quarter this warp may access
@@ -354,8 +424,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int i = gtid; i < p.block_n; i += 128) bias_s[i] = (n0f + i < p.bias_len) ? __ldg(p.bias + n0f + i) : 0.f;
       named_bar_sync(bar_id, 128);
     }
+#ifdef YB_EPI_TIMING
+    long long t_prev_ = clock64();
+#endif
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
       if ((lt & 1) != g) continue;
+      YB_EPI_TICK(0);   // loop overhead / previous tile's tail
       const int as = lt % p.acc_stages;
       const uint32_t aph = (lt / p.acc_stages) & 1;
       const int m_tile = tile / p.n_tiles;
@@ -380,8 +454,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (issuer) tma_store_wait_read<0>();
       }
       if (kChain || !fixed_n) named_bar_sync(bar_id, 128);
+      YB_EPI_TICK(1);   // tile set-up
       mbar_wait(&acc_full[as], aph);
       tc_fence_after();
+      YB_EPI_TICK(2);   // waiting for the accumulator
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * p.acc_stride;
       if constexpr (kDecode) {
         // ---- fused post-processing front end (yolort/models/box_head.py:328-360,418) ----
@@ -491,9 +567,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // store has finished reading its buffer, which is the one the next box will overwrite.
         uint8_t* buf = my_staging + (kChain ? ((c0 / store_cols) & 1) : (store_idx & 1)) * kStageBufBytes;
         uint8_t* my_row = buf + row_in_tile * row_bytes;
+        if constexpr (kStoreWarp) {   // the store that read this buffer two boxes ago has released it
+          mbar_wait(&buf_free[g][store_idx & 1], ((store_idx >> 1) & 1) ^ 1);
+        }
         if (!YB_DBG(p, 1)) {
           epilogue_box_select<kBf16, kStoreCols, kRareAct, kRes>(p.ep, store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
         }
+        YB_EPI_TICK(3);   // TMEM load + bias/activation(/shortcut) + swizzled shared-memory writes of one box
         if (c0 + store_cols >= p.block_n) {
           // all TMEM reads of this tile are done: hand the accumulator stage back to the MMA warp
           tc_fence_before();
@@ -501,14 +581,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
         fence_proxy_async_smem();
+        YB_EPI_TICK(4);   // fences
+        if constexpr (kStoreWarp) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&box_ready[g][store_idx & 1]);   // warp 2 issues the store
+          YB_EPI_TICK(7);
+          continue;
+        }
         if constexpr (!kChain) {
           if (issuer) tma_store_wait_read<0>();
         }
+        YB_EPI_TICK(5);   // previous store's shared-memory read
         named_bar_sync(bar_id, 128);
+        YB_EPI_TICK(6);   // group barrier
         if (issuer) {
           if ((!kChain || p.ch.store_first) && n0 + c0 < p.ep.Cout && !YB_DBG(p, 5)) tma_store_2d(&tmap_out, buf, n0 + c0, m0);
           tma_store_commit();
         }
+        YB_EPI_TICK(7);   // store issue
       }
       if constexpr (kChain) {
         // every box of the tile is in shared memory, visible to the async proxy (fence + barrier above), and every
@@ -946,3 +1036,16 @@ void conv_op_destroy(ConvOp* op) {
 }
 
 }  // namespace yb
+
+#ifdef YB_EPI_TIMING
+extern "C" int yb_debug_epi_ticks(unsigned long long* out16, int reset) {
+  if (out16) {
+    if (cudaMemcpyFromSymbol(out16, yb::g_epi_ticks, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+  }
+  if (reset) {
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(yb::g_epi_ticks, z, sizeof(z)) != cudaSuccess) return -1;
+  }
+  return 0;
+}
+#endif

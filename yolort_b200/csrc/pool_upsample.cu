@@ -7,8 +7,6 @@
 //    produces all three (nested windows), 8 channels (16 bytes) per thread.
 //  * nearest-neighbour 2x upsample (nn.Upsample(scale_factor=2), path_aggregation_network.py:123,134),
 //    writing into a channel window of the next concat buffer.
-#include <cstdlib>
-
 #include "common.cuh"
 #include "conv_sm100.h"
 
@@ -71,9 +69,7 @@ __global__ void spp_pool_kernel(const uint16_t* __restrict__ in, int in_cs, uint
 // SPPF-style cascade in shared memory: mp9 = mp5(mp5(x)), mp13 = mp5(mp9) (exactly equal to the direct
 // windows with -inf padding, yolort/v5/models/common.py:196).  One CTA owns the H x W planes of G adjacent channel
 // octets of one image: 3 buffers of H*W*G 16-byte items [pixel][octet] in shared memory, separable 5-tap max (rows then
-// columns).  G octets = 16 G contiguous bytes per pixel in global memory: with G = 8 a warp's load / store instruction
-// covers four whole 128-byte lines, where the one-octet-per-CTA version touched 32 lines for 16 bytes each (the pixel
-// stride of the concat buffer is 2 KB) -- 20.6 us for 26 MB of traffic on B200, bound by those wavefronts.
+// columns).  G octets = 16 G contiguous bytes per pixel in global memory (whole 32-byte sectors from G = 2).
 template <bool kBf16>
 __global__ void spp_pool_cascade_kernel(const uint16_t* __restrict__ in, int in_cs, uint16_t* __restrict__ out,
                                         int out_cs, int H, int W, int C, int G) {
@@ -158,9 +154,9 @@ int validate_pool_or_upsample(const yb_op_desc& d) {
 
 int spp_pool_launch(const yb_op_desc& d, cudaStream_t stream) {
   // channel octets per CTA: as many (8, 4, 2, 1) as divide the octet count and fit 3 buffers in shared memory
-  static int g_max = 0;     // TEMPORARY A/B knob (removed once measured)
-  if (g_max == 0) { const char* e = getenv("YB_POOL_G"); g_max = e ? atoi(e) : 2; if (g_max < 1) g_max = 1; }
-  int G = g_max;
+  // (measured on B200, 256 channels at 20 x 20, batch 32: G = 1 / 2 / 4 all 22.5 us, G = 8 24.6 us -- the kernel is bound by
+  // its seven barrier-separated passes per CTA, not by the lines a load touches; two octets keep loads at whole sectors)
+  int G = 2;
   while (G > 1 && (((d.Cin >> 3) % G) != 0 || static_cast<size_t>(d.H) * d.W * 16 * 3 * G > 200 * 1024)) G >>= 1;
   const size_t plane_smem = static_cast<size_t>(d.H) * d.W * 16 * 3 * G;
   if (plane_smem <= 200 * 1024) {
