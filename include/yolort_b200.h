@@ -158,7 +158,9 @@ typedef struct {
                                    halo-patch kernel's stride-2 parity-plane variant whatever the channel counts (tests);
                                    bit 3: do not split N over CTAs with resident weights (A/B timing, tests);
                                    bit 4: four TMEM accumulator stages instead of two where they fit (measured equal or slower on
-                                   B200: 1.315 vs 1.312 ms per yolov5s plan; opt-in for A/B timing) */
+                                   B200: 1.315 vs 1.312 ms per yolov5s plan; opt-in for A/B timing);
+                                   bit 5: four epilogue groups (608 threads) where that kernel variant applies (measured slower
+                                   than two on B200; opt-in for A/B timing and tests) */
   const yb_head_decode* decode; /* optional (host pointer, copied at plan creation): fused decode epilogue */
   const yb_conv_chain* chain;   /* optional (host pointer, copied at plan creation): chained pointwise tail  */
 } yb_op_desc;

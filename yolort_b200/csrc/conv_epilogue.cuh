@@ -115,10 +115,12 @@ __device__ __noinline__ void epilogue_batch_exact(int act, int Cout, const void*
 // kRes: the layer adds a residual (Bottleneck shortcut).  Those take the fp32 tail: SiLU(v) and the shortcut can cancel
 // (|sum| << |SiLU(v)|), and a SiLU value already rounded to fp16 then carries an error that is large against the
 // 2^-9 (1 + |ref|) bound of the SUM (tests/test_gpu_conv.py, random shortcuts: 2 violations in 338 k with the packed tail).
-template <bool kBf16, int kCols, bool kRareAct = false, bool kRes = true>
+// kBatchMax: columns whose TMEM / shortcut loads are in flight together (32; 16 for the four-group kernel variant, whose
+// threads live in 104 registers).
+template <bool kBf16, int kCols, bool kRareAct = false, bool kRes = true, int kBatchMax = 32>
 __device__ __forceinline__ void epilogue_box(const EpilogueParams& p, uint32_t taddr, const float* __restrict__ s_bias,
                                              long long row, bool row_ok, int col0, uint8_t* my_row, int row_in_tile) {
-  constexpr int kBatch = kCols < 32 ? kCols : 32;
+  constexpr int kBatch = kCols < kBatchMax ? kCols : kBatchMax;
   constexpr int kChunks = kBatch / 16;
   constexpr int kRowBytes = kCols * 2;
   const bool has_res = kRes && p.residual != nullptr && row_ok;
@@ -287,12 +289,12 @@ __device__ __forceinline__ void epilogue_box_dispatch(const EpilogueParams& p, i
 // path uses is its own kernel with exactly ONE epilogue copy inlined: with all copies inlined in one kernel and
 // selected at run time, adding the r3.1 activations cost the r6.0 plan 5-13% (measured A/B on the same box,
 // 1.85 -> 1.95 / 2.10 ms); kStoreCols == 0 keeps the run-time selection for the rarely used variants.
-template <bool kBf16, int kStoreCols, bool kRareAct, bool kRes = true>
+template <bool kBf16, int kStoreCols, bool kRareAct, bool kRes = true, int kBatchMax = 32>
 __device__ __forceinline__ void epilogue_box_select(const EpilogueParams& p, int store_cols, uint32_t taddr,
                                                     const float* s_bias, long long row, bool row_ok, int col0,
                                                     uint8_t* my_row, int row_in_tile) {
   if constexpr (kStoreCols != 0)
-    epilogue_box<kBf16, kStoreCols, kRareAct, kRes>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
+    epilogue_box<kBf16, kStoreCols, kRareAct, kRes, kBatchMax>(p, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
   else
     epilogue_box_dispatch<kBf16, kRareAct, kRes>(p, store_cols, taddr, s_bias, row, row_ok, col0, my_row, row_in_tile);
 }

@@ -54,10 +54,12 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kMaxStages = 12;
-constexpr int kEpiGroups = 2;
+constexpr int kEpiGroups = 2;                         // epilogue groups of the standard variants
+constexpr int kMaxGroups = 4;                         // ... of the wide variant (kGroups template parameter)
 constexpr int kMaxAccStages = 4;
 constexpr int kFirstEpiWarp = 3;                     // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warp 2: idle
 constexpr int kThreads = 32 * kFirstEpiWarp + kEpiGroups * 128;
+constexpr int kThreadsWide = 32 * kFirstEpiWarp + kMaxGroups * 128;   // 608: 104 registers per thread
 constexpr int kStageBufBytes = 128 * 128;  // 128 rows x (up to) 64 columns x 2 B
 constexpr int kMaxBlockN = 256;
 constexpr size_t kSmemBudget = 222 * 1024;  // dynamic shared memory per CTA (227 KB limit minus static)
@@ -78,6 +80,7 @@ struct ConvKernelParams {
   int dbg;         // ablation knobs, -DYB_ABLATION builds only (common.cuh)
   uint32_t a_stage_bytes, b_stage_bytes, tmem_cols, idesc;
   int acc_stride;  // TMEM columns between accumulator stages (= block_n)
+  int epi_groups;  // 2, or 4 for the wide variant (host-side: selects the kernel and the block size)
   int acc_stages;  // 2 or 4 accumulator stages: with 4, each epilogue group owns two and the MMAs of its next tile have
                    // completed by the time it has stored the current one (with 2 the group waited out MMA + commit latency
                    // at the start of every tile)
@@ -101,8 +104,11 @@ __device__ __forceinline__ void issue_group(int cnt, bool first_group, uint32_t 
 
 // kRes: the layer adds a shortcut (fp32 epilogue tail, conv_epilogue.cuh).  kStore2 != 0: a pointwise tail is chained
 // onto every tile (conv_chain.cuh), its output stored in boxes of kStore2 columns.
-template <bool kBf16, int kStoreCols, bool kRareAct, bool kDecode, bool kRes = true, int kStore2 = 0>
-__global__ void __launch_bounds__(kThreads, 1)
+// kGroups = 4 ("wide" variant, opt-in): four epilogue groups of four warps, each owning one accumulator stage and two
+// staging buffers, 608 threads at <= 104 registers (TMEM / shortcut loads batched 16 columns at a time).  Built to test
+// whether the shallow layers are bound by the latency chain of their epilogue; they are not (see conv_configure).
+template <bool kBf16, int kStoreCols, bool kRareAct, bool kDecode, bool kRes = true, int kStore2 = 0, int kGroups = kEpiGroups>
+__global__ void __launch_bounds__(32 * kFirstEpiWarp + kGroups * 128, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_w2,
                  const __grid_constant__ CUtensorMap tmap_out2, const ConvKernelParams p) {
@@ -113,7 +119,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // time).  Measured on B200: 1.317 ms per yolov5s plan against 1.311 ms with the in-group issue -- those slices were not
   // on the kernels' critical path -- so the shipped kernels keep the in-group issue and carry none of this.
 #ifdef YB_STORE_WARP
-  constexpr bool kStoreWarp = !kChain && !kDecode;
+  constexpr bool kStoreWarp = !kChain && !kDecode && kGroups == kEpiGroups;
 #else
   constexpr bool kStoreWarp = false;
 #endif
@@ -124,7 +130,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __shared__ __align__(8) uint64_t acc_empty[kMaxAccStages];
   __shared__ __align__(8) uint64_t b_full;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(16) float s_bias[kEpiGroups][kMaxBlockN];
+  __shared__ __align__(16) float s_bias[kGroups][kGroups == kEpiGroups ? kMaxBlockN : 128];   // wide variant: N tile <= 128
   __shared__ __align__(8) uint64_t a2_full[kEpiGroups];     // chain: the tile's output boxes are in shared memory
   __shared__ __align__(8) uint64_t acc2_full[kEpiGroups];   // chain: the tail's accumulator is complete
   __shared__ __align__(8) uint64_t w2_full;
@@ -141,7 +147,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t stage_bytes = p.kpg * (p.a_stage_bytes + (p.b_resident ? 0u : p.b_stage_bytes));
   uint8_t* b_res = tiles + static_cast<size_t>(p.stages) * stage_bytes;   // resident weights (optional)
   uint8_t* staging = b_res + p.b_res_bytes;                                // [kEpiGroups][2][kStageBufBytes]
-  uint8_t* w2_res = staging + kEpiGroups * 2 * kStageBufBytes;             // chain: resident tail weights
+  uint8_t* w2_res = staging + kGroups * 2 * kStageBufBytes;                // chain: resident tail weights
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -353,7 +359,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (YB_ELECT()) umma_commit(&acc_full[as]);  // accumulator of this tile complete
         if constexpr (kChain) {
           if (pend >= 0) issue_tail(pend);
-          pend = lt & 1;   // the group that drains this tile
+          pend = lt & 1;   // the group that drains this tile (chained kernels run two groups)
         }
       }
       if constexpr (kChain) {
@@ -397,7 +403,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp >= kFirstEpiWarp) {
     // ===================== epilogue groups =====================
-    const int g = (warp - kFirstEpiWarp) >> 2;   // group == accumulator stage it drains
+    const int g = (warp - kFirstEpiWarp) >> 2;   // epilogue group (two groups: drains stages g, g + 2; four: stage g)
     const int q = warp & 3;          // TMEM lane quarter this warp may access
     const int gtid = threadIdx.x - 32 * kFirstEpiWarp - g * 128;
     const int row_in_tile = q * 32 + lane;
@@ -428,7 +434,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     long long t_prev_ = clock64();
 #endif
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++lt) {
-      if ((lt & 1) != g) continue;
+      if ((lt % kGroups) != g) continue;
       YB_EPI_TICK(0);   // loop overhead / previous tile's tail
       const int as = lt % p.acc_stages;
       const uint32_t aph = (lt / p.acc_stages) & 1;
@@ -571,7 +577,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&buf_free[g][store_idx & 1], ((store_idx >> 1) & 1) ^ 1);
         }
         if (!YB_DBG(p, 1)) {
-          epilogue_box_select<kBf16, kStoreCols, kRareAct, kRes>(p.ep, store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
+          epilogue_box_select<kBf16, kStoreCols, kRareAct, kRes, kGroups == kEpiGroups ? 32 : 16>(p.ep, store_cols, taddr + c0, bias_s + c0, row, row_ok, n0 + c0, my_row, row_in_tile);
         }
         YB_EPI_TICK(3);   // TMEM load + bias/activation(/shortcut) + swizzled shared-memory writes of one box
         if (c0 + store_cols >= p.block_n) {
@@ -695,6 +701,9 @@ ConvKernelFn select_conv_kernel_t(const ConvKernelParams& kp) {
     if (res) return s2 == 64 ? conv_umma_kernel<kBf16, 64, false, false, true, 64> : conv_umma_kernel<kBf16, 64, false, false, true, 32>;
     return s2 == 64 ? conv_umma_kernel<kBf16, 64, false, false, kResAlways, 64> : conv_umma_kernel<kBf16, 64, false, false, kResAlways, 32>;
   }
+  if (kp.epi_groups == kMaxGroups)   // conv_configure admits only 64-column boxes here
+    return res ? conv_umma_kernel<kBf16, 64, false, false, true, 0, kMaxGroups>
+               : conv_umma_kernel<kBf16, 64, false, false, kResAlways, 0, kMaxGroups>;
   if (res) {
     switch (kp.store_cols) {
       case 64: return conv_umma_kernel<kBf16, 64, false, false, true>;
@@ -823,7 +832,17 @@ static int conv_configure(const yb_op_desc& d, ConvKernelParams& kp, dim3& grid,
                kp.acc2_base, 2 * kp.ch.n2);
     chain_bytes = static_cast<size_t>(kp.ch.w2_chunks) * kp.ch.w2_sub_bytes;
   }
-  const size_t fixed = static_cast<size_t>(kEpiGroups) * 2 * kStageBufBytes + 1024 + chain_bytes;
+  // Wide variant (four epilogue groups, see the kernel's header), opt-in through reserved bit 5: plain SiLU / linear
+  // layers with 64-column store boxes, an N tile of at most 128 columns and at least four tiles per CTA; it needs 128 KB
+  // of staging, so it is dropped again below if fewer than three pipeline stages would be left.  Measured on B200
+  // (yolov5s batch 32, every convolution its own launch): 1.333 ms per plan with it, 1.327 ms without -- the 1x1 layers at
+  // 160 x 160 / 80 x 80 already move 4.9 TB/s of mixed read + write traffic, which is what this part sustains.
+  const int grid_x = kp.num_tiles < sms ? kp.num_tiles : sms;
+  bool wide = d.chain == nullptr && !kp.decode_on && d.act < YB_ACT_HARDSWISH && kp.store_cols == 64 && kp.block_n <= 128 &&
+              kp.num_tiles >= 4 * grid_x && (d.reserved & 32);
+retry_groups:
+  kp.epi_groups = wide ? kMaxGroups : kEpiGroups;
+  const size_t fixed = static_cast<size_t>(kp.epi_groups) * 2 * kStageBufBytes + 1024 + chain_bytes;
   // Weights stay resident in shared memory when the layer has a single N tile and they are small:
   // the persistent CTA then streams only activations (halves the L2->SM traffic of the shallow layers).
   const size_t b_total = static_cast<size_t>(kp.num_k_iters) * kp.b_stage_bytes;
@@ -842,8 +861,13 @@ static int conv_configure(const yb_op_desc& d, ConvKernelParams& kp, dim3& grid,
   const uint32_t stage_bytes = kp.kpg * per_iter;
   int stages = static_cast<int>((kSmemBudget - fixed - kp.b_res_bytes) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
+  if (wide && stages < 3) {
+    wide = false;
+    goto retry_groups;
+  }
   if (stages < 2) stages = 2;
   kp.stages = stages;
+  if (wide) kp.acc_stages = 4;
   if (!kp.ch.on && 4 * kp.acc_stride <= 512 && (d.reserved & 16)) kp.acc_stages = 4;   // reserved bit 4: four stages (measured equal or slower: opt-in)
   kp.tmem_cols = pow2_cols(kp.acc_stages * kp.acc_stride + (kp.ch.on ? 2 * kp.ch.n2 : 0));
   kp.ep.is_bf16 = d.dtype == YB_BF16;
@@ -877,7 +901,7 @@ int conv_configure_check(const yb_op_desc& d, int* info) {
     info[5] = kp.stages;
     info[6] = kp.kpg;
     info[7] = kp.store_cols;
-    info[8] = 2;
+    info[8] = kp.epi_groups;      // (im2col / 1x1 kernel: epilogue groups; each has two staging buffers)
     info[9] = static_cast<int>(smem);
     info[10] = static_cast<int>(grid.x);
     info[11] = kp.ch.on;
@@ -1018,7 +1042,7 @@ int conv_op_launch(const ConvOp* op, cudaStream_t stream) {
   if (op->patch) return patch_conv_launch(op->patch, stream);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = op->grid;
-  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.blockDim = dim3(op->kp.epi_groups == kMaxGroups ? kThreadsWide : kThreads, 1, 1);
   cfg.dynamicSmemBytes = op->smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];

@@ -555,6 +555,7 @@ class PlanInstance:
         self._chains: List[_C.ConvChain] = []    # yb_conv_chain blocks the descriptors point at (kept alive)
         no_nsplit = os.environ.get("YB_NO_NSPLIT", "0") == "1"    # A/B timing: keep streamed weights + tile pairs
         acc2 = os.environ.get("YB_ACC4", "0") == "1"              # A/B timing: four accumulator stages instead of two
+        no_wide = os.environ.get("YB_WIDE", "0") == "1"           # A/B timing: four epilogue groups where they apply
 
         def make_desc(op: _Op, ptr) -> "_C.OpDesc":
             d = _C.OpDesc()
@@ -575,7 +576,7 @@ class PlanInstance:
                 d.Cout_pad, _, d.Cin_pad = op.weight.shape
                 if op.band:
                     d.Cin_pad = 64     # [Cout_pad, 3, 2 x 64] banded stem matrix: one 64-channel chunk of super-pixels
-            d.reserved = (1 if op.force_im2col else 0) | (2 if op.band else 0) | (8 if no_nsplit else 0) | (16 if acc2 else 0)
+            d.reserved = (1 if op.force_im2col else 0) | (2 if op.band else 0) | (8 if no_nsplit else 0) | (16 if acc2 else 0) | (32 if no_wide else 0)
             if op.residual is not None:
                 d.residual, d.res_cstride = ptr(op.residual), op.residual.buf.C
             return d
