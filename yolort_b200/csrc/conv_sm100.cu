@@ -22,8 +22,13 @@
 //                -> swizzled shared-memory staging -> TMA store into the NHWC destination view (a
 //                channel window of a concat buffer is just a strided tensor map; ragged M is clipped
 //                by the TMA unit).
-// The kernel is a template over (dtype, store-box width, activation family, fused decode): every variant the hot
-// path launches carries exactly one inlined epilogue (conv_epilogue.cuh, select_conv_kernel below).
+// The kernel is a template over (dtype, store-box width, activation family, fused decode, shortcut, chained tail):
+// every variant the hot path launches carries exactly one inlined epilogue per output (conv_epilogue.cuh,
+// select_conv_kernel below).  A chained tail (conv_chain.cuh) is a second, pointwise GEMM over the tile the epilogue has
+// just staged: the MMA warp issues it into a tail accumulator of the same epilogue group and a second epilogue pass stores
+// it.  Opt-in build / descriptor variants kept for A/B timing and measured equal or slower (profiles/r02_ab_variants.txt):
+// four accumulator stages, four epilogue groups (kGroups), a store warp (-DYB_STORE_WARP), clock64 instrumentation
+// of the epilogue (-DYB_EPI_TIMING).
 #include <cstdlib>
 
 #include "common.cuh"

@@ -7,19 +7,23 @@
 //   torchvision.ops.batched_nms :422 (coordinate-offset trick or per-class, by numel) ; keep[:max_det]
 // and YOLOTransform.postprocess / scale_coords (yolort/models/transform.py:332-367).
 //
-// Two kernels per batch, no host round trip:
-//   1. decode_candidates_kernel -- one thread per anchor.  Reads the objectness logit first; an anchor
-//      whose sigmoid(obj) <= thr cannot produce a candidate (cls < 1), so most threads touch one 32-byte
-//      sector.  Survivors decode the box once (fp32, unfused ops in the reference's order), write it to a
-//      dense per-anchor array and append one 64-bit sort key per (anchor, class) over threshold:
+// Two kernels per batch (plus a counter reset), no host round trip:
+//   1. decode.  decode_rows_kernel for the plan's NHWC head buffers (one 512-byte row per pixel): a warp copies the
+//      rows of its 32 pixels into shared memory, lane = pixel tests the objectness of its anchors (an anchor whose
+//      sigmoid(obj) <= thr cannot produce a candidate: cls < 1), the (pixel, anchor) pairs that passed are compacted
+//      across the warp and lane q scans the classes of pair q; decode_candidates_kernel (one thread per anchor) for any
+//      other layout (the reference's [N,A,H,W,K], fp32 logits).  Survivors decode the box once (fp32, unfused ops in the
+//      reference's order), write it to a dense per-anchor array and append one 64-bit sort key per (anchor, class) over
+//      threshold:
 //          key = ~orderable(score) << 32 | (anchor * nc + class)
 //      so ascending key order == score descending, ties in row-major candidate order (what a stable
 //      sort of the reference's candidate list gives).
-//   2. nms_image_kernel -- one 1024-thread CTA per image: sorts the image's keys (bitonic network in
-//      shared memory up to 4096 keys, in-CTA LSD radix sort through global memory above that), then the
-//      greedy sweep: candidates are consumed 1024 at a time; each thread tests its candidate against the
-//      kept list (<= max_det boxes in shared memory), then survivors are resolved in order with warp
-//      ballots.  The sweep stops at max_det keeps, exactly like keep[:detections_per_img].
+//   2. nms_image_kernel -- one 512-thread CTA per image: sorts the image's keys (bitonic network on keys held in
+//      registers, up to 4096; in-CTA LSD radix sort through global memory above that), then the greedy sweep:
+//      candidates are consumed 512 at a time; each thread tests its candidate against the kept list (<= max_det boxes
+//      in shared memory), the survivors' suppression bit-matrix is built with the (row, word) pairs dealt out evenly,
+//      and they are resolved in order 32 at a time from registers.  The sweep stops at max_det keeps, exactly like
+//      keep[:detections_per_img].
 // IoU arithmetic mirrors torchvision's CPU nms kernel in fp32 with explicit non-fused operations so the
 // keep set is bit-identical on identical inputs.
 #include <climits>
