@@ -172,7 +172,8 @@ int yb_conv_chain_supported(const yb_op_desc* op);
 /* Host-only introspection of how a convolution would be launched (tests, tuning): fills 12 ints
  *   [0] 1 = halo-patch kernel, 0 = im2col / 1x1 kernel   [1] N-tile width   [2] N tiles   [3] weights resident in
  *   shared memory   [4] M tiles per weight pass   [5] patch slots (pipeline stages)   [6] weight-ring slabs (k-iterations
- *   per stage)   [7] store-box columns   [8] staging buffers per epilogue group   [9] dynamic shared memory   [10] grid
+ *   per stage)   [7] store-box columns   [8] staging buffers per epilogue group (halo-patch kernel) / epilogue groups
+ *   (1x1 / im2col kernel)   [9] dynamic shared memory   [10] grid
  *   [11] chained tail fused.  Pure host logic. */
 int yb_conv_config(const yb_op_desc* op, int32_t* info12);
 

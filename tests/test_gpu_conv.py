@@ -40,7 +40,7 @@ def run_conv(N, H, W, Cin, Cout, k, s, p, dtype=torch.float16, act=True, residua
         d.residual, d.res_cstride = res.data_ptr(), Cout
     d.reserved = (1 if force_im2col else 0) | (4 if force_planes else 0) | (32 if wide else 0)
     if wide:
-        assert _C.conv_config(d)["store_bufs"] == 4      # (for the 1x1 kernel this field is the number of epilogue groups)
+        assert _C.conv_config(d)["epilogue_groups"] == 4
     plan = _C.Plan([d], DEV)
     plan.run()
     torch.cuda.synchronize()

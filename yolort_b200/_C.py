@@ -344,7 +344,10 @@ def conv_config(op: "OpDesc") -> dict:
     check(lib().yb_conv_config(ctypes.byref(op), info), "yb_conv_config")
     keys = ("patch_kernel", "block_n", "n_tiles", "weights_resident", "tiles_per_pass", "slots", "ring", "store_cols",
             "store_bufs", "smem_bytes", "grid", "chained")
-    return dict(zip(keys, [int(v) for v in info]))
+    cfg = dict(zip(keys, [int(v) for v in info]))
+    if not cfg["patch_kernel"]:     # slot 8 of the 1x1 / im2col kernel: epilogue groups (two staging buffers each)
+        cfg["epilogue_groups"] = cfg.pop("store_bufs")
+    return cfg
 
 
 class Plan:

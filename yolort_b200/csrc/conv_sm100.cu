@@ -845,31 +845,44 @@ static int conv_configure(const yb_op_desc& d, ConvKernelParams& kp, dim3& grid,
   const int grid_x = kp.num_tiles < sms ? kp.num_tiles : sms;
   bool wide = d.chain == nullptr && !kp.decode_on && d.act < YB_ACT_HARDSWISH && kp.store_cols == 64 && kp.block_n <= 128 &&
               kp.num_tiles >= 4 * grid_x && (d.reserved & 32);
-retry_groups:
-  kp.epi_groups = wide ? kMaxGroups : kEpiGroups;
-  const size_t fixed = static_cast<size_t>(kp.epi_groups) * 2 * kStageBufBytes + 1024 + chain_bytes;
-  // Weights stay resident in shared memory when the layer has a single N tile and they are small:
-  // the persistent CTA then streams only activations (halves the L2->SM traffic of the shallow layers).
-  const size_t b_total = static_cast<size_t>(kp.num_k_iters) * kp.b_stage_bytes;
-  kp.b_resident = (n_tiles == 1 && b_total <= 80 * 1024) ? 1 : 0;
-  kp.b_res_bytes = kp.b_resident ? static_cast<uint32_t>(b_total) : 0u;
-  // k-iterations per pipeline stage: aim at ~32 KB per stage so that one mbarrier round trip moves
-  // enough bytes (a 16-channel tap is only 4 KB), in near-equal groups.
-  const uint32_t per_iter = kp.a_stage_bytes + (kp.b_resident ? 0u : kp.b_stage_bytes);
-  const size_t avail = kSmemBudget - fixed - kp.b_res_bytes;
-  size_t target = avail / 3 < 32 * 1024 ? avail / 3 : 32 * 1024;   // keep at least three stages in flight
-  int kpg_max = static_cast<int>(target / per_iter);
-  if (kpg_max < 1) kpg_max = 1;
-  if (kpg_max > kp.num_k_iters) kpg_max = kp.num_k_iters;
-  const int groups = (kp.num_k_iters + kpg_max - 1) / kpg_max;
-  kp.kpg = (kp.num_k_iters + groups - 1) / groups;
-  const uint32_t stage_bytes = kp.kpg * per_iter;
-  int stages = static_cast<int>((kSmemBudget - fixed - kp.b_res_bytes) / stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (wide && stages < 3) {
+  // shared-memory pipeline for a given number of epilogue groups (each owns two staging buffers)
+  struct Pipe {
+    size_t fixed;
+    uint32_t stage_bytes;
+    int stages;
+  };
+  auto size_pipeline = [&](int epi_groups) {
+    Pipe pp;
+    pp.fixed = static_cast<size_t>(epi_groups) * 2 * kStageBufBytes + 1024 + chain_bytes;
+    // Weights stay resident in shared memory when the layer has a single N tile and they are small:
+    // the persistent CTA then streams only activations (halves the L2->SM traffic of the shallow layers).
+    const size_t b_total = static_cast<size_t>(kp.num_k_iters) * kp.b_stage_bytes;
+    kp.b_resident = (n_tiles == 1 && b_total <= 80 * 1024) ? 1 : 0;
+    kp.b_res_bytes = kp.b_resident ? static_cast<uint32_t>(b_total) : 0u;
+    // k-iterations per pipeline stage: aim at ~32 KB per stage so that one mbarrier round trip moves
+    // enough bytes (a 16-channel tap is only 4 KB), in near-equal groups.
+    const uint32_t per_iter = kp.a_stage_bytes + (kp.b_resident ? 0u : kp.b_stage_bytes);
+    const size_t avail = kSmemBudget - pp.fixed - kp.b_res_bytes;
+    size_t target = avail / 3 < 32 * 1024 ? avail / 3 : 32 * 1024;   // keep at least three stages in flight
+    int kpg_max = static_cast<int>(target / per_iter);
+    if (kpg_max < 1) kpg_max = 1;
+    if (kpg_max > kp.num_k_iters) kpg_max = kp.num_k_iters;
+    const int groups = (kp.num_k_iters + kpg_max - 1) / kpg_max;
+    kp.kpg = (kp.num_k_iters + groups - 1) / groups;
+    pp.stage_bytes = kp.kpg * per_iter;
+    pp.stages = static_cast<int>(avail / pp.stage_bytes);
+    if (pp.stages > kMaxStages) pp.stages = kMaxStages;
+    return pp;
+  };
+  Pipe pp = size_pipeline(wide ? kMaxGroups : kEpiGroups);
+  if (wide && pp.stages < 3) {   // 128 KB of staging would starve the operand pipeline: back to two groups
     wide = false;
-    goto retry_groups;
+    pp = size_pipeline(kEpiGroups);
   }
+  kp.epi_groups = wide ? kMaxGroups : kEpiGroups;
+  const size_t fixed = pp.fixed;
+  const uint32_t stage_bytes = pp.stage_bytes;
+  int stages = pp.stages;
   if (stages < 2) stages = 2;
   kp.stages = stages;
   if (wide) kp.acc_stages = 4;
