@@ -330,3 +330,66 @@ def test_conv_config_and_chain_support_are_host_logic():
     assert not ok
     ok, _ = chain(_conv_desc(32, 20, 20, 512, 512, 1, 1, 0), 256, 256, 256)                # several N tiles
     assert not ok
+
+
+def test_fused_launch_list_and_arena_liveness_on_cpu(monkeypatch):
+    """Host logic of the plan, without a GPU: which convolutions ride as chained tails (yolov5s: the pointwise chains of
+    the 32 / 64-channel C3 blocks), and the arena invariant that makes liveness reuse safe with fused launches -- every
+    buffer a launch touches (source, destination, shortcut, the tail's second operand and output) is live for the whole
+    launch, and two different buffers that are live at the same time never share a byte."""
+    import torch
+
+    from yolort_b200 import engine
+    from yolort_b200.models import yolov5s
+
+    class _NoPlan:                       # the native plan needs a GPU; everything before it is host logic
+        def __init__(self, descs, device):
+            self.n_ops = len(descs)
+
+    monkeypatch.setattr(_C, "Plan", _NoPlan)
+    m = yolov5s().eval()
+    low = engine.Lowered(m.model, torch.float16, torch.device("cpu"))
+    N, H, W = 4, 640, 640
+    inst = engine.PlanInstance(low, N, H, W)
+    L = low.L
+    fused = [(L.ops[g[0]].name, L.ops[g[1]].name) for g in inst.launch_ops if len(g) == 2]
+    assert len(L.ops) == 55 and len(inst.launch_ops) == 48
+    assert fused == [("body.2.cv1+cv2", "body.2.m.0.cv1"), ("body.2.m.0.cv2", "body.2.cv3"),
+                     ("body.4.cv1+cv2", "body.4.m.0.cv1"), ("body.4.m.0.cv2", "body.4.m.1.cv1"),
+                     ("body.4.m.1.cv2", "body.4.cv3"),
+                     ("pan.layer_blocks.0.cv1+cv2", "pan.layer_blocks.0.m.0.cv1"),
+                     ("pan.layer_blocks.0.m.0.cv2", "pan.layer_blocks.0.cv3")]
+    # byte range of every buffer inside the arena
+    base = inst.arena.data_ptr()
+    rng = {}
+    for b in L.bufs:
+        t = inst.buffers[b.name]
+        lo = t.data_ptr() - base
+        rng[b.name] = (lo, lo + t.numel() * t.element_size())
+        assert 0 <= lo and rng[b.name][1] <= inst.arena.numel()
+    # live interval of every buffer in launch steps: first writer .. last reader (inputs / results stay live)
+    first, last = {}, {}
+    for t, grp in enumerate(inst.launch_ops):
+        for i in grp:
+            op = L.ops[i]
+            for v in (op.src, op.dst, op.residual, op.chain_extra if len(grp) == 2 and i == grp[0] else None):
+                if v is not None:
+                    first.setdefault(v.buf.name, t)
+                    last[v.buf.name] = t
+    keep = {low.x0.name} | {b.name for b in low.head_bufs} | {v.buf.name for v in low.feats.values()}
+    n_steps = len(inst.launch_ops)
+    for k in keep:
+        last[k] = n_steps
+    first[low.x0.name] = -1
+    names = [n for n in rng if n in first]
+    clashes = 0
+    for a in range(len(names)):
+        for b2 in range(a + 1, len(names)):
+            na, nb = names[a], names[b2]
+            overlap_time = first[na] <= last[nb] and first[nb] <= last[na]
+            overlap_bytes = rng[na][0] < rng[nb][1] and rng[nb][0] < rng[na][1]
+            if overlap_time and overlap_bytes:
+                clashes += 1
+                print("CLASH", na, first[na], last[na], rng[na], "|", nb, first[nb], last[nb], rng[nb])
+    assert clashes == 0
+    assert inst.arena_bytes < 0.5 * inst.unshared_bytes        # and the reuse still pays
