@@ -332,6 +332,72 @@ def test_conv_config_and_chain_support_are_host_logic():
     assert not ok
 
 
+def _cpu_plan(monkeypatch, ctor, N, H, W, **kw):
+    import torch
+
+    from yolort_b200 import engine
+
+    class _NoPlan:                       # the native plan needs a GPU; everything before it is host logic
+        def __init__(self, descs, device):
+            self.n_ops = len(descs)
+
+    monkeypatch.setattr(_C, "Plan", _NoPlan)
+    m = ctor(**kw).eval()
+    low = engine.Lowered(m.model, torch.float16, torch.device("cpu"))
+    return low, engine.PlanInstance(low, N, H, W)
+
+
+def _assert_arena_liveness(low, inst):
+    """Two different buffers that are live during the same launch never share a byte of the arena (a fused launch keeps
+    everything both of its convolutions touch live for its whole duration)."""
+    L = low.L
+    assert len({b.name for b in L.bufs}) == len(L.bufs)          # `PlanInstance.buffers` is keyed by name
+    base = inst.arena.data_ptr()
+    rng = {}
+    for b in L.bufs:
+        t = inst.buffers[b.name]
+        lo = t.data_ptr() - base
+        rng[b.name] = (lo, lo + t.numel() * t.element_size())
+        assert 0 <= lo and rng[b.name][1] <= inst.arena.numel()
+    first, last = {}, {}
+    for t, grp in enumerate(inst.launch_ops):
+        for i in grp:
+            op = L.ops[i]
+            for v in (op.src, op.dst, op.residual, op.chain_extra if len(grp) == 2 and i == grp[0] else None):
+                if v is not None:
+                    first.setdefault(v.buf.name, t)
+                    last[v.buf.name] = t
+    for k in {low.x0.name} | {b.name for b in low.head_bufs} | {v.buf.name for v in low.feats.values()}:
+        last[k] = len(inst.launch_ops)
+    first[low.x0.name] = -1
+    names = [n for n in rng if n in first]
+    for a in range(len(names)):
+        for b2 in range(a + 1, len(names)):
+            na, nb = names[a], names[b2]
+            if first[na] <= last[nb] and first[nb] <= last[na]:
+                assert not (rng[na][0] < rng[nb][1] and rng[nb][0] < rng[na][1]), (na, first[na], last[na], rng[na], nb, first[nb], last[nb], rng[nb])
+
+
+@pytest.mark.parametrize("name", ["yolov5n", "yolov5m", "yolov5l", "yolov5x", "yolov5n6", "yolov5s_r40"])
+def test_arena_liveness_with_fused_launches_across_the_zoo(monkeypatch, name):
+    """The same invariant for the other topologies and widths (different fusion decisions per model: 16 / 48 / 80-channel
+    levels are never chained, yolov5l's 64-channel level is), small canvas."""
+    import yolort_b200.models as M
+
+    if name == "yolov5s_r40":
+        ctor, kw = M.yolov5s, {"upstream_version": "r4.0"}
+    else:
+        ctor, kw = getattr(M, name), {}
+    low, inst = _cpu_plan(monkeypatch, ctor, 2, 256, 256, **kw)
+    assert sum(len(g) for g in inst.launch_ops) == len(low.L.ops)
+    assert [i for g in inst.launch_ops for i in g] == list(range(len(low.L.ops)))      # every op exactly once, in order
+    _assert_arena_liveness(low, inst)
+    if name == "yolov5l":
+        assert any(len(g) == 2 for g in inst.launch_ops)
+    if name in ("yolov5m", "yolov5x"):
+        assert all(len(g) == 1 for g in inst.launch_ops)
+
+
 def test_fused_launch_list_and_arena_liveness_on_cpu(monkeypatch):
     """Host logic of the plan, without a GPU: which convolutions ride as chained tails (yolov5s: the pointwise chains of
     the 32 / 64-channel C3 blocks), and the arena invariant that makes liveness reuse safe with fused launches -- every

@@ -377,7 +377,7 @@ def lower_yolo(model: nn.Module, dtype: torch.dtype, device: torch.device, stem_
         p6m = pan.intermediate_blocks.p6
         t = _View(L.buf("pan.p6.conv", 64, ch[3]), 0, ch[3])
         L.conv_module("pan.intermediate_blocks.p6.0", p6m[0], top, t)
-        top = _View(L.buf("pan.p6", 64, ch[3]), 0, ch[3])
+        top = _View(L.buf("pan.p6.c3", 64, ch[3]), 0, ch[3])     # (the ascending pass's level-6 result is "pan.p6")
         L.block("pan.intermediate_blocks.p6.1", p6m[1], t, top)
 
     inner, layer = pan.inner_blocks, pan.layer_blocks
